@@ -1,0 +1,84 @@
+"""ctypes mirror of include/awegpu.h (``awegpu_problem_t``) and its construction from an OcpProblem."""
+import ctypes as C
+
+import numpy as np
+
+P_I32 = C.POINTER(C.c_int32)
+P_I64 = C.POINTER(C.c_int64)
+P_F64 = C.POINTER(C.c_double)
+
+AWEGPU_JAC_INSTANCE_MAJOR = 0
+AWEGPU_JAC_BATCH_MINOR = 1
+AWEGPU_P_FULL = 0
+AWEGPU_P_THETA0 = 4
+AWEGPU_P_SHARED = 8
+AWEGPU_SKIP_JAC = 16
+
+
+class ProblemStruct(C.Structure):
+    _fields_ = [
+        ('n_v', C.c_int32), ('n_p', C.c_int32), ('n_g', C.c_int32),
+        ('nnz', C.c_int64),
+        ('n_k', C.c_int32), ('d', C.c_int32),
+        ('n_x', C.c_int32), ('n_u', C.c_int32), ('n_z', C.c_int32), ('n_theta', C.c_int32),
+        ('n_phi', C.c_int32), ('n_theta0', C.c_int32), ('n_var', C.c_int32),
+        ('v_phi', C.c_int32), ('p_theta0', C.c_int32),
+        ('n_coll_out', C.c_int32), ('n_shoot_out', C.c_int32),
+        ('n_shoot_eq', C.c_int32), ('n_ineq', C.c_int32),
+        ('n_const', C.c_int32), ('n_periodic', C.c_int32), ('row_periodic', C.c_int32), ('x_last', C.c_int32),
+        ('x_base', P_I32), ('x_next', P_I32),
+        ('u_base', P_I32), ('xdot_base', P_I32), ('z_base', P_I32),
+        ('cz_base', P_I32), ('theta_idx', P_I32), ('tf_idx', P_I32),
+        ('row_shoot', P_I32), ('row_path', P_I32), ('row_cont', P_I32), ('row_coll', P_I32),
+        ('periodic_idx', P_I32),
+        ('coll_slot', P_I32), ('shoot_slot', P_I32), ('const_slot', P_I32),
+        ('const_val', P_F64), ('const_begin', P_I32),
+        ('coeff_coll', P_F64), ('coeff_cont', P_F64),
+        ('colind', P_I64), ('row', P_I64),
+        ('constraint_scale', C.c_double),
+    ]
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1))
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+
+
+def _i64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64).reshape(-1))
+
+
+def make_problem(ocp):
+    """-> (ProblemStruct, keepalive list of numpy arrays)."""
+    n_k, d = ocp.n_k, ocp.d
+    arrays = {
+        'x_base': _i32([[ocp.x_base(k, r) for r in range(d + 1)] for k in range(n_k)]),
+        'x_next': _i32([ocp.v_x[k + 1] for k in range(n_k)]),
+        'u_base': _i32(ocp.v_u), 'xdot_base': _i32(ocp.v_xdot), 'z_base': _i32(ocp.v_z),
+        'cz_base': _i32(ocp.v_cz), 'theta_idx': _i32(ocp.theta_idx), 'tf_idx': _i32(ocp.tf_idx),
+        'row_shoot': _i32(ocp.row_shoot), 'row_path': _i32(ocp.row_path), 'row_cont': _i32(ocp.row_cont),
+        'row_coll': _i32(ocp.row_coll), 'periodic_idx': _i32(ocp.periodic_idx),
+        'coll_slot': _i32(ocp.coll_slot), 'shoot_slot': _i32(ocp.shoot_slot),
+        'const_slot': _i32(ocp.const_slot), 'const_val': _f64(ocp.const_val),
+        'const_begin': _i32(ocp.const_begin),
+        'coeff_coll': _f64(ocp.coll.coeff_collocation), 'coeff_cont': _f64(ocp.coll.coeff_continuity),
+        'colind': _i64(ocp.colind), 'row': _i64(ocp.row),
+    }
+    ps = ProblemStruct()
+    ps.n_v, ps.n_p, ps.n_g, ps.nnz = ocp.n_v, ocp.n_p, ocp.n_g, ocp.nnz
+    ps.n_k, ps.d = n_k, d
+    ps.n_x, ps.n_u, ps.n_z, ps.n_theta = ocp.n_x, ocp.n_u, ocp.n_z, ocp.n_theta
+    ps.n_phi, ps.n_theta0, ps.n_var = ocp.n_phi, ocp.n_theta0, ocp.n_var
+    ps.v_phi, ps.p_theta0 = ocp.v_phi, ocp.p_theta0
+    ps.n_coll_out, ps.n_shoot_out = len(ocp.coll_out), len(ocp.shoot_out)
+    ps.n_shoot_eq, ps.n_ineq = ocp.n_shoot_eq, ocp.n_ineq
+    ps.n_const, ps.n_periodic = len(ocp.const_slot), len(ocp.periodic_idx)
+    ps.row_periodic, ps.x_last = ocp.row_periodic, ocp.v_cx[n_k - 1][d - 1]
+    ps.constraint_scale = ocp.constraint_scale
+    for name, arr in arrays.items():
+        ctype = dict(ProblemStruct._fields_)[name]
+        setattr(ps, name, arr.ctypes.data_as(ctype))
+    return ps, arrays

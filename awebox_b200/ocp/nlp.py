@@ -1,0 +1,335 @@
+"""OCP assembly: layout of the decision vector ``w = V.cat`` and parameter vector ``p = P.cat``, row
+order of ``g``, structural CCS pattern of ``jac_g`` and the scatter tables that take node-local
+Jacobian entries to CCS slots.
+
+Follows (direct collocation, Radau/Legendre, zero-order-hold controls):
+  awebox/ocp/var_struct.py:39-110           V = [theta, phi, xi, (x[nk+1], u[nk], xdot[nk], z[nk], coll_var[nk,d]{x,z})]
+  awebox/ocp/discretization.py:129-179      P = [p{ref(|V|), weights(|vars|)}, cost(20), theta0]
+  awebox/tools/struct_operations.py:69-116, 230-302, 363-471   node gathers, t_f selection
+  awebox/ocp/collocation.py:202-258, 319-336                    xdot from the polynomial, continuity
+  awebox/ocp/constraints.py:210-373         rows: per k  shooting(eq) path(ineq) {collocation}_d continuity
+  awebox/ocp/operation.py:245-267           periodicity rows  x(0) - x(coll nk-1, d-1)
+  awebox/ocp/constraints.py:147-168         t_f bound rows (single_reelout)
+"""
+import numpy as np
+
+from .. import sym as S
+from ..mdl.model import NodeModel, VAR_TYPES
+from .collocation import Collocation
+
+N_COST = 20          # entries of the cost struct, awebox/ocp/discretization.py:129-154
+
+
+class OcpProblem(object):
+    def __init__(self, spec, node_model=None, n_k=None):
+        self.spec = spec
+        self.model = node_model if node_model is not None else NodeModel(spec)
+        m = self.model
+        nlp = spec.nlp
+        if nlp.get('discretization', 'direct_collocation') != 'direct_collocation':
+            raise NotImplementedError('only direct collocation is supported')
+        if nlp.get('collocation.u_param', 'zoh') != 'zoh':
+            raise NotImplementedError("only u_param='zoh' is supported")
+        self.n_k = int(nlp['n_k'] if n_k is None else n_k)
+        self.d = int(nlp['collocation.d'])
+        self.coll = Collocation(self.n_k, self.d, nlp.get('collocation.scheme', 'radau'))
+        self.phase_fix = nlp.get('phase_fix', 'simple')
+        self.single_reelout = (self.phase_fix == 'single_reelout')
+        self.constraint_scale = float(nlp.get('constraint_scale', 1.0))
+        self.n_x, self.n_u, self.n_z, self.n_theta = m.n_x, m.n_u, m.n_z, m.n_theta
+        self.n_var, self.n_phi, self.n_theta0 = m.n_var, len(spec.phi_names), m.n_theta0
+        self._layout()
+        self._local_patterns()
+        self._rows()
+        self._pattern()
+
+    # ------------------------------------------------------------------ V / P layout
+    def _layout(self):
+        m, n_k, d = self.model, self.n_k, self.d
+        off = 0
+        self.theta_names = m.names('theta')
+        self.v_theta = {}
+        for nm in self.theta_names:
+            sz = 2 if (nm == 't_f' and self.single_reelout) else 1
+            self.v_theta[nm] = (off, sz)
+            off += sz
+        self.n_v_theta = off
+        self.v_phi = off
+        off += self.n_phi
+        self.v_xi = off
+        off += 2
+        self.v_x, self.v_u, self.v_xdot, self.v_z = [], [], [], []
+        self.v_cx = [[None] * d for _ in range(n_k)]
+        self.v_cz = [[None] * d for _ in range(n_k)]
+        for k in range(n_k + 1):
+            self.v_x.append(off)
+            off += self.n_x
+            if k < n_k:
+                self.v_u.append(off)
+                off += self.n_u
+                self.v_xdot.append(off)
+                off += self.n_x
+                self.v_z.append(off)
+                off += self.n_z
+                for j in range(d):
+                    self.v_cx[k][j] = off
+                    off += self.n_x
+                    self.v_cz[k][j] = off
+                    off += self.n_z
+        self.n_v = off
+        self.p_theta0 = self.n_v + self.n_var + N_COST
+        self.n_p = self.p_theta0 + self.n_theta0
+        # theta gather per interval (get_V_theta / calculate_tf)
+        switch = int(round(n_k * float(self.spec.nlp.get('phase_fix_reelout', 0.7))))
+        self.theta_idx = np.zeros((n_k, self.n_theta), dtype=np.int32)
+        self.tf_idx = np.zeros(n_k, dtype=np.int32)
+        for k in range(n_k):
+            for t, nm in enumerate(self.theta_names):
+                o, sz = self.v_theta[nm]
+                self.theta_idx[k, t] = o + (1 if (sz == 2 and k >= switch) else 0)
+            self.tf_idx[k] = self.theta_idx[k, self.theta_names.index('t_f')]
+        self.tf_local = m.offset[('theta', 't_f')][0]      # position of t_f in the node input column
+
+    def default_p(self):
+        p = np.zeros(self.n_p)
+        p[self.p_theta0:] = self.spec.theta0_values
+        return p
+
+    def x_base(self, k, r):
+        """V offset of the state block X_r of interval k (r=0: x_k, r>=1: coll_var[k, r-1].x)."""
+        return self.v_x[k] if r == 0 else self.v_cx[k][r - 1]
+
+    # ------------------------------------------------------------------ node-local patterns
+    def _local_patterns(self):
+        m = self.model
+        self.local_in = np.concatenate([m.vars, m.params[m.n_theta0:]])     # 59 vars + phi
+        self.n_local = len(self.local_in)
+        eq, ineq = m.eq_exprs(), m.ineq_exprs()
+        self.n_eq, self.n_ineq = len(eq), len(ineq)
+        self.dep_eq = S.dependency(eq, self.local_in)
+        self.dep_ineq = S.dependency(ineq, self.local_in)
+        # rows of the shooting-node equality subset (constraints.py:170-207): rows whose structural
+        # Jacobian w.r.t. every non-x variable is empty are not enforced at the shooting nodes
+        n_x = self.n_x
+        self.shoot_eq_rows = [i for i, dcols in enumerate(self.dep_eq) if any((c >= n_x and c < self.n_var) for c in dcols)]
+        o = m.offset
+        self.rng = {}
+        k = 0
+        for vt in VAR_TYPES:
+            sz = sum(s for _, s in m.var_list[vt])
+            self.rng[vt] = (k, k + sz)
+            k += sz
+        self.rng['phi'] = (k, k + self.n_phi)
+
+    def _split(self, cols):
+        out = {key: [] for key in ('x', 'xdot', 'u', 'z', 'theta', 'phi')}
+        for c in cols:
+            for key, (a, b) in self.rng.items():
+                if a <= c < b:
+                    out[key].append(c - a)
+        return out
+
+    # ------------------------------------------------------------------ g rows
+    def _rows(self):
+        n_k, d = self.n_k, self.d
+        self.n_shoot_eq = len(self.shoot_eq_rows)
+        r = 0
+        self.row_shoot, self.row_path, self.row_coll, self.row_cont = [], [], [], []
+        for k in range(n_k):
+            self.row_shoot.append(r)
+            r += self.n_shoot_eq
+            self.row_path.append(r)
+            r += self.n_ineq
+            self.row_coll.append([])
+            for j in range(d):
+                self.row_coll[k].append(r)
+                r += self.n_eq
+            self.row_cont.append(r)
+            r += self.n_x
+        # periodicity: every non-integral state, names sorted (operation.py:245-267)
+        m = self.model
+        self.periodic_idx = []
+        for nm in m.sorted_names('x'):
+            if nm in ('e',):
+                continue
+            o, sz = m.offset[('x', nm)]
+            self.periodic_idx += list(range(o, o + sz))
+        self.row_periodic = r
+        r += len(self.periodic_idx)
+        self.row_tf_bounds = None
+        if self.single_reelout:
+            self.row_tf_bounds = r
+            r += 2
+        self.n_g = r
+
+    # ------------------------------------------------------------------ jac_g pattern + scatter tables
+    def _pattern(self):
+        n_k, d = self.n_k, self.d
+        C, D = self.coll.coeff_collocation, self.coll.coeff_continuity
+        ent_r, ent_c = [], []          # every structural entry once
+
+        def add(r, c):
+            ent_r.append(r)
+            ent_c.append(c)
+
+        # ---- collocation-node local output list (same for every (k, j)); see codegen
+        #   ('res', i) | ('X', i, m, r) | ('u', i, c) | ('z', i, c) | ('theta', i, t) | ('phi', i, c)
+        eq_split = [self._split(cols) for cols in self.dep_eq]
+        self.coll_out = []
+        for i in range(self.n_eq):
+            self.coll_out.append(('res', i))
+        for t in range(self.n_theta):
+            for i in range(self.n_eq):
+                direct = t in eq_split[i]['theta']
+                via_tf = (t == self.tf_local - self.rng['theta'][0]) and len(eq_split[i]['xdot']) > 0
+                if direct or via_tf:
+                    self.coll_out.append(('theta', i, t))
+        for c in range(self.n_phi):
+            for i in range(self.n_eq):
+                if c in eq_split[i]['phi']:
+                    self.coll_out.append(('phi', i, c))
+        #   ('Xc', i, m, r): d r_i/d X_r[m] through xdot (plus the direct part when r is the node's own
+        #   block and (i, m) is also a direct dependency);  ('Xo', i, m): direct-only dependency
+        for r in range(d + 1):
+            for mm in range(self.n_x):
+                for i in range(self.n_eq):
+                    if mm in eq_split[i]['xdot']:
+                        self.coll_out.append(('Xc', i, mm, r))
+            if r == 0:
+                for mm in range(self.n_x):
+                    for i in range(self.n_eq):
+                        if mm in eq_split[i]['x'] and mm not in eq_split[i]['xdot']:
+                            self.coll_out.append(('Xo', i, mm))
+            if r == 0:
+                for c in range(self.n_u):
+                    for i in range(self.n_eq):
+                        if c in eq_split[i]['u']:
+                            self.coll_out.append(('u', i, c))
+        for c in range(self.n_z):
+            for i in range(self.n_eq):
+                if c in eq_split[i]['z']:
+                    self.coll_out.append(('z', i, c))
+        self.eq_split = eq_split
+
+        # ---- shooting-node local outputs: residual rows then direct entries
+        sh_rows = [('eq', i) for i in self.shoot_eq_rows] + [('ineq', i) for i in range(self.n_ineq)]
+        self.shoot_rows = sh_rows
+        self.shoot_out = [('res', n) for n in range(len(sh_rows))]
+        sh_dep = [self.dep_eq[i] if kind == 'eq' else self.dep_ineq[i] for kind, i in sh_rows]
+        self.shoot_dep = sh_dep
+        for c in range(self.n_local):
+            for n, cols in enumerate(sh_dep):
+                if c in cols:
+                    self.shoot_out.append(('jac', n, c))
+
+        # ---- global entries
+        coll_keys = np.full((n_k, d, len(self.coll_out), 2), -1, dtype=np.int64)
+        shoot_keys = np.full((n_k, len(self.shoot_out), 2), -1, dtype=np.int64)
+        for k in range(n_k):
+            # shooting node k
+            xb, ub, xdb, zb = self.v_x[k], self.v_u[k], self.v_xdot[k], self.v_z[k]
+            for n, item in enumerate(self.shoot_out):
+                if item[0] != 'jac':
+                    continue
+                _, rr, c = item
+                row = (self.row_shoot[k] + rr) if rr < self.n_shoot_eq else (self.row_path[k] + rr - self.n_shoot_eq)
+                col = self._local_to_v(c, k, xb, xdb, ub, zb)
+                shoot_keys[k, n] = (row, col)
+                add(row, col)
+            for j in range(d):
+                row0 = self.row_coll[k][j]
+                for n, item in enumerate(self.coll_out):
+                    kind = item[0]
+                    if kind == 'res':
+                        continue
+                    i = item[1]
+                    row = row0 + i
+                    if kind == 'theta':
+                        col = int(self.theta_idx[k, item[2]])
+                    elif kind == 'phi':
+                        col = self.v_phi + item[2]
+                    elif kind == 'u':
+                        col = self.v_u[k] + item[2]
+                    elif kind == 'z':
+                        col = self.v_cz[k][j] + item[2]
+                    elif kind == 'Xo':
+                        col = self.x_base(k, j + 1) + item[2]
+                    else:
+                        _, _, mm, r = item
+                        has_b = C[r, j + 1] != 0.0
+                        has_a = (mm in self.eq_split[i]['x']) and (r == j + 1)
+                        if not (has_a or has_b):
+                            continue
+                        col = self.x_base(k, r) + mm
+                    coll_keys[k, j, n] = (row, col)
+                    add(row, col)
+        # ---- constant entries: continuity, periodicity, t_f bounds
+        const_r, const_c, const_v = [], [], []
+        const_begin = []
+        for k in range(n_k):
+            const_begin.append(len(const_r))
+            for mm in range(self.n_x):
+                row = self.row_cont[k] + mm
+                const_r.append(row), const_c.append(self.v_x[k + 1] + mm), const_v.append(1.0)
+                for r in range(d + 1):
+                    if D[r] != 0.0:
+                        const_r.append(row), const_c.append(self.x_base(k, r) + mm), const_v.append(-D[r])
+        last = self.v_cx[n_k - 1][d - 1]
+        for n, mm in enumerate(self.periodic_idx):
+            row = self.row_periodic + n
+            const_r.append(row), const_c.append(self.v_x[0] + mm), const_v.append(1.0)
+            const_r.append(row), const_c.append(last + mm), const_v.append(-1.0)
+        if self.single_reelout:
+            raise NotImplementedError('t_f bound rows of single_reelout are assembled in tf_bounds()')
+        const_begin.append(len(const_r))       # periodicity entries belong to the last interval
+        self.const_begin = np.array(const_begin, dtype=np.int32)
+        for r_, c_ in zip(const_r, const_c):
+            add(r_, c_)
+
+        ent_r = np.array(ent_r, dtype=np.int64)
+        ent_c = np.array(ent_c, dtype=np.int64)
+        key = ent_c * self.n_g + ent_r
+        ukey = np.unique(key)
+        if len(ukey) != len(key):
+            raise AssertionError('duplicate structural entries in jac_g assembly')
+        self.nnz = len(ukey)
+        self.row = (ukey % self.n_g).astype(np.int64)
+        cols = (ukey // self.n_g).astype(np.int64)
+        self.colind = np.zeros(self.n_v + 1, dtype=np.int64)
+        np.add.at(self.colind, cols + 1, 1)
+        self.colind = np.cumsum(self.colind)
+
+        def slots(keys):
+            flat = keys.reshape(-1, 2)
+            out = np.full(flat.shape[0], -1, dtype=np.int32)
+            ok = flat[:, 0] >= 0
+            kk = flat[ok, 1] * self.n_g + flat[ok, 0]
+            out[ok] = np.searchsorted(ukey, kk).astype(np.int32)
+            return out.reshape(keys.shape[:-1])
+
+        self.coll_slot = slots(coll_keys)            # [n_k, d, n_coll_out]   (-1: not an entry)
+        self.shoot_slot = slots(shoot_keys)          # [n_k, n_shoot_out]
+        ck = np.stack([np.array(const_r, dtype=np.int64), np.array(const_c, dtype=np.int64)], axis=1)
+        self.const_slot = slots(ck)
+        self.const_val = np.array(const_v, dtype=float) * self.constraint_scale
+
+    def _local_to_v(self, c, k, xb, xdb, ub, zb):
+        for key, (a, b) in self.rng.items():
+            if a <= c < b:
+                if key == 'x':
+                    return xb + (c - a)
+                if key == 'xdot':
+                    return xdb + (c - a)
+                if key == 'u':
+                    return ub + (c - a)
+                if key == 'z':
+                    return zb + (c - a)
+                if key == 'theta':
+                    return int(self.theta_idx[k, c - a])
+                return self.v_phi + (c - a)
+        raise IndexError(c)
+
+    # ------------------------------------------------------------------ summaries
+    def algorithmic_bytes(self):
+        """compulsory HBM traffic per OCP instance and call: every datum once."""
+        return 8 * (self.n_v + self.n_theta0 + self.n_g + self.nnz)

@@ -1,0 +1,129 @@
+/* awegpu.h — C ABI of the B200 evaluator for awebox's collocation constraint residual g(w,p) and
+ * its sparse Jacobian.
+ *
+ * Two groups of entry points:
+ *
+ * (1) the batched ABI (plain pointers and sizes; what a ctypes / cgo / JNI stub binds).  It replaces
+ *     the numeric evaluation of the reference's ``NLP.g_fun`` (awebox/ocp/nlp.py:119-121, 270-272)
+ *     and of the ``jac_g`` that CasADi derives from it inside ``cas.nlpsol``
+ *     (awebox/opti/preparation.py:366-380, 395), for B independent OCP instances per call.
+ *
+ * (2) the CasADi "external function" ABI (``casadi.external(name, lib)`` loads a shared library
+ *     that exports ``<name>``, ``<name>_n_in``, ``<name>_sparsity_in`` ...; casadi/core/external.cpp,
+ *     the same symbols ``Function.generate`` emits).  ``awegpu_g`` is g(V,P); ``jac_awegpu_g`` is the
+ *     Jacobian function with CasADi 3.6 conventions (inputs V, P, out_g; outputs jac_g_V [sparse CCS],
+ *     jac_g_P [structurally empty]).  They are bound to a handle with ``awegpu_casadi_bind``.
+ *
+ * All matrices are FP64; index arrays are int64 (``casadi_int``) on the ABI, int32 inside.
+ * Return value 0 = ok, non-zero = failure (message via awegpu_last_error).  A handle owns one CUDA
+ * stream and is not re-entrant.  There is NO CPU fallback: every entry point fails when no CUDA
+ * device is usable.
+ */
+#ifndef AWEGPU_H
+#define AWEGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Discretised-OCP description produced by awebox_b200/ocp/nlp.py (host side, build time).  Layout
+ * follows awebox/ocp/var_struct.py:39-97 (V), awebox/ocp/discretization.py:157-179 (P) and
+ * awebox/ocp/constraints.py:282-352 (rows of g).  All table pointers are host pointers; create()
+ * copies them to the device. */
+typedef struct awegpu_problem {
+    int32_t n_v, n_p, n_g;          /* |V|, |P|, |g| */
+    int64_t nnz;                    /* nnz of jac_g (w.r.t. V) */
+    int32_t n_k, d;                 /* intervals, collocation order */
+    int32_t n_x, n_u, n_z, n_theta, n_phi, n_theta0, n_var;
+    int32_t v_phi;                  /* offset of phi in V */
+    int32_t p_theta0;               /* offset of theta0 in P */
+    int32_t n_coll_out, n_shoot_out;/* node-local output counts (must match the compiled model) */
+    int32_t n_shoot_eq, n_ineq;
+    int32_t n_const;                /* constant Jacobian entries (continuity, periodicity) */
+    int32_t n_periodic;
+    int32_t row_periodic;           /* first periodicity row */
+    int32_t x_last;                 /* V offset of coll_var[n_k-1, d-1].x */
+    const int32_t *x_base;          /* [n_k*(d+1)]  V offset of X_r of interval k */
+    const int32_t *x_next;          /* [n_k]        V offset of x_{k+1} */
+    const int32_t *u_base, *xdot_base, *z_base;   /* [n_k] */
+    const int32_t *cz_base;         /* [n_k*d]      V offset of coll_var[k,j].z */
+    const int32_t *theta_idx;       /* [n_k*n_theta] V index of every theta entry seen by interval k */
+    const int32_t *tf_idx;          /* [n_k]        V index of the t_f used by interval k */
+    const int32_t *row_shoot, *row_path, *row_cont;   /* [n_k] */
+    const int32_t *row_coll;        /* [n_k*d] */
+    const int32_t *periodic_idx;    /* [n_periodic] state components tied by periodicity */
+    const int32_t *coll_slot;       /* [n_k*d*n_coll_out]  CCS slot of every local output, -1 = none */
+    const int32_t *shoot_slot;      /* [n_k*n_shoot_out] */
+    const int32_t *const_slot;      /* [n_const] */
+    const double  *const_val;       /* [n_const] */
+    const int32_t *const_begin;     /* [n_k+1] range of constant entries written by interval k */
+    const double  *coeff_coll;      /* [(d+1)*(d+1)]  C[r*(d+1)+j] = l_r'(tau_j) */
+    const double  *coeff_cont;      /* [d+1]          l_r(1) */
+    const int64_t *colind;          /* [n_v+1] */
+    const int64_t *row;             /* [nnz] */
+    double constraint_scale;
+} awegpu_problem_t;
+
+typedef struct awegpu_handle awegpu_handle_t;
+
+/* flags of awegpu_eval_batch */
+#define AWEGPU_JAC_INSTANCE_MAJOR 0   /* Jv[b*nnz + slot]   (what CasADi consumes per instance) */
+#define AWEGPU_JAC_BATCH_MINOR    1   /* Jv[slot*B + b]     (for batched on-device consumers)   */
+#define AWEGPU_P_FULL             0   /* P holds full parameter vectors, leading dimension n_p  */
+#define AWEGPU_P_THETA0           4   /* P holds theta0 only, leading dimension n_theta0        */
+#define AWEGPU_P_SHARED           8   /* one parameter vector shared by all instances           */
+#define AWEGPU_SKIP_JAC          16   /* residual only                                          */
+
+const char *awegpu_model_name(void);             /* spec the node functions were generated from */
+int awegpu_model_dims(int32_t *n_var, int32_t *n_param, int32_t *n_coll_out, int32_t *n_shoot_out,
+                      int64_t *flops_coll, int64_t *flops_shoot);
+
+int  awegpu_create(const awegpu_problem_t *problem, int device, awegpu_handle_t **out);
+void awegpu_destroy(awegpu_handle_t *h);
+const char *awegpu_last_error(awegpu_handle_t *h);   /* h may be NULL: last create() error */
+
+int awegpu_sparsity(awegpu_handle_t *h, int64_t *colind /*[n_v+1]*/, int64_t *row /*[nnz]*/);
+
+/* Device-pointer entry: W [B,n_v], P (see flags), G [B,n_g], Jv [B*nnz] are device pointers.
+ * stream: a cudaStream_t (NULL = the handle's own stream).  Asynchronous w.r.t. the host. */
+int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W, const double *P,
+                      double *G, double *Jv, int32_t flags, void *stream);
+
+/* Host-pointer entry: copies inputs host->device and results device->host through pinned staging
+ * buffers owned by the handle (grown on demand), synchronises before returning. */
+int awegpu_eval_batch_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P,
+                           double *G, double *Jv, int32_t flags);
+
+/* device time of the most recent eval (ms, CUDA events on the launching stream); <0 if none */
+float awegpu_last_eval_ms(awegpu_handle_t *h);
+/* number of kernel launches issued by this handle so far */
+int64_t awegpu_launch_count(awegpu_handle_t *h);
+int awegpu_synchronize(awegpu_handle_t *h);
+
+/* ---- CasADi external-function ABI (casadi_real = double, casadi_int = long long) ---- */
+int awegpu_casadi_bind(awegpu_handle_t *h);      /* handle used by awegpu_g / jac_awegpu_g */
+
+int awegpu_g(const double **arg, double **res, long long *iw, double *w, int mem);
+long long awegpu_g_n_in(void);
+long long awegpu_g_n_out(void);
+const char *awegpu_g_name_in(long long i);
+const char *awegpu_g_name_out(long long i);
+const long long *awegpu_g_sparsity_in(long long i);
+const long long *awegpu_g_sparsity_out(long long i);
+int awegpu_g_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w);
+
+int jac_awegpu_g(const double **arg, double **res, long long *iw, double *w, int mem);
+long long jac_awegpu_g_n_in(void);
+long long jac_awegpu_g_n_out(void);
+const char *jac_awegpu_g_name_in(long long i);
+const char *jac_awegpu_g_name_out(long long i);
+const long long *jac_awegpu_g_sparsity_in(long long i);
+const long long *jac_awegpu_g_sparsity_out(long long i);
+int jac_awegpu_g_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AWEGPU_H */

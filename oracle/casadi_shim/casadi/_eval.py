@@ -97,23 +97,25 @@ class Tape(object):
             rows.append(cols)
         return rows
 
-    def jac_ccs(self):
-        """CCS (colind,row) of d out / d in from the structural pattern."""
+    def jac_ccs(self, n_cols=None):
+        """CCS (colind,row) of d out / d in[:n_cols] from the structural pattern."""
+        n_cols = self.n_in if n_cols is None else n_cols
         rows = self.pattern()
-        cols = [[] for _ in range(self.n_in)]
+        cols = [[] for _ in range(n_cols)]
         for i, cs in enumerate(rows):
             for j in cs:
-                cols[j].append(i)
+                if j < n_cols:
+                    cols[j].append(i)
         colind = [0]
         row = []
-        for j in range(self.n_in):
+        for j in range(n_cols):
             row.extend(cols[j])
             colind.append(len(row))
         return np.array(colind, dtype=np.int64), np.array(row, dtype=np.int64)
 
     def colouring(self, colind, row):
         """greedy unidirectional (distance-2) column colouring."""
-        n = self.n_in
+        n = len(colind) - 1
         row_cols = {}
         for j in range(n):
             for r in row[colind[j]:colind[j + 1]]:
@@ -142,11 +144,15 @@ class Tape(object):
         w = [None] * self.n_work
         dw = [None] * self.n_work
         zero = np.zeros(nc)
+        n_cols = len(colind) - 1
         for j in range(self.n_in):
             w[j] = x[j]
-            s = np.zeros(nc)
-            s[colour[j]] = 1.0
-            dw[j] = s
+            if j < n_cols:
+                s = np.zeros(nc)
+                s[colour[j]] = 1.0
+                dw[j] = s
+            else:
+                dw[j] = None
         for k, v in self.consts:
             w[k] = v
             dw[k] = None
@@ -178,7 +184,7 @@ class Tape(object):
                             dw[k] = pa * da + pb * db
         vals = np.zeros(len(row))
         outs = [dw[s] for s in self.out_slots]
-        for j in range(self.n_in):
+        for j in range(n_cols):
             c = colour[j]
             for p in range(colind[j], colind[j + 1]):
                 d = outs[int(row[p])]

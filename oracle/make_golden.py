@@ -1,0 +1,96 @@
+"""Generate the model specs and the golden vectors by running the REFERENCE here.  TEST INFRASTRUCTURE.
+
+    python oracle/make_golden.py [config ...]
+
+For every configuration (oracle/ref_build.py) this script imports the reference's own Python from
+/root/reference over the CasADi restatement (oracle/casadi_shim), builds the reference's model and
+NLP, takes the reference's own initial guess as base point and writes
+
+  awebox_b200/specs/<config>.json     numeric ModelSpec read off the reference's Options / Model
+  tests/golden/<config>_nk<N>.npz     w [n, n_v], p [n_p], g [n, n_g] = NLP.g_fun(w, p),
+                                      colind/row = structural CCS pattern of d g / d V,
+                                      jv [n, nnz] = its values (compressed forward sweeps),
+                                      node_vars/node_eq/node_ineq = Model.dynamics / inequality
+                                      function values at random node inputs, and the V / g labels' hash
+
+These files are what the oracle (oracle/awebox_oracle.c) and the CUDA path are pinned against.  The
+script cannot run on the GPU box (no /root/reference there); its outputs are committed.
+"""
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_build                                   # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+JOBS = {
+    # config: [(n_k, number of points with Jacobian)]
+    'ampyx_ap2': [(4, 3), (40, 2)],
+    'dual_kites': [(3, 2), (20, 1)],
+}
+
+
+def perturbed_points(w0, n, seed):
+    rng = np.random.default_rng(seed)
+    pts = [w0]
+    for _ in range(n - 1):
+        pts.append(w0 * (1.0 + 1e-2 * rng.uniform(-1.0, 1.0, w0.shape)))
+    return np.array(pts)
+
+
+def run(config, n_k, n_pts, write_spec):
+    from awebox_b200 import spec as bspec
+    t0 = time.time()
+    T = ref_build.build(config, n_k=n_k)
+    import casadi as cas            # the restatement under oracle/casadi_shim (activated by ref_build)
+    theta0 = np.array(T.p_fix_num['theta0'].full()).ravel()
+    sp = bspec.from_awebox(config, T.options, T.architecture, T.model, theta0_values=theta0)
+    if write_spec:
+        os.makedirs(bspec.SPEC_DIR, exist_ok=True)
+        sp.to_json(os.path.join(bspec.SPEC_DIR, config + '.json'))
+    n_v = T.nlp.V.cat.shape[0]
+    W = perturbed_points(T.w0, n_pts, 20261018 + n_k)
+    p = T.p0
+    G = []
+    for w in W:
+        G.append(np.array(T.nlp.g_fun(cas.DM(w), cas.DM(p)).full()).ravel())
+    tape = T.nlp.g_fun._tape
+    colind, row = tape.jac_ccs(n_v)
+    JV = [tape.jac_values(np.concatenate([w, p]), colind, row) for w in W]
+    # node-level vectors
+    M = T.model
+    mdl_eq = M.constraints_list.get_function(T.options['nlp'], M.variables, M.parameters, 'eq')
+    mdl_ineq = M.constraints_list.get_function(T.options['nlp'], M.variables, M.parameters, 'ineq')
+    rng = np.random.default_rng(7 + n_k)
+    n_var = M.variables.cat.shape[0]
+    node_vars = rng.uniform(0.5, 1.5, (8, n_var))
+    node_p = np.concatenate([theta0, np.ones(M.parameters.cat.shape[0] - len(theta0))])
+    node_eq = np.array([np.array(mdl_eq(cas.DM(v), cas.DM(node_p)).full()).ravel() for v in node_vars])
+    node_ineq = np.array([np.array(mdl_ineq(cas.DM(v), cas.DM(node_p)).full()).ravel() for v in node_vars])
+    labels = '\n'.join(T.nlp.V.labels()) + '\n--\n' + '\n'.join(T.nlp.g.labels())
+    os.makedirs(GOLDEN, exist_ok=True)
+    out = os.path.join(GOLDEN, '%s_nk%d.npz' % (config, n_k))
+    np.savez_compressed(out, w=W, p=p, g=np.array(G), colind=colind, row=row, jv=np.array(JV),
+                        node_vars=node_vars, node_p=node_p, node_eq=node_eq, node_ineq=node_ineq,
+                        eq_names=np.array(M.constraints_list.get_name_list('eq')),
+                        ineq_names=np.array(M.constraints_list.get_name_list('ineq')),
+                        var_labels=np.array(M.variables.labels()),
+                        labels_sha256=np.array(hashlib.sha256(labels.encode()).hexdigest()))
+    print('%s n_k=%d: n_v=%d n_g=%d nnz=%d  %d points  (%.1f s)  -> %s'
+          % (config, n_k, n_v, len(G[0]), len(row), n_pts, time.time() - t0, os.path.relpath(out, ROOT)))
+
+
+if __name__ == '__main__':
+    import logging
+    logging.disable(logging.CRITICAL)
+    for config in (sys.argv[1:] or list(JOBS)):
+        for i, (n_k, n_pts) in enumerate(JOBS[config]):
+            run(config, n_k, n_pts, write_spec=(i == len(JOBS[config]) - 1))
