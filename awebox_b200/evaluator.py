@@ -1,0 +1,175 @@
+"""Host-side mirror of the reference interface for the hot path.
+
+``Evaluator`` plays the role of the reference's ``NLP.g_fun`` (a ``casadi.Function`` named
+'cstr_fun' with inputs ``(V, P)`` and one output ``g``; awebox/ocp/nlp.py:119-121, 270-272) and of the
+``jac_g`` function CasADi derives from it for IPOPT (awebox/opti/preparation.py:379): same argument
+meaning and order, same row / CCS ordering, evaluated for a whole batch of instances per call on the
+GPU through the C ABI (include/awegpu.h).  There is no CPU fallback: construction raises when the
+compiled CUDA library is missing or no CUDA device is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import cabi
+from .build import lib_path
+from .ocp.nlp import OcpProblem
+from .spec import ModelSpec
+
+
+class AwegpuError(RuntimeError):
+    pass
+
+
+def load_library(spec_name):
+    path = lib_path(spec_name)
+    if not os.path.exists(path):
+        raise AwegpuError('CUDA library %s is missing: run `python -m awebox_b200.build %s` '
+                          '(there is no CPU fallback)' % (path, spec_name))
+    lib = C.CDLL(path)
+    lib.awegpu_model_name.restype = C.c_char_p
+    lib.awegpu_last_error.restype = C.c_char_p
+    lib.awegpu_last_error.argtypes = [C.c_void_p]
+    lib.awegpu_create.restype = C.c_int
+    lib.awegpu_create.argtypes = [C.POINTER(cabi.ProblemStruct), C.c_int, C.POINTER(C.c_void_p)]
+    lib.awegpu_destroy.argtypes = [C.c_void_p]
+    lib.awegpu_destroy.restype = None
+    lib.awegpu_sparsity.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.awegpu_eval_batch.restype = C.c_int
+    lib.awegpu_eval_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int32, C.c_void_p]
+    lib.awegpu_eval_batch_host.restype = C.c_int
+    lib.awegpu_eval_batch_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int32]
+    lib.awegpu_last_eval_ms.restype = C.c_float
+    lib.awegpu_last_eval_ms.argtypes = [C.c_void_p]
+    lib.awegpu_launch_count.restype = C.c_int64
+    lib.awegpu_launch_count.argtypes = [C.c_void_p]
+    lib.awegpu_synchronize.argtypes = [C.c_void_p]
+    lib.awegpu_casadi_bind.argtypes = [C.c_void_p]
+    lib.awegpu_model_dims.argtypes = [C.POINTER(C.c_int32)] * 4 + [C.POINTER(C.c_int64)] * 2
+    if lib.awegpu_model_name().decode() != spec_name:
+        raise AwegpuError('library %s was generated for model %r' % (path, lib.awegpu_model_name().decode()))
+    return lib
+
+
+class Evaluator(object):
+    def __init__(self, spec, n_k=None, device=0, ocp=None):
+        if isinstance(spec, str):
+            spec = ModelSpec.load(spec)
+        self.spec = spec
+        self.ocp = ocp if ocp is not None else OcpProblem(spec, n_k=n_k)
+        self.lib = load_library(spec.name)
+        self.problem, self._keep = cabi.make_problem(self.ocp)
+        self.handle = C.c_void_p()
+        rc = self.lib.awegpu_create(C.byref(self.problem), int(device), C.byref(self.handle))
+        if rc != 0:
+            raise AwegpuError('awegpu_create failed (%d): %s' % (rc, self.lib.awegpu_last_error(None).decode()))
+        self.device = int(device)
+        self.n_v, self.n_p, self.n_g, self.nnz = self.ocp.n_v, self.ocp.n_p, self.ocp.n_g, self.ocp.nnz
+        self.n_theta0 = self.ocp.n_theta0
+        fl = (C.c_int64 * 2)()
+        self.lib.awegpu_model_dims(None, None, None, None, C.byref(fl, 0), C.byref(fl, 8))
+        self.flops_coll, self.flops_shoot = int(fl[0]), int(fl[1])
+
+    def close(self):
+        if getattr(self, 'handle', None) and self.handle.value:
+            self.lib.awegpu_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise AwegpuError('%s failed (%d): %s' % (what, rc, self.lib.awegpu_last_error(self.handle).decode()))
+
+    # ---- structure (bit-exact integer data)
+    def sparsity(self):
+        """CCS pattern of jac_g w.r.t. V as (colind [n_v+1], row [nnz]) int64 — casadi_int."""
+        colind = np.empty(self.n_v + 1, dtype=np.int64)
+        row = np.empty(self.nnz, dtype=np.int64)
+        self.lib.awegpu_sparsity(self.handle, colind.ctypes.data, row.ctypes.data)
+        return colind, row
+
+    @staticmethod
+    def p_flags(P, n_p, n_theta0, B):
+        P = np.asarray(P)
+        flags = 0
+        if P.shape[-1] == n_theta0:
+            flags |= cabi.AWEGPU_P_THETA0
+        elif P.shape[-1] != n_p:
+            raise ValueError('P has %d columns; expected n_p=%d or n_theta0=%d' % (P.shape[-1], n_p, n_theta0))
+        if P.ndim == 1 or P.shape[0] == 1:
+            flags |= cabi.AWEGPU_P_SHARED
+        elif P.shape[0] != B:
+            raise ValueError('P has %d rows for a batch of %d' % (P.shape[0], B))
+        return flags
+
+    # ---- host entry: numpy in, numpy out (H2D / D2H inside the call)
+    def eval(self, W, P, jac=True, batch_minor=False):
+        """g and jac_g values for a batch.  W [B, n_v] (or [n_v]); P [B, n_p] | [n_p] | [B, n_theta0] |
+        [n_theta0].  Returns (G [B, n_g], Jv [B, nnz]) — Jv in CCS order of ``sparsity()``
+        (``[nnz, B]`` / ``[n_g, B]`` when batch_minor)."""
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        if W.ndim == 1:
+            W = W[None, :]
+        if W.shape[1] != self.n_v:
+            raise ValueError('W has %d columns, expected n_v=%d' % (W.shape[1], self.n_v))
+        B = W.shape[0]
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        if batch_minor:
+            flags |= cabi.AWEGPU_JAC_BATCH_MINOR
+        if not jac:
+            flags |= cabi.AWEGPU_SKIP_JAC
+        G = np.empty((self.n_g, B) if batch_minor else (B, self.n_g))
+        Jv = (np.empty((self.nnz, B) if batch_minor else (B, self.nnz))) if jac else None
+        rc = self.lib.awegpu_eval_batch_host(self.handle, B, W.ctypes.data, P.ctypes.data, G.ctypes.data,
+                                             Jv.ctypes.data if jac else None, flags)
+        self._check(rc, 'awegpu_eval_batch_host')
+        return G, Jv
+
+    # ---- device entry: torch CUDA tensors (device memory stays with the caller)
+    def eval_device(self, W, P, G, Jv=None, batch_minor=False, stream=None):
+        import torch
+        for t in (W, P, G) + ((Jv,) if Jv is not None else ()):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+                raise ValueError('eval_device needs contiguous float64 CUDA tensors')
+        B = W.shape[0]
+        flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        if batch_minor:
+            flags |= cabi.AWEGPU_JAC_BATCH_MINOR
+        if Jv is None:
+            flags |= cabi.AWEGPU_SKIP_JAC
+        if stream is None:
+            stream = torch.cuda.current_stream(W.device).cuda_stream
+        rc = self.lib.awegpu_eval_batch(self.handle, B, W.data_ptr(), P.data_ptr(), G.data_ptr(),
+                                        Jv.data_ptr() if Jv is not None else None, flags, C.c_void_p(stream))
+        self._check(rc, 'awegpu_eval_batch')
+
+    def last_eval_ms(self):
+        return float(self.lib.awegpu_last_eval_ms(self.handle))
+
+    def launch_count(self):
+        return int(self.lib.awegpu_launch_count(self.handle))
+
+    # ---- single-instance, reference-style callables
+    def g_fun(self, V, P):
+        """``nlp.g_fun(V, P)``: one instance, returns g [n_g]."""
+        G, _ = self.eval(np.asarray(V, dtype=float).reshape(1, -1), np.asarray(P, dtype=float).reshape(-1), jac=False)
+        return G[0]
+
+    def jac_g_fun(self, V, P):
+        """values of jac_g(V, P) in CCS order, [nnz]."""
+        _, Jv = self.eval(np.asarray(V, dtype=float).reshape(1, -1), np.asarray(P, dtype=float).reshape(-1))
+        return Jv[0]
+
+    def jac_g_scipy(self, V, P):
+        import scipy.sparse as sps
+        colind, row = self.sparsity()
+        return sps.csc_matrix((self.jac_g_fun(V, P), row, colind), shape=(self.n_g, self.n_v))
