@@ -13,6 +13,7 @@ AWEGPU_P_FULL = 0
 AWEGPU_P_THETA0 = 4
 AWEGPU_P_SHARED = 8
 AWEGPU_SKIP_JAC = 16
+AWEGPU_HOST_PINNED = 32
 
 
 class ProblemStruct(C.Structure):

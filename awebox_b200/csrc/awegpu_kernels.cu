@@ -24,6 +24,9 @@
 #include "model_defs.h"
 
 #define TILE 32
+#ifndef AWE_MIN_BLOCKS
+#define AWE_MIN_BLOCKS 2
+#endif
 #define N_X AWE_N_X
 #define N_U AWE_N_U
 #define N_Z AWE_N_Z
@@ -113,7 +116,7 @@ __device__ __forceinline__ void node_shoot(const double *__restrict__ xs, const 
 #undef VIN
 }
 
-__global__ void __launch_bounds__(N_THREADS, 2)
+__global__ void __launch_bounds__(N_THREADS, AWE_MIN_BLOCKS)
 awegpu_eval_kernel(const DevProblem pr, const int B, const double *__restrict__ W, const double *__restrict__ P,
                    const long long ldp, const int p_off, double *__restrict__ G, double *__restrict__ Jv,
                    const int batch_minor)
@@ -228,7 +231,8 @@ struct awegpu_handle {
     // staging for the host entry
     double *dW = nullptr, *dP = nullptr, *dG = nullptr, *dJ = nullptr;
     double *hW = nullptr, *hP = nullptr, *hG = nullptr, *hJ = nullptr;
-    size_t capW = 0, capP = 0, capG = 0, capJ = 0;
+    size_t capW = 0, capP = 0, capG = 0, capJ = 0, hcapW = 0, hcapP = 0, hcapG = 0, hcapJ = 0;
+    cudaStream_t stream2 = nullptr;
     // casadi sparsity buffers
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
     std::vector<double> scratch_g;
@@ -290,6 +294,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
 }
 
@@ -441,15 +446,20 @@ extern "C" float awegpu_last_eval_ms(awegpu_handle_t *h)
 
 extern "C" int64_t awegpu_launch_count(awegpu_handle_t *h) { return h ? h->launches : 0; }
 
-static int grow(awegpu_handle *h, double **dev, double **host, size_t *cap, size_t need)
+static int grow(awegpu_handle *h, double **dev, double **host, size_t *cap, size_t *hcap, size_t need, bool with_host)
 {
-    if (need <= *cap) return 0;
-    if (*dev) cudaFree(*dev);
-    if (*host) cudaFreeHost(*host);
-    *dev = nullptr, *host = nullptr, *cap = 0;
-    CK(cudaMalloc((void **)dev, need * sizeof(double)));
-    CK(cudaMallocHost((void **)host, need * sizeof(double)));
-    *cap = need;
+    if (need > *cap) {
+        if (*dev) cudaFree(*dev);
+        *dev = nullptr, *cap = 0;
+        CK(cudaMalloc((void **)dev, need * sizeof(double)));
+        *cap = need;
+    }
+    if (with_host && need > *hcap) {
+        if (*host) cudaFreeHost(*host);
+        *host = nullptr, *hcap = 0;
+        CK(cudaMallocHost((void **)host, need * sizeof(double)));
+        *hcap = need;
+    }
     return 0;
 }
 
@@ -465,9 +475,45 @@ extern "C" int awegpu_eval_batch_host(awegpu_handle_t *h, int32_t B, const doubl
     const size_t p_len = (flags & AWEGPU_P_THETA0) ? d.n_theta0 : d.n_p;
     const size_t nP = (flags & AWEGPU_P_SHARED) ? p_len : (size_t)B * p_len;
     const size_t nG = (size_t)B * d.n_g, nJ = want_j ? (size_t)B * d.nnz : 0;
-    int rc = grow(h, &h->dW, &h->hW, &h->capW, nW) | grow(h, &h->dP, &h->hP, &h->capP, nP) |
-             grow(h, &h->dG, &h->hG, &h->capG, nG) | (want_j ? grow(h, &h->dJ, &h->hJ, &h->capJ, nJ) : 0);
+    const bool stage = !(flags & AWEGPU_HOST_PINNED);
+    int rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, nW, stage) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, nP, stage) |
+             grow(h, &h->dG, &h->hG, &h->capG, &h->hcapG, nG, stage) |
+             (want_j ? grow(h, &h->dJ, &h->hJ, &h->capJ, &h->hcapJ, nJ, stage) : 0);
     if (rc) return rc;
+    if (flags & AWEGPU_HOST_PINNED) {
+        // caller buffers are page-locked: copy straight from / into them, in chunks on two streams so
+        // that H2D of chunk c+1, the kernel of chunk c and D2H of chunk c-1 overlap.
+        if (!h->stream2) CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        const bool shared = (flags & AWEGPU_P_SHARED) != 0;
+        if (shared) CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const int chunk = 512;
+        int c = 0;
+        for (int b0 = 0; b0 < B; b0 += chunk, ++c) {
+            const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
+            cudaStream_t st = (c & 1) ? h->stream2 : h->stream;
+            CK(cudaMemcpyAsync(h->dW + (size_t)b0 * d.n_v, W + (size_t)b0 * d.n_v, (size_t)nb * d.n_v * sizeof(double),
+                               cudaMemcpyHostToDevice, st));
+            if (!shared)
+                CK(cudaMemcpyAsync(h->dP + (size_t)b0 * p_len, P + (size_t)b0 * p_len, (size_t)nb * p_len * sizeof(double),
+                                   cudaMemcpyHostToDevice, st));
+            if (flags & AWEGPU_JAC_BATCH_MINOR) {
+                set_err(h, "AWEGPU_HOST_PINNED supports the instance-major layout only");
+                return 1;
+            }
+            rc = awegpu_eval_batch(h, nb, h->dW + (size_t)b0 * d.n_v, shared ? h->dP : h->dP + (size_t)b0 * p_len,
+                                   h->dG + (size_t)b0 * d.n_g, want_j ? h->dJ + (size_t)b0 * d.nnz : nullptr, flags, st);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(G + (size_t)b0 * d.n_g, h->dG + (size_t)b0 * d.n_g, (size_t)nb * d.n_g * sizeof(double),
+                               cudaMemcpyDeviceToHost, st));
+            if (want_j)
+                CK(cudaMemcpyAsync(Jv + (size_t)b0 * d.nnz, h->dJ + (size_t)b0 * d.nnz, (size_t)nb * d.nnz * sizeof(double),
+                                   cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaStreamSynchronize(h->stream2));
+        return 0;
+    }
     memcpy(h->hW, W, nW * sizeof(double));
     memcpy(h->hP, P, nP * sizeof(double));
     CK(cudaMemcpyAsync(h->dW, h->hW, nW * sizeof(double), cudaMemcpyHostToDevice, h->stream));

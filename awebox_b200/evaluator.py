@@ -69,9 +69,9 @@ class Evaluator(object):
         self.device = int(device)
         self.n_v, self.n_p, self.n_g, self.nnz = self.ocp.n_v, self.ocp.n_p, self.ocp.n_g, self.ocp.nnz
         self.n_theta0 = self.ocp.n_theta0
-        fl = (C.c_int64 * 2)()
-        self.lib.awegpu_model_dims(None, None, None, None, C.byref(fl, 0), C.byref(fl, 8))
-        self.flops_coll, self.flops_shoot = int(fl[0]), int(fl[1])
+        fc, fs = C.c_int64(0), C.c_int64(0)
+        self.lib.awegpu_model_dims(None, None, None, None, C.byref(fc), C.byref(fs))
+        self.flops_coll, self.flops_shoot = int(fc.value), int(fs.value)
 
     def close(self):
         if getattr(self, 'handle', None) and self.handle.value:
@@ -98,16 +98,16 @@ class Evaluator(object):
 
     @staticmethod
     def p_flags(P, n_p, n_theta0, B):
-        P = np.asarray(P)
+        shape = tuple(P.shape)
         flags = 0
-        if P.shape[-1] == n_theta0:
+        if shape[-1] == n_theta0:
             flags |= cabi.AWEGPU_P_THETA0
-        elif P.shape[-1] != n_p:
-            raise ValueError('P has %d columns; expected n_p=%d or n_theta0=%d' % (P.shape[-1], n_p, n_theta0))
-        if P.ndim == 1 or P.shape[0] == 1:
+        elif shape[-1] != n_p:
+            raise ValueError('P has %d columns; expected n_p=%d or n_theta0=%d' % (shape[-1], n_p, n_theta0))
+        if len(shape) == 1 or shape[0] == 1:
             flags |= cabi.AWEGPU_P_SHARED
-        elif P.shape[0] != B:
-            raise ValueError('P has %d rows for a batch of %d' % (P.shape[0], B))
+        elif shape[0] != B:
+            raise ValueError('P has %d rows for a batch of %d' % (shape[0], B))
         return flags
 
     # ---- host entry: numpy in, numpy out (H2D / D2H inside the call)

@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py — collocation-node g + Jacobian evaluations per second (BASELINE.json: metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A step = one pass of the hot path over one batch of synthetic OCP instances.  Workload at N=1:
+BASELINE.json configs[1] — the Ampyx AP2 OCP (Radau d=4, n_k=40), batched g + Jacobian at 4096
+randomly perturbed primal points.  Weak scaling: every GPU gets its own 4096 instances (batch
+sharded, no data-path collective); value = coll-node-evals of all ranks / max-over-ranks time.
+
+``value``  : inputs resident in HBM, outputs left in HBM (device-pointer C-ABI entry).
+``e2e``    : the same metric through the host-buffer C-ABI entry (pinned host memory, H2D of W / P
+             and D2H of g / jac_g values inside the timed region).
+``roofline``: the one kernel of the step, algorithmic bytes / CUDA-event duration vs measured HBM peak.
+``cpu_baseline`` / ``--impl reference``: the plain-C checker (oracle/awebox_oracle.c, the CPU port of
+             the same path) on the host cores of this box; CasADi itself cannot be installed here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SPEC, N_K, BATCH = 'ampyx_ap2', 40, 4096
+WORKLOAD = 'ampyx_ap2 OCP (Radau d=4, n_k=40): batched g+jac_g at 4096 perturbed primal points per GPU'
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(',')]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
+                'samples': len(self.samples)}
+
+
+def cpu_leg(ocp, n_threads, budget_s, W, p):
+    """time the CPU port on a bounded sample; returns (node-evals/s, seconds, instances, threads)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import build_oracle
+    from awebox_b200 import cabi
+    orc = build_oracle.Oracle(ocp)
+    sample = W[:256]
+    orc.eval(sample, p, flags=cabi.AWEGPU_P_SHARED, n_threads=n_threads)      # warm-up
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        orc.eval(sample, p, flags=cabi.AWEGPU_P_SHARED, n_threads=n_threads)
+        done += sample.shape[0]
+        dt = time.perf_counter() - t0
+        if dt >= budget_s:
+            break
+    return done * ocp.n_k * ocp.d / dt, dt, done, n_threads
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from awebox_b200.spec import ModelSpec
+    from awebox_b200.ocp.nlp import OcpProblem
+    from awebox_b200 import synthetic
+    ocp = OcpProblem(ModelSpec.load(SPEC), n_k=N_K)
+    W = synthetic.batch(ocp, 256, seed=20261018 + 2)
+    p = ocp.default_p()
+    threads = os.cpu_count()
+    per_step = max(1.0, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_leg(ocp, threads, 0.2, W, p)
+    vals, secs, inst = [], 0.0, 0
+    for _ in range(args.steps):
+        v, dt, n, _ = cpu_leg(ocp, threads, per_step / 2, W, p)
+        vals.append(v)
+        secs += dt
+        inst += n
+    value = inst * ocp.n_k * ocp.d / secs
+    sample = 'bounded sample: 256-instance blocks of the same workload repeated for %.1f s per step' % (per_step / 2)
+    line = {
+        'impl': 'reference', 'metric': 'collocation-node g+Jacobian evals/s', 'value': value, 'unit': 'node-evals/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / max(1, args.steps),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'n_k': N_K, 'd': ocp.d, 'n_v': ocp.n_v, 'n_g': ocp.n_g, 'nnz': int(ocp.nnz)},
+        'cpu_baseline': {'value': value, 'unit': 'node-evals/s', 'cores': threads, 'kind': 'port', 'sample': sample,
+                         'note': 'plain-C port of the path (gcc -O2, OpenMP over instances); CasADi 3.6.4 itself is '
+                                 'not installable on this box'},
+        'e2e': {'value': value, 'unit': 'node-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH, help='instances per GPU')
+    ap.add_argument('--cpu-seconds', type=float, default=10.0)
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from awebox_b200.evaluator import Evaluator
+    from awebox_b200 import synthetic, cabi
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device visible — this benchmark has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    ev = Evaluator(SPEC, n_k=N_K, device=local_rank)
+    ocp = ev.ocp
+    B = args.batch
+    # weak scaling: rank r owns instances [r*B, (r+1)*B) of the global batch of world*B instances
+    W = synthetic.batch(ocp, B, seed=20261018 + 2 + 1000 * rank)
+    p = ocp.default_p()
+    dW = torch.from_numpy(W).cuda()
+    dP = torch.from_numpy(p).cuda()
+    dG = torch.empty((B, ocp.n_g), dtype=torch.float64, device='cuda')
+    dJ = torch.empty((B, ocp.nnz), dtype=torch.float64, device='cuda')
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = ev.launch_count()
+    for _ in range(args.warmup):
+        ev.eval_device(dW, dP, dG, dJ)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches1 = ev.launch_count()
+    kernel_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        ev.eval_device(dW, dP, dG, dJ)
+    e1.record(stream)
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    gpu_launches = ev.launch_count() - launches1
+    # per-launch duration of the one kernel, CUDA events on the launching stream (a few extra launches)
+    for _ in range(5):
+        ev.eval_device(dW, dP, dG, dJ)
+        torch.cuda.synchronize()
+        kernel_ms.append(ev.last_eval_ms())
+    sampler.stop_flag = True
+    t = torch.tensor([total_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    nodes_per_step = world * B * ocp.n_k * ocp.d
+    value = nodes_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry (pinned host memory)
+    hW = torch.from_numpy(W).pin_memory()
+    hP = torch.from_numpy(p).pin_memory()
+    hG = torch.empty((B, ocp.n_g), dtype=torch.float64).pin_memory()
+    hJ = torch.empty((B, ocp.nnz), dtype=torch.float64).pin_memory()
+    flags = cabi.AWEGPU_P_SHARED | cabi.AWEGPU_HOST_PINNED
+
+    def e2e_step():
+        rc = ev.lib.awegpu_eval_batch_host(ev.handle, B, hW.data_ptr(), hP.data_ptr(), hG.data_ptr(), hJ.data_ptr(), flags)
+        if rc != 0:
+            raise SystemExit('awegpu_eval_batch_host failed: %s' % ev.lib.awegpu_last_error(ev.handle).decode())
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = nodes_per_step * args.e2e_steps / float(t.item())
+    assert bool(np.isfinite(hG.numpy()).all())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        k_ms = float(np.median(kernel_ms))
+        alg_bytes = B * ocp.algorithmic_bytes()
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        flops = B * (ocp.n_k * ocp.d * ev.flops_coll + ocp.n_k * ev.flops_shoot)
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get('dram_bytes_per_launch')
+        cpu_v, cpu_dt, cpu_n, cpu_thr = cpu_leg(ocp, os.cpu_count(), args.cpu_seconds, W, p)
+        line = {
+            'metric': 'collocation-node g+Jacobian evals/s', 'value': value, 'unit': 'node-evals/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'n_k': N_K, 'd': ocp.d, 'instances_per_gpu': B, 'n_v': ocp.n_v,
+                       'n_g': ocp.n_g, 'nnz': int(ocp.nnz), 'jac_layout': 'instance-major CCS values',
+                       'l2': 'inputs+outputs per step (3.2 GB) exceed the 126 MB L2; no flush needed',
+                       'parallelism': 'batch sharded over %d GPU(s), no data-path collective' % world},
+            'clocks': sampler.summary(),
+            'e2e': {'value': e2e_value, 'unit': 'node-evals/s',
+                    'h2d_bytes_per_step': int(8 * (W.size + p.size)) * world,
+                    'd2h_bytes_per_step': int(8 * B * (ocp.n_g + ocp.nnz)) * world,
+                    'api': 'awegpu_eval_batch_host (pinned host buffers)'},
+            'gpu_launches': int(gpu_launches),
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'awegpu_eval_kernel',
+                         'kernel_ms': k_ms, 'algorithmic_bytes_per_launch': int(alg_bytes),
+                         'fp64_gflops_achieved': flops / (k_ms * 1e-3) / 1e9, 'algorithmic_flops_per_launch': int(flops)},
+            'cpu_baseline': {'value': cpu_v, 'unit': 'node-evals/s', 'cores': cpu_thr, 'kind': 'port',
+                             'sample': '256-instance blocks of the same workload repeated for %.1f s (%d instances)'
+                                       % (cpu_dt, cpu_n)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

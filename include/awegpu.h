@@ -75,6 +75,8 @@ typedef struct awegpu_handle awegpu_handle_t;
 #define AWEGPU_P_THETA0           4   /* P holds theta0 only, leading dimension n_theta0        */
 #define AWEGPU_P_SHARED           8   /* one parameter vector shared by all instances           */
 #define AWEGPU_SKIP_JAC          16   /* residual only                                          */
+#define AWEGPU_HOST_PINNED       32   /* eval_batch_host: caller buffers are page-locked; copy   */
+                                      /* directly, chunked over two streams (no staging copy)    */
 
 const char *awegpu_model_name(void);             /* spec the node functions were generated from */
 int awegpu_model_dims(int32_t *n_var, int32_t *n_param, int32_t *n_coll_out, int32_t *n_shoot_out,

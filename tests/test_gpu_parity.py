@@ -1,0 +1,155 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU checker on the same
+seeded inputs, against the golden fixtures, and — at BASELINE.json's full size — through
+size-independent properties.  Integer structure bit-exact; FP64 values within 1e-12 (entry-relative,
+row-scale floor: see conftest.jac_tolerance)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, get_ocp, get_oracle, jac_tolerance
+from awebox_b200 import cabi, synthetic
+
+pytestmark = pytest.mark.gpu
+
+_EV = {}
+
+
+def evaluator(name, n_k):
+    from awebox_b200.evaluator import Evaluator
+    if (name, n_k) not in _EV:
+        _EV[(name, n_k)] = Evaluator(name, ocp=get_ocp(name, n_k))
+    return _EV[(name, n_k)]
+
+
+def assert_parity(ocp, G, Jv, G0, J0):
+    assert np.all(np.abs(G - G0) <= 1e-12 * np.maximum(1.0, np.abs(G0)))
+    assert np.all(np.abs(Jv - J0) <= jac_tolerance(ocp, J0))
+
+
+def test_native_library_is_loaded():
+    ev = evaluator('ampyx_ap2', 4)
+    assert ev.lib.awegpu_model_name() == b'ampyx_ap2'
+    with open('/proc/self/maps') as f:
+        assert 'libawegpu_ampyx_ap2.so' in f.read()
+
+
+@pytest.mark.parametrize('name,n_k', [('ampyx_ap2', 4), ('ampyx_ap2', 40)])
+def test_sparsity_bit_exact(name, n_k):
+    ev = evaluator(name, n_k)
+    colind, row = ev.sparsity()
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d.npz' % (name, n_k)))
+    assert colind.dtype == np.int64 and row.dtype == np.int64
+    assert np.array_equal(colind, gold['colind']) and np.array_equal(row, gold['row'])
+
+
+@pytest.mark.parametrize('name,n_k', [('ampyx_ap2', 4), ('ampyx_ap2', 40)])
+def test_against_reference_golden_vectors(name, n_k):
+    ev = evaluator(name, n_k)
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d.npz' % (name, n_k)))
+    G, Jv = ev.eval(gold['w'], gold['p'])
+    assert_parity(ev.ocp, G, Jv, gold['g'], gold['jv'])
+
+
+@pytest.mark.parametrize('name,n_k,B', [('ampyx_ap2', 4, 257), ('ampyx_ap2', 40, 96)])
+def test_against_checker_on_seeded_batch(name, n_k, B):
+    ev = evaluator(name, n_k)
+    ocp = ev.ocp
+    W = synthetic.batch(ocp, B, seed=20261018 + n_k)
+    p = ocp.default_p()
+    G0, J0 = get_oracle(name, n_k).eval(W, p, flags=cabi.AWEGPU_P_SHARED)
+    G, Jv = ev.eval(W, p)
+    assert_parity(ocp, G, Jv, G0, J0)
+
+
+@pytest.mark.parametrize('B', [1, 31, 32, 33])
+def test_ragged_tiles(B):
+    ev = evaluator('ampyx_ap2', 4)
+    W = synthetic.batch(ev.ocp, B, seed=5)
+    p = ev.ocp.default_p()
+    G0, J0 = get_oracle('ampyx_ap2', 4).eval(W, p, flags=cabi.AWEGPU_P_SHARED)
+    G, Jv = ev.eval(W, p)
+    assert G.shape == (B, ev.n_g) and Jv.shape == (B, ev.nnz)
+    assert_parity(ev.ocp, G, Jv, G0, J0)
+
+
+def test_empty_batch_is_a_no_op():
+    ev = evaluator('ampyx_ap2', 4)
+    G, Jv = ev.eval(np.zeros((0, ev.n_v)), ev.ocp.default_p())
+    assert G.shape == (0, ev.n_g) and Jv.shape == (0, ev.nnz)
+
+
+def test_layouts_and_parameter_modes_agree():
+    ev = evaluator('ampyx_ap2', 4)
+    ocp = ev.ocp
+    B = 70
+    W = synthetic.batch(ocp, B, seed=11)
+    rng = np.random.default_rng(2)
+    P = np.tile(ocp.default_p(), (B, 1))
+    iu = ocp.p_theta0 + ocp.spec.theta0_labels.index('[theta0,wind,u_ref,0]')
+    P[:, iu] = rng.uniform(5.0, 8.0, B)                 # per-instance wind speed (power-curve batch)
+    G0, J0 = get_oracle('ampyx_ap2', 4).eval(W, P, flags=cabi.AWEGPU_P_FULL)
+    G1, J1 = ev.eval(W, P)
+    assert_parity(ocp, G1, J1, G0, J0)
+    G2, J2 = ev.eval(W, P[:, ocp.p_theta0:])             # theta0-only parameter block
+    assert np.array_equal(G1, G2) and np.array_equal(J1, J2)
+    G3, J3 = ev.eval(W, P, batch_minor=True)             # [n_g, B] / [nnz, B]
+    assert np.array_equal(G3.T, G1) and np.array_equal(J3.T, J1)
+    G4, _ = ev.eval(W, P, jac=False)
+    assert np.array_equal(G4, G1)
+
+
+def test_reference_style_single_instance_calls():
+    ev = evaluator('ampyx_ap2', 4)
+    gold = np.load(os.path.join(GOLDEN, 'ampyx_ap2_nk4.npz'))
+    g = ev.g_fun(gold['w'][0], gold['p'])
+    assert g.shape == (ev.n_g,)
+    assert np.all(np.abs(g - gold['g'][0]) <= 1e-12 * np.maximum(1.0, np.abs(gold['g'][0])))
+    J = ev.jac_g_scipy(gold['w'][0], gold['p'])
+    assert J.shape == (ev.n_g, ev.n_v) and J.nnz == ev.nnz
+
+
+def test_full_size_properties():
+    """BASELINE configs[1]: AP2 n_k=40, B=4096 — properties that do not need the checker at full size."""
+    import torch
+    ev = evaluator('ampyx_ap2', 40)
+    ocp = ev.ocp
+    B = 4096
+    W = synthetic.batch(ocp, B, seed=20261018 + 2)
+    p = ocp.default_p()
+    dW, dP = torch.from_numpy(W).cuda(), torch.from_numpy(p).cuda()
+    dG = torch.empty((B, ocp.n_g), dtype=torch.float64, device='cuda')
+    dJ = torch.empty((B, ocp.nnz), dtype=torch.float64, device='cuda')
+    dJ.fill_(float('nan'))
+    ev.eval_device(dW, dP, dG, dJ)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(dG).all()) and bool(torch.isfinite(dJ).all())      # every slot was written
+    # (1) a sample of instances against the checker
+    idx = np.arange(0, B, 257)
+    G0, J0 = get_oracle('ampyx_ap2', 40).eval(W[idx], p, flags=cabi.AWEGPU_P_SHARED)
+    assert_parity(ocp, dG[idx].cpu().numpy(), dJ[idx].cpu().numpy(), G0, J0)
+    # (2) instance independence: evaluating a permuted batch permutes the results bit for bit
+    perm = torch.randperm(B, device='cuda', generator=torch.Generator(device='cuda').manual_seed(0))
+    dG2, dJ2 = torch.empty_like(dG), torch.empty_like(dJ)
+    ev.eval_device(dW[perm].contiguous(), dP, dG2, dJ2)
+    torch.cuda.synchronize()
+    assert torch.equal(dG2, dG[perm]) and torch.equal(dJ2, dJ[perm])
+    # (3) directional-derivative check of the whole sparse Jacobian, all instances at once:
+    #     g(w + e v) - g(w - e v) = 2 e J v + O(e^3)
+    colind = torch.from_numpy(ocp.colind).cuda()
+    col = torch.repeat_interleave(torch.arange(ocp.n_v, device='cuda'), colind[1:] - colind[:-1])
+    row = torch.from_numpy(ocp.row).cuda()
+    v = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, (B, ocp.n_v))).cuda() * dW.abs()
+    eps = 1e-6
+    Gp, Gm = torch.empty_like(dG), torch.empty_like(dG)
+    ev.eval_device((dW + eps * v).contiguous(), dP, Gp)
+    ev.eval_device((dW - eps * v).contiguous(), dP, Gm)
+    Jv_prod = torch.zeros_like(dG).index_add_(1, row, dJ * v[:, col])
+    fd = (Gp - Gm) / (2 * eps)
+    scale = torch.zeros_like(dG).index_add_(1, row, (dJ * v[:, col]).abs()) + 1e-3
+    assert float(((fd - Jv_prod).abs() / scale).max()) < 1e-5
+    # (4) continuity rows are linear: x_{k+1} - x_{k,d}  (Radau), checked exactly on the inputs
+    k = 7
+    r0 = ocp.row_cont[k]
+    want = dW[:, ocp.v_x[k + 1]:ocp.v_x[k + 1] + ocp.n_x] - dW[:, ocp.v_cx[k][ocp.d - 1]:ocp.v_cx[k][ocp.d - 1] + ocp.n_x]
+    assert float((dG[:, r0:r0 + ocp.n_x] - want).abs().max()) < 1e-14
