@@ -61,8 +61,8 @@ def compile_cuda(spec_name, force=False, verbose=False, extra_flags=()):
     os.makedirs(LIBDIR, exist_ok=True)
     g = gen_dir(spec_name)
     srcs = [os.path.join(CSRC, 'awegpu_kernels.cu')]
-    deps = srcs + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cuh', '.h'))] + \
-        [os.path.join(g, f) for f in ('model_defs.h', 'node_coll.inc', 'node_shoot.inc')] + \
+    deps = srcs + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
+        [os.path.join(g, f) for f in sorted(os.listdir(g)) if f.endswith(('.h', '.inc'))] + \
         [os.path.join(ROOT, 'include', 'awegpu.h')]
     out = lib_path(spec_name)
     stamp = out + '.sha256'

@@ -16,6 +16,7 @@ The emitted body only uses macros (``VIN(i)``, ``PIN(i)``, ``CCIN(r)``, ``OWNIN(
 import numpy as np
 
 from . import sym as S
+from . import schedule as SCH
 
 
 def _fmt(v):
@@ -27,6 +28,30 @@ def _fmt(v):
     if 'e' not in r and '.' not in r:
         r += '.0'
     return r
+
+
+# back-end parameters of the CUDA emission (awebox_b200/schedule.py): FP64 registers handed to the
+# allocator, reload look-ahead (statements), shared-memory scratch slots per thread, statements
+# between two CTA-wide re-convergence points (instruction-cache locality)
+N_REGS = 100
+LOOKAHEAD = 8
+HOT_SLOTS = 176
+SYNC_EVERY = 512
+
+
+def _rhs(op, a, b):
+    if op == S.ADD: return '%s + %s' % (a, b)
+    if op == S.SUB: return '%s - %s' % (a, b)
+    if op == S.MUL: return '%s * %s' % (a, b)
+    if op == S.DIV: return '%s / %s' % (a, b)
+    if op == S.NEG: return '-%s' % a
+    if op == S.SQRT: return 'sqrt(%s)' % a
+    if op == S.RSQRT: return 'RSQRT(%s)' % a
+    if op in (S.POWC, S.POW): return 'pow(%s, %s)' % (a, b)
+    if op == S.ATAN2: return 'atan2(%s, %s)' % (a, b)
+    if op == S.SIGN: return 'SIGN(%s)' % a
+    return '%s(%s)' % ({S.SIN: 'sin', S.COS: 'cos', S.TAN: 'tan', S.ASIN: 'asin', S.ACOS: 'acos',
+                        S.ATAN: 'atan', S.EXP: 'exp', S.LOG: 'log', S.FABS: 'fabs'}[op], a)
 
 
 class NodeCode(object):
@@ -93,6 +118,7 @@ class NodeCode(object):
                 e = (j_eq[i] if kind == 'eq' else j_ineq[i]).get(c, S.ZERO)
             outs.append(sc(S._e(e)))
         self.shoot_exprs = outs
+        self._kernel_exprs()
         self._names = {}
         for i, v in enumerate(m.vars):
             self._names[v.idx] = 'VIN(%d)' % i
@@ -102,6 +128,117 @@ class NodeCode(object):
             self._names[self.cc[r].idx] = 'CCIN(%d)' % r
             self._names[self.own[r].idx] = 'OWNIN(%d)' % r
         self._names[self.itf.idx] = 'ITF'
+
+    # ------------------------------------------------------------------ kernel-side expressions
+    def _kernel_exprs(self):
+        """The same outputs over the leaves the CUDA kernels actually read: the state blocks X_r of
+        the interval (``XR(r,m)``), the node's own block (``XO(m)``), ``UIN/ZIN/THIN/PIN`` and the per-lane
+        collocation coefficients, with ``xdot_m = sum_r cc_r X_r[m]`` (awebox/ocp/collocation.py:225,
+        239-250) part of the graph so that the scheduler sees the contraction."""
+        ocp, m = self.ocp, self.ocp.model
+        rng, d = ocp.rng, ocp.d
+        leaf = {}
+        self.k_leaf = leaf              # sym idx -> macro text
+        xo = [S.sym('XO(%d)' % i) for i in range(ocp.n_x)]
+        xr = [[S.sym('XR(%d,%d)' % (r, i)) for i in range(ocp.n_x)] for r in range(d + 1)]
+        xd = [S.sym('XD(%d)' % i) for i in range(ocp.n_x)]
+        ui = [S.sym('UIN(%d)' % i) for i in range(ocp.n_u)]
+        zi = [S.sym('ZIN(%d)' % i) for i in range(ocp.n_z)]
+        th = [S.sym('THIN(%d)' % i) for i in range(ocp.n_theta)]
+        pi = [S.sym('PIN(%d)' % i) for i in range(m.n_param)]
+        for group in (xo, xd, ui, zi, th, pi) + tuple(xr):
+            for v in group:
+                leaf[v.idx] = v.name
+        for r in range(d + 1):
+            leaf[self.cc[r].idx] = 'CCIN(%d)' % r
+            leaf[self.own[r].idx] = 'OWNIN(%d)' % r
+        leaf[self.itf.idx] = 'ITF'
+        base = {}
+        for i in range(ocp.n_x):
+            base[m.vars[rng['x'][0] + i]] = xo[i]
+        for i in range(ocp.n_u):
+            base[m.vars[rng['u'][0] + i]] = ui[i]
+        for i in range(ocp.n_z):
+            base[m.vars[rng['z'][0] + i]] = zi[i]
+        for i in range(ocp.n_theta):
+            base[m.vars[rng['theta'][0] + i]] = th[i]
+        for i in range(m.n_param):
+            base[m.params[i]] = pi[i]
+        coll_map = dict(base)
+        for i in range(ocp.n_x):
+            e = S.ZERO
+            for r in range(d + 1):
+                e = e + self.cc[r] * xr[r][i]
+            coll_map[m.vars[rng['xdot'][0] + i]] = e
+        shoot_map = dict(base)
+        for i in range(ocp.n_x):
+            shoot_map[m.vars[rng['xdot'][0] + i]] = xd[i]
+        self.k_coll = S.substitute(self.coll_exprs, coll_map)
+        self.k_shoot = S.substitute(self.shoot_exprs, shoot_map)
+
+    def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=32):
+        """-> (text, stats): register-allocated straight-line code (awebox_b200/schedule.py) printed
+        with statement macros:
+            LD_XR(reg, r, m) LD_XO(reg, m) LD_XD(reg, m) LD_U(reg, c) LD_Z(reg, c) LD_TH(reg, t)
+            LD_P(reg, i) LD_CC(reg, r) LD_OWN(reg, r) LD_ITF(reg)        input loads
+            SPILL_ST(slot, reg) SPILL_LD(reg, slot)                       hot scratch tier (shared memory)
+            OVF_ST(slot, reg) OVF_LD(reg, slot)                           cold scratch tier
+            OUT(n, value) FLUSH(chunk, count) SYNC_HINT()                 staged outputs
+        Scratch slots are ranked by access count; the ``hot_slots`` busiest go to the hot tier."""
+        prog = SCH.allocate(exprs, n_regs, lookahead)
+        access = {}
+        for it in prog.ins:
+            if it[0] == 'ld':
+                access[it[2]] = access.get(it[2], 0) + 1
+            elif it[0] == 'st':
+                access[it[1]] = access.get(it[1], 0) + 1
+        ranked = sorted(access, key=lambda s_: (-access[s_], s_))
+        tier = {}
+        for rank, s_ in enumerate(ranked):
+            tier[s_] = ('SPILL', rank) if rank < hot_slots else ('OVF', rank - hot_slots)
+        n_hot = min(len(ranked), hot_slots)
+        n_cold = max(0, len(ranked) - hot_slots)
+        lines = ['double ' + ', '.join('r%d' % i for i in range(prog.n_regs)) + ';']
+
+        def src(s_):
+            return _fmt(s_.val) if isinstance(s_, S.Expr) else 'r%d' % s_
+
+        n_stmt = 0
+        n_out = len(exprs)
+        cold_acc = 0
+        for it in prog.ins:
+            k = it[0]
+            if k == 'leaf':
+                name = self.k_leaf[it[2].idx]
+                if '(' in name:
+                    kind, args = name[:-1].split('(')
+                    lines.append('LD_%s(r%d, %s);' % (kind.replace('IN', ''), it[1], args))
+                else:
+                    lines.append('LD_%s(r%d);' % (name, it[1]))
+            elif k == 'ld':
+                t, idx = tier[it[2]]
+                cold_acc += t == 'OVF'
+                lines.append('%s_LD(r%d, %d);' % (t, it[1], idx))
+            elif k == 'st':
+                t, idx = tier[it[1]]
+                cold_acc += t == 'OVF'
+                lines.append('%s_ST(%d, r%d);' % (t, idx, it[2]))
+            elif k == 'out':
+                n = it[1]
+                lines.append('OUT(%d, %s);' % (n, src(it[2])))
+                if (n + 1) % chunk == 0 or n + 1 == n_out:
+                    lines.append('FLUSH(%d, %d);' % (n // chunk, n % chunk + 1))
+            else:
+                r, n, srcs = it[1], it[2], it[3]
+                lines.append('r%d = %s;' % (r, _rhs(n.op, src(srcs[0]), src(srcs[1]) if len(srcs) > 1 else None)))
+                n_stmt += 1
+                if n_stmt % SYNC_EVERY == 0:
+                    lines.append('SYNC_HINT();')
+        stats = dict(prog.stats)
+        stats.update(S.count_ops(exprs))
+        stats.update(outputs=n_out, chunks=(n_out + chunk - 1) // chunk, hot_slots=n_hot, cold_slots=n_cold,
+                     cold_accesses=cold_acc)
+        return '\n'.join(lines) + '\n', stats
 
     # ------------------------------------------------------------------
     def emit(self, exprs):
@@ -130,22 +267,7 @@ class NodeCode(object):
                 if n.idx not in names:
                     raise ValueError('free symbol %s in node function' % n.name)
             else:
-                a = ref(n.a)
-                b = ref(n.b) if n.b is not None else None
-                op = n.op
-                if op == S.ADD: rhs = '%s + %s' % (a, b)
-                elif op == S.SUB: rhs = '%s - %s' % (a, b)
-                elif op == S.MUL: rhs = '%s * %s' % (a, b)
-                elif op == S.DIV: rhs = '%s / %s' % (a, b)
-                elif op == S.NEG: rhs = '-%s' % a
-                elif op == S.SQRT: rhs = 'sqrt(%s)' % a
-                elif op == S.RSQRT: rhs = 'RSQRT(%s)' % a
-                elif op in (S.POWC, S.POW): rhs = 'pow(%s, %s)' % (a, b)
-                elif op == S.ATAN2: rhs = 'atan2(%s, %s)' % (a, b)
-                elif op == S.SIGN: rhs = 'SIGN(%s)' % a
-                else:
-                    rhs = '%s(%s)' % ({S.SIN: 'sin', S.COS: 'cos', S.TAN: 'tan', S.ASIN: 'asin', S.ACOS: 'acos',
-                                       S.ATAN: 'atan', S.EXP: 'exp', S.LOG: 'log', S.FABS: 'fabs'}[op], a)
+                rhs = _rhs(n.op, ref(n.a), ref(n.b) if n.b is not None else None)
                 nm = 't%d' % n_tmp
                 n_tmp += 1
                 names[n.idx] = nm
@@ -175,7 +297,21 @@ class NodeCode(object):
         head += '#define AWE_FLOPS_COLL %d\n#define AWE_FLOPS_SHOOT %d\n' % (flops(cs), flops(ss))
         banner = '// generated by awebox_b200/codegen.py from spec "%s" -- do not edit\n' % ocp.spec.name
         files = {'model_defs.h': head, 'node_coll.inc': banner + coll, 'node_shoot.inc': banner + shoot}
-        return files, {'coll': cs, 'shoot': ss}
+        stats = {'coll': cs, 'shoot': ss}
+        # ---- CUDA emission: scheduled + register-allocated; full (g + jac_g) and residual-only variants
+        n_sh = len(ocp.shoot_rows)
+        variants = {'k_coll': self.k_coll, 'k_shoot': self.k_shoot,
+                    'k_coll_res': self.k_coll[:ocp.n_eq], 'k_shoot_res': self.k_shoot[:n_sh]}
+        kdefs = ''
+        for name, exprs in variants.items():
+            text, st = self.emit_scheduled(exprs)
+            files[name + '.inc'] = banner + text
+            stats[name] = st
+            up = name.upper()
+            kdefs += '#define AWE_%s_HOT %d\n#define AWE_%s_COLD %d\n#define AWE_%s_CHUNKS %d\n' % (
+                up, st['hot_slots'], up, st['cold_slots'], up, st['chunks'])
+        files['model_defs.h'] = head + kdefs
+        return files, stats
 
     def write(self, out_dir):
         import os
@@ -192,4 +328,4 @@ class NodeCode(object):
 
 def flops(stats):
     """algorithmic flop count of an emitted function: every listed operation counts once."""
-    return sum(v for k, v in stats.items() if k not in ('statements', 'outputs'))
+    return sum(v for k, v in stats.items() if k in S._NAMES.values())

@@ -1,17 +1,23 @@
 // awegpu_kernels.cu — sm_100a kernels and C ABI (include/awegpu.h) of the collocation g / jac_g
-// evaluator.  Compiled once per model spec: the node arithmetic comes from the generated
-// node_coll.inc / node_shoot.inc (awebox_b200/codegen.py); everything else here is hand-written.
+// evaluator.  Compiled once per model spec: the node arithmetic comes from the generated, already
+// scheduled and register-allocated k_*.inc files (awebox_b200/codegen.py, awebox_b200/schedule.py);
+// everything else here is hand-written.
 //
 // Work decomposition:
-//   grid  = (ceil(B / TILE), n_k)            one CTA = TILE OCP instances x one collocation interval k
-//   block = 32 * (d + 1) threads             warp j < d : collocation node (k, j)  (lane = instance)
-//                                            warp d     : shooting node k, continuity rows of k, constant
-//                                                         Jacobian entries, periodicity rows (k = n_k-1)
-// The interval's slice of V (x_k u_k xdot_k z_k {x,z}_{k,0..d-1} x_{k+1}, contiguous in V:
-// awebox/ocp/var_struct.py:49-93) is staged into shared memory with coalesced loads, one padded row
-// per instance (odd row stride -> conflict-free lane-strided FP64 reads), together with theta, theta0
-// and phi.  Each lane then runs the straight-line FP64 node function on its instance and writes
-// residual rows and Jacobian entries straight into their CCS slots through the per-(k,j) slot table.
+//   coll kernel   grid = (ceil(B/32), n_k), block = 32*d threads
+//                 warp j = collocation node (k, j), lane = OCP instance of the 32-instance tile
+//   shoot kernel  grid = (ceil(B/32), ceil(n_k/4)), block = 128 threads
+//                 warp  = shooting node of interval k = 4*blockIdx.y + warp, lane = instance; also
+//                 writes the continuity rows, the constant Jacobian entries of its interval and the
+//                 periodicity rows (k = n_k-1)
+// One CTA per SM, 255 registers per thread.  Each thread runs a straight-line FP64 program of ~8600
+// operations whose working set (~420 FP64 values) does not fit the register file: the generator's
+// Belady allocation keeps 100 values in registers and moves the rest through numbered scratch slots —
+// the hot tier is a per-thread column of shared memory (slot-major, lane-minor: conflict-free), the
+// cold tier goes to local memory.  Inputs are read where the schedule needs them straight from W
+// (L1-cached sectors); results are staged 32 outputs x 32 instances at a time in shared memory and
+// written instance-major with lane = output, so that entries that are adjacent in the CCS value array
+// leave the SM in the same store instruction.
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -24,18 +30,16 @@
 #include "model_defs.h"
 
 #define TILE 32
-#ifndef AWE_MIN_BLOCKS
-#define AWE_MIN_BLOCKS 2
-#endif
 #define N_X AWE_N_X
 #define N_U AWE_N_U
 #define N_Z AWE_N_Z
 #define N_TH AWE_N_THETA
 #define N_D AWE_D
-#define N_WARPS (AWE_D + 1)
-#define N_THREADS (32 * N_WARPS)
+#define COLL_THREADS (32 * N_D)
+#define SHOOT_WARPS 4
+#define SHOOT_THREADS (32 * SHOOT_WARPS)
 
-// offsets inside the interval slab of V
+// offsets inside the interval slab of V (awebox/ocp/var_struct.py:49-93)
 #define OFF_X0 0
 #define OFF_U (N_X)
 #define OFF_XDOT (N_X + N_U)
@@ -43,20 +47,19 @@
 #define OFF_CX(j) (2 * N_X + N_U + N_Z + (j) * (N_X + N_Z))
 #define OFF_CZ(j) (OFF_CX(j) + N_X)
 #define OFF_XNEXT (2 * N_X + N_U + N_Z + N_D * (N_X + N_Z))
-#define SLAB (OFF_XNEXT + N_X)
-#define SLAB_STRIDE (SLAB | 1)
-// per-instance globals: theta (N_TH), then [theta0; phi] (AWE_N_PARAM)
-#define GLOB (N_TH + AWE_N_PARAM)
-#define GLOB_STRIDE (GLOB | 1)
-#define XD_STRIDE (N_X | 1)
-#define SMEM_DOUBLES (TILE * SLAB_STRIDE + TILE * GLOB_STRIDE + N_D * TILE * XD_STRIDE)
+#define OFF_XR(r) ((r) == 0 ? OFF_X0 : OFF_CX((r) - 1))
+
+// per-thread constants kept in shared memory: cc[0..d], 1/t_f, theta[0..n_theta)
+#define N_CST (N_D + 2 + N_TH)
+#define STG_STRIDE 33
+#define STG_DOUBLES (32 * STG_STRIDE)
 
 struct DevProblem {
     int n_v, n_p, n_g, n_k, n_theta0, n_phi, v_phi, p_theta0;
     long long nnz;
     int n_coll_out, n_shoot_out, n_shoot_eq, n_ineq, n_periodic, row_periodic, x_last, x_first;
-    const int *x_base, *theta_idx, *tf_idx, *row_shoot, *row_path, *row_cont, *row_coll, *periodic_idx;
-    const int *coll_slot, *shoot_slot, *const_slot, *const_begin;
+    const int *x_base, *theta_idx, *tf_idx, *row_cont, *periodic_idx;
+    const int *coll_dest, *shoot_dest, *const_slot, *const_begin;
     const double *const_val;
     double cscale;
 };
@@ -66,154 +69,236 @@ __constant__ double c_coeff_cont[N_D + 1];
 
 #define RSQRT(x) rsqrt(x)
 #define SIGN(x) ((double)(((x) > 0.0) - ((x) < 0.0)))
-#define PIN(i) gl[N_TH + (i)]
-#define CCIN(r) cc[r]
-#define OWNIN(r) own[r]
-#define ITF itf
 
-// --------------------------------------------------------------------------- collocation node
-__device__ __forceinline__ void node_coll(const double *__restrict__ xs, const double *__restrict__ xd,
-                                          const double *__restrict__ us, const double *__restrict__ zs,
-                                          const double *__restrict__ gl, const double (&cc)[N_D + 1],
-                                          const double (&own)[N_D + 1], const double itf,
-                                          const int *__restrict__ tab, double *__restrict__ gout, size_t gstride,
-                                          double *__restrict__ jout, size_t jstride)
-{
-#define VIN(i) ((i) < N_X ? xs[(i)] : (i) < 2 * N_X ? xd[(i) - N_X] : (i) < 2 * N_X + N_U ? us[(i) - 2 * N_X] \
-                : (i) < 2 * N_X + N_U + N_Z ? zs[(i) - 2 * N_X - N_U] : gl[(i) - 2 * N_X - N_U - N_Z])
-#define OUT(n, val)                                                        \
-    do {                                                                   \
-        if ((n) < AWE_N_EQ) {                                              \
-            gout[(size_t)(n) * gstride] = (val);                           \
-        } else if (jout) {                                                 \
-            const int sl_ = __ldg(tab + (n));                              \
-            if (sl_ >= 0) jout[(size_t)sl_ * jstride] = (val);             \
-        }                                                                  \
+// ---- statement macros of the generated code -------------------------------------------------------
+// inputs: asm volatile so that the compiler neither merges the generator's reloads into one
+// long-lived register nor hoists them; the address is base register + immediate
+#define LDG_(reg, ptr) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(reg) : "l"(ptr))
+#define LDS_(reg, addr) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(reg) : "r"(addr))
+#define STS_(addr, reg) asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(reg))
+#define LD_XR(reg, r, m) LDG_(reg, w_slab + (OFF_XR(r) + (m)))
+#define LD_XO(reg, m) LDG_(reg, w_own + (m))
+#define LD_XD(reg, m) LDG_(reg, w_slab + (OFF_XDOT + (m)))
+#define LD_U(reg, c) LDG_(reg, w_slab + (OFF_U + (c)))
+#define LD_Z(reg, c) LDG_(reg, w_z + (c))
+#define LD_P(reg, i) LDG_(reg, ((i) < AWE_N_THETA0 ? p_th0 + (i) : w_phi + ((i) - AWE_N_THETA0)))
+#define LD_CC(reg, r) LDS_(reg, cst_addr + (r) * (8 * NTHR))
+#define LD_ITF(reg) LDS_(reg, cst_addr + (N_D + 1) * (8 * NTHR))
+#define LD_TH(reg, t) LDS_(reg, cst_addr + (N_D + 2 + (t)) * (8 * NTHR))
+#define LD_OWN(reg, r) reg = (own_r == (r)) ? 1.0 : 0.0
+#define SPILL_ST(slot, reg) STS_(scr_addr + (slot) * (8 * NTHR), reg)
+#define SPILL_LD(reg, slot) LDS_(reg, scr_addr + (slot) * (8 * NTHR))
+#define OVF_ST(slot, reg) ovf[slot] = reg
+#define OVF_LD(reg, slot) reg = ovf[slot]
+#define SYNC_HINT() __syncthreads()
+
+// staged output: OUT parks the value of output n for this lane's instance, FLUSH writes one chunk of
+// up to 32 outputs for the 32 instances of the tile with lane = output
+#define OUT(n, val)                                                            \
+    do {                                                                       \
+        if (BATCH_MINOR) {                                                     \
+            const int code_ = __ldg(dest + (n));                               \
+            if (valid) {                                                       \
+                if (code_ >= 0) {                                              \
+                    if (Jv) Jv[(size_t)code_ * B + b] = (val);                 \
+                } else if (code_ <= -2)                                        \
+                    G[(size_t)(-2 - code_) * B + b] = (val);                   \
+            }                                                                  \
+        } else                                                                 \
+            stg[((n) & 31) * STG_STRIDE + lane] = (val);                       \
     } while (0)
-#include "node_coll.inc"
-#undef OUT
+#define FLUSH(c, cnt)                                                          \
+    do {                                                                       \
+        if (!BATCH_MINOR) flush_chunk(stg, dest + (c) * 32, cnt, lane, n_valid, g_tile, j_tile, n_g, nnz); \
+    } while (0)
+
+__device__ __forceinline__ void flush_chunk(double *stg, const int *__restrict__ dest, const int cnt, const int lane,
+                                            const int n_valid, double *__restrict__ g_tile, double *__restrict__ j_tile,
+                                            const int n_g, const long long nnz)
+{
+    __syncwarp();
+    const int code = lane < cnt ? __ldg(dest + lane) : -1;
+    double *p = nullptr;
+    size_t stride = 0;
+    if (code >= 0) {
+        if (j_tile) p = j_tile + code, stride = (size_t)nnz;
+    } else if (code <= -2) {
+        p = g_tile + (-2 - code), stride = (size_t)n_g;
+    }
+    if (p) {
+        const double *src = stg + lane * STG_STRIDE;
+#pragma unroll 4
+        for (int i = 0; i < n_valid; ++i) p[(size_t)i * stride] = src[i];
+    }
+    __syncwarp();
 }
 
-// --------------------------------------------------------------------------- shooting node
-__device__ __forceinline__ void node_shoot(const double *__restrict__ xs, const double *__restrict__ xd,
-                                           const double *__restrict__ us, const double *__restrict__ zs,
-                                           const double *__restrict__ gl, const int *__restrict__ tab,
-                                           double *__restrict__ gout_eq, double *__restrict__ gout_ineq,
-                                           size_t gstride, double *__restrict__ jout, size_t jstride, int n_shoot_eq)
+// --------------------------------------------------------------------------- collocation nodes
+template <bool FULL, bool BATCH_MINOR>
+__global__ void __launch_bounds__(COLL_THREADS, 1)
+awegpu_coll_kernel(const DevProblem pr, const int B, const double *__restrict__ W, const double *__restrict__ P,
+                   const long long ldp, const int p_off, double *__restrict__ G, double *__restrict__ Jv)
 {
-#define OUT(n, val)                                                        \
-    do {                                                                   \
-        if ((n) < AWE_N_SHOOT_ROWS) {                                      \
-            if ((n) < n_shoot_eq) gout_eq[(size_t)(n) * gstride] = (val);  \
-            else gout_ineq[(size_t)((n) - n_shoot_eq) * gstride] = (val);  \
-        } else if (jout) {                                                 \
-            const int sl_ = __ldg(tab + (n));                              \
-            if (sl_ >= 0) jout[(size_t)sl_ * jstride] = (val);             \
-        }                                                                  \
-    } while (0)
-#include "node_shoot.inc"
-#undef OUT
-#undef VIN
-}
-
-__global__ void __launch_bounds__(N_THREADS, AWE_MIN_BLOCKS)
-awegpu_eval_kernel(const DevProblem pr, const int B, const double *__restrict__ W, const double *__restrict__ P,
-                   const long long ldp, const int p_off, double *__restrict__ G, double *__restrict__ Jv,
-                   const int batch_minor)
-{
+    constexpr int NTHR = COLL_THREADS;
+    constexpr int HOT = FULL ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT;
+    constexpr int COLD = FULL ? AWE_K_COLL_COLD : AWE_K_COLL_RES_COLD;
     extern __shared__ double smem[];
-    double *slab = smem;
-    double *glob = smem + TILE * SLAB_STRIDE;
-    double *xdot = glob + TILE * GLOB_STRIDE;
+    const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
+    const int k = blockIdx.y, b0 = blockIdx.x * TILE;
+    const int b_raw = b0 + lane;
+    const bool valid = b_raw < B;
+    const int b = valid ? b_raw : B - 1;          // surplus lanes of a ragged tile recompute the last instance
+    const int n_valid = min(TILE, B - b0);
+    const int n_g = pr.n_g;
+    const long long nnz = pr.nnz;
+    double *stg = smem + (size_t)(HOT + N_CST) * NTHR + j * STG_DOUBLES;
+    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
+    const unsigned cst_addr = (unsigned)__cvta_generic_to_shared(smem + (size_t)HOT * NTHR + tid);
+    double ovf[COLD > 0 ? COLD : 1];
 
-    const int k = blockIdx.y;
-    const int b0 = blockIdx.x * TILE;
-    const int tid = threadIdx.x;
-    const int x0 = pr.x_base[k * (N_D + 1)];
-
-    // ---- stage the interval slab of every instance of the tile (coalesced along the slab)
-    for (int e = tid; e < TILE * SLAB; e += N_THREADS) {
-        const int u = e / SLAB, o = e - u * SLAB;
-        const int b = b0 + u;
-        if (b < B) slab[u * SLAB_STRIDE + o] = __ldg(W + (size_t)b * pr.n_v + x0 + o);
-    }
-    for (int e = tid; e < TILE * GLOB; e += N_THREADS) {
-        const int u = e / GLOB, o = e - u * GLOB;
-        const int b = b0 + u;
-        if (b < B) {
-            double val;
-            if (o < N_TH)
-                val = __ldg(W + (size_t)b * pr.n_v + pr.theta_idx[k * N_TH + o]);
-            else if (o < N_TH + pr.n_theta0)
-                val = __ldg(P + (size_t)b * ldp + p_off + (o - N_TH));
-            else
-                val = __ldg(W + (size_t)b * pr.n_v + pr.v_phi + (o - N_TH - pr.n_theta0));
-            glob[u * GLOB_STRIDE + o] = val;
-        }
-    }
-    __syncthreads();
-
-    const int lane = tid & 31, warp = tid >> 5;
-    const int b = b0 + lane;
-    if (b >= B) return;
-    const double *s = slab + lane * SLAB_STRIDE;
-    const double *gl = glob + lane * GLOB_STRIDE;
-    const size_t gstride = batch_minor ? (size_t)B : 1;
-    double *gbase = batch_minor ? (G + b) : (G + (size_t)b * pr.n_g);
-    double *jbase = Jv ? (batch_minor ? (Jv + b) : (Jv + (size_t)b * pr.nnz)) : nullptr;
-    const double tf = gl[AWE_TF_LOCAL - (2 * N_X + N_U + N_Z)];
-
-    if (warp < N_D) {
-        const int j = warp;
-        double *xd = xdot + (j * TILE + lane) * XD_STRIDE;
-        double cc[N_D + 1], own[N_D + 1];
-        const double inv_h = (double)pr.n_k;
-        const double itf = 1.0 / tf;
+    const double *w = W + (size_t)b * pr.n_v;
+    const double *w_slab = w + __ldg(pr.x_base + k * (N_D + 1));
+    const double *w_own = w_slab + OFF_CX(j);
+    const double *w_z = w_own + N_X;
+    const double *w_phi = w + pr.v_phi;
+    const double *p_th0 = P + (size_t)b * ldp + p_off;
+    const int own_r = j + 1;
+    {
+        // per-lane constants: cc[r] = C[r, j+1] / h / t_f (awebox/ocp/collocation.py:225), 1/t_f, theta
+        const double itf = 1.0 / __ldg(w + __ldg(pr.tf_idx + k));
+        double *cst = smem + (size_t)HOT * NTHR + tid;
 #pragma unroll
-        for (int r = 0; r <= N_D; ++r) {
-            cc[r] = c_coeff_coll[r * (N_D + 1) + (j + 1)] * inv_h * itf;
-            own[r] = (r == j + 1) ? 1.0 : 0.0;
-        }
-        // xdot_kj = (sum_r C[r, j+1] X_r) / h / t_f      (awebox/ocp/collocation.py:225, 239-250)
-        for (int m = 0; m < N_X; ++m) {
-            double xp = c_coeff_coll[0 * (N_D + 1) + (j + 1)] * s[OFF_X0 + m];
+        for (int r = 0; r <= N_D; ++r) cst[r * NTHR] = c_coeff_coll[r * (N_D + 1) + (j + 1)] * (double)pr.n_k * itf;
+        cst[(N_D + 1) * NTHR] = itf;
 #pragma unroll
-            for (int r = 1; r <= N_D; ++r) xp += c_coeff_coll[r * (N_D + 1) + (j + 1)] * s[OFF_CX(r - 1) + m];
-            xd[m] = xp * inv_h * itf;
-        }
-        const int *tab = pr.coll_slot + (size_t)(k * N_D + j) * pr.n_coll_out;
-        node_coll(s + OFF_CX(j), xd, s + OFF_U, s + OFF_CZ(j), gl, cc, own, itf, tab,
-                  gbase + (size_t)pr.row_coll[k * N_D + j] * gstride, gstride, jbase, gstride == 1 ? 1 : (size_t)B);
+        for (int t = 0; t < N_TH; ++t) cst[(N_D + 2 + t) * NTHR] = __ldg(w + __ldg(pr.theta_idx + k * N_TH + t));
+    }
+    const int *dest = pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
+    double *g_tile = G + (size_t)b0 * n_g;
+    double *j_tile = Jv ? Jv + (size_t)b0 * nnz : nullptr;
+    __syncwarp();
+    if (FULL) {
+#include "k_coll.inc"
     } else {
-        const int *tab = pr.shoot_slot + (size_t)k * pr.n_shoot_out;
-        const size_t jstride = batch_minor ? (size_t)B : 1;
-        node_shoot(s + OFF_X0, s + OFF_XDOT, s + OFF_U, s + OFF_Z, gl, tab,
-                   gbase + (size_t)pr.row_shoot[k] * gstride, gbase + (size_t)pr.row_path[k] * gstride, gstride,
-                   jbase, jstride, pr.n_shoot_eq);
-        // continuity rows: x_{k+1} - sum_r D[r] X_r        (awebox/ocp/collocation.py:319-336)
-        double *gc = gbase + (size_t)pr.row_cont[k] * gstride;
-        for (int m = 0; m < N_X; ++m) {
-            double xf = c_coeff_cont[0] * s[OFF_X0 + m];
+#include "k_coll_res.inc"
+    }
+}
+
+// --------------------------------------------------------------------------- shooting nodes
+template <bool FULL, bool BATCH_MINOR>
+__global__ void __launch_bounds__(SHOOT_THREADS, 1)
+awegpu_shoot_kernel(const DevProblem pr, const int B, const double *__restrict__ W, const double *__restrict__ P,
+                    const long long ldp, const int p_off, double *__restrict__ G, double *__restrict__ Jv)
+{
+    constexpr int NTHR = SHOOT_THREADS;
+    constexpr int HOT = FULL ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT;
+    constexpr int COLD = FULL ? AWE_K_SHOOT_COLD : AWE_K_SHOOT_RES_COLD;
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int k_raw = blockIdx.y * SHOOT_WARPS + wid;
+    const bool k_ok = k_raw < pr.n_k;
+    const int k = k_ok ? k_raw : pr.n_k - 1;
+    const int b0 = blockIdx.x * TILE;
+    const int b_raw = b0 + lane;
+    const bool valid = k_ok && b_raw < B;
+    const int b = b_raw < B ? b_raw : B - 1;
+    const int n_valid = k_ok ? min(TILE, B - b0) : 0;
+    const int n_g = pr.n_g;
+    const long long nnz = pr.nnz;
+    double *stg = smem + (size_t)(HOT + N_CST) * NTHR + wid * STG_DOUBLES;
+    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
+    const unsigned cst_addr = (unsigned)__cvta_generic_to_shared(smem + (size_t)HOT * NTHR + tid);
+    double ovf[COLD > 0 ? COLD : 1];
+
+    const double *w = W + (size_t)b * pr.n_v;
+    const double *w_slab = w + __ldg(pr.x_base + k * (N_D + 1));
+    const double *w_own = w_slab + OFF_X0;
+    const double *w_z = w_slab + OFF_Z;
+    const double *w_phi = w + pr.v_phi;
+    const double *p_th0 = P + (size_t)b * ldp + p_off;
+    {
+        double *cst = smem + (size_t)HOT * NTHR + tid;
 #pragma unroll
-            for (int r = 1; r <= N_D; ++r) xf += c_coeff_cont[r] * s[OFF_CX(r - 1) + m];
-            gc[(size_t)m * gstride] = pr.cscale * (s[OFF_XNEXT + m] - xf);
+        for (int t = 0; t < N_TH; ++t) cst[(N_D + 2 + t) * NTHR] = __ldg(w + __ldg(pr.theta_idx + k * N_TH + t));
+    }
+    const int *dest = pr.shoot_dest + (size_t)k * pr.n_shoot_out;
+    double *g_tile = G + (size_t)b0 * n_g;
+    double *j_tile = Jv ? Jv + (size_t)b0 * nnz : nullptr;
+    __syncwarp();
+    {
+        const int own_r = -1;
+        (void)own_r;
+        if (FULL) {
+#include "k_shoot.inc"
+        } else {
+#include "k_shoot_res.inc"
         }
-        // constant Jacobian entries owned by this interval
-        if (jbase) {
-            const int e1 = pr.const_begin[k + 1];
-            for (int e = pr.const_begin[k]; e < e1; ++e)
-                jbase[(size_t)__ldg(pr.const_slot + e) * jstride] = __ldg(pr.const_val + e);
+    }
+    // ---- continuity rows  x_{k+1} - sum_r D[r] X_r   (awebox/ocp/collocation.py:319-336)
+    const int row_cont = __ldg(pr.row_cont + k);
+    if (BATCH_MINOR) {
+        if (valid)
+            for (int m = 0; m < N_X; ++m) {
+                double xf = c_coeff_cont[0] * __ldg(w_slab + OFF_X0 + m);
+#pragma unroll
+                for (int r = 1; r <= N_D; ++r) xf += c_coeff_cont[r] * __ldg(w_slab + OFF_CX(r - 1) + m);
+                G[(size_t)(row_cont + m) * B + b] = pr.cscale * (__ldg(w_slab + OFF_XNEXT + m) - xf);
+            }
+    } else {
+        for (int m0 = 0; m0 < N_X; m0 += 32) {
+            const int cnt = min(32, N_X - m0);
+            for (int m = m0; m < m0 + cnt; ++m) {
+                double xf = c_coeff_cont[0] * __ldg(w_slab + OFF_X0 + m);
+#pragma unroll
+                for (int r = 1; r <= N_D; ++r) xf += c_coeff_cont[r] * __ldg(w_slab + OFF_CX(r - 1) + m);
+                stg[(m - m0) * STG_STRIDE + lane] = pr.cscale * (__ldg(w_slab + OFF_XNEXT + m) - xf);
+            }
+            __syncwarp();
+            if (lane < cnt) {
+                double *p = g_tile + row_cont + m0 + lane;
+                const double *src = stg + lane * STG_STRIDE;
+                for (int i = 0; i < n_valid; ++i) p[(size_t)i * n_g] = src[i];
+            }
+            __syncwarp();
         }
-        // periodicity rows  x_0 - x_{n_k-1, d-1}           (awebox/ocp/operation.py:245-267)
-        if (k == pr.n_k - 1) {
-            const double *w = W + (size_t)b * pr.n_v;
-            double *gp = gbase + (size_t)pr.row_periodic * gstride;
-            for (int n = 0; n < pr.n_periodic; ++n) {
-                const int m = __ldg(pr.periodic_idx + n);
-                gp[(size_t)n * gstride] = pr.cscale * (__ldg(w + pr.x_first + m) - s[OFF_CX(N_D - 1) + m]);
+    }
+    // ---- constant Jacobian entries owned by this interval (continuity; periodicity on the last one):
+    //      the value does not depend on the instance, lane = entry
+    if (Jv && k_ok) {
+        const int e1 = __ldg(pr.const_begin + k + 1);
+        for (int e = __ldg(pr.const_begin + k) + lane; e < e1; e += 32) {
+            const int slot = __ldg(pr.const_slot + e);
+            const double v = __ldg(pr.const_val + e);
+            if (BATCH_MINOR) {
+                for (int i = 0; i < n_valid; ++i) Jv[(size_t)slot * B + b0 + i] = v;
+            } else {
+                for (int i = 0; i < n_valid; ++i) j_tile[(size_t)i * nnz + slot] = v;
             }
         }
     }
+    // ---- periodicity rows  x_0 - x_{n_k-1, d-1}           (awebox/ocp/operation.py:245-267)
+    if (k_raw == pr.n_k - 1 && valid) {
+        for (int n = 0; n < pr.n_periodic; ++n) {
+            const int m = __ldg(pr.periodic_idx + n);
+            const double v = pr.cscale * (__ldg(w + pr.x_first + m) - __ldg(w_slab + OFF_CX(N_D - 1) + m));
+            if (BATCH_MINOR)
+                G[(size_t)(pr.row_periodic + n) * B + b] = v;
+            else
+                G[(size_t)b * n_g + pr.row_periodic + n] = v;
+        }
+    }
+}
+
+template <bool FULL>
+static constexpr size_t coll_smem_bytes()
+{
+    return sizeof(double) * ((size_t)((FULL ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT) + N_CST) * COLL_THREADS + N_D * STG_DOUBLES);
+}
+template <bool FULL>
+static constexpr size_t shoot_smem_bytes()
+{
+    return sizeof(double) *
+           ((size_t)((FULL ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT) + N_CST) * SHOOT_THREADS + SHOOT_WARPS * STG_DOUBLES);
 }
 
 // =========================================================================== host side / C ABI
@@ -340,17 +425,27 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     d.n_periodic = p->n_periodic, d.row_periodic = p->row_periodic, d.x_last = p->x_last, d.x_first = p->x_base[0];
     d.cscale = p->constraint_scale;
     const int nk = p->n_k, dd = p->d;
+    // destination codes of the node-local outputs: >= 0 slot of the CCS value array, -1 none,
+    // <= -2 row (-2 - code) of g
+    std::vector<int> coll_dest((size_t)nk * dd * p->n_coll_out), shoot_dest((size_t)nk * p->n_shoot_out);
+    for (int kj = 0; kj < nk * dd; ++kj)
+        for (int n = 0; n < p->n_coll_out; ++n)
+            coll_dest[(size_t)kj * p->n_coll_out + n] =
+                n < AWE_N_EQ ? -2 - (p->row_coll[kj] + n) : p->coll_slot[(size_t)kj * p->n_coll_out + n];
+    for (int k = 0; k < nk; ++k)
+        for (int n = 0; n < p->n_shoot_out; ++n)
+            shoot_dest[(size_t)k * p->n_shoot_out + n] =
+                n < p->n_shoot_eq                ? -2 - (p->row_shoot[k] + n)
+                : n < p->n_shoot_eq + p->n_ineq ? -2 - (p->row_path[k] + n - p->n_shoot_eq)
+                                                : p->shoot_slot[(size_t)k * p->n_shoot_out + n];
     int rc = 0;
     rc |= to_device(h, p->x_base, (size_t)nk * (dd + 1), &d.x_base);
     rc |= to_device(h, p->theta_idx, (size_t)nk * p->n_theta, &d.theta_idx);
     rc |= to_device(h, p->tf_idx, (size_t)nk, &d.tf_idx);
-    rc |= to_device(h, p->row_shoot, (size_t)nk, &d.row_shoot);
-    rc |= to_device(h, p->row_path, (size_t)nk, &d.row_path);
     rc |= to_device(h, p->row_cont, (size_t)nk, &d.row_cont);
-    rc |= to_device(h, p->row_coll, (size_t)nk * dd, &d.row_coll);
     rc |= to_device(h, p->periodic_idx, (size_t)p->n_periodic, &d.periodic_idx);
-    rc |= to_device(h, p->coll_slot, (size_t)nk * dd * p->n_coll_out, &d.coll_slot);
-    rc |= to_device(h, p->shoot_slot, (size_t)nk * p->n_shoot_out, &d.shoot_slot);
+    rc |= to_device(h, coll_dest.data(), coll_dest.size(), &d.coll_dest);
+    rc |= to_device(h, shoot_dest.data(), shoot_dest.size(), &d.shoot_dest);
     rc |= to_device(h, p->const_slot, (size_t)p->n_const, &d.const_slot);
     rc |= to_device(h, p->const_begin, (size_t)nk + 1, &d.const_begin);
     rc |= to_device(h, p->const_val, (size_t)p->n_const, &d.const_val);
@@ -362,8 +457,16 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
-    CK(cudaFuncSetAttribute(awegpu_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)(SMEM_DOUBLES * sizeof(double))));
+#define SET_SMEM(kern, bytes) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
+    SET_SMEM((awegpu_coll_kernel<true, false>), coll_smem_bytes<true>());
+    SET_SMEM((awegpu_coll_kernel<true, true>), coll_smem_bytes<true>());
+    SET_SMEM((awegpu_coll_kernel<false, false>), coll_smem_bytes<false>());
+    SET_SMEM((awegpu_coll_kernel<false, true>), coll_smem_bytes<false>());
+    SET_SMEM((awegpu_shoot_kernel<true, false>), shoot_smem_bytes<true>());
+    SET_SMEM((awegpu_shoot_kernel<true, true>), shoot_smem_bytes<true>());
+    SET_SMEM((awegpu_shoot_kernel<false, false>), shoot_smem_bytes<false>());
+    SET_SMEM((awegpu_shoot_kernel<false, true>), shoot_smem_bytes<false>());
+#undef SET_SMEM
     // host copies of pointers are not kept: null them so nobody dereferences caller memory later
     h->host.x_base = h->host.x_next = h->host.u_base = h->host.xdot_base = h->host.z_base = nullptr;
     return 0;
@@ -413,13 +516,23 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
         p_off = h->dp.p_theta0;
     }
     double *jv = (flags & AWEGPU_SKIP_JAC) ? nullptr : Jv;
-    dim3 grid((B + TILE - 1) / TILE, h->dp.n_k);
+    const bool full = jv != nullptr, bm = (flags & AWEGPU_JAC_BATCH_MINOR) != 0;
+    const int tiles = (B + TILE - 1) / TILE;
+    dim3 gc(tiles, h->dp.n_k), gs(tiles, (h->dp.n_k + SHOOT_WARPS - 1) / SHOOT_WARPS);
     CK(cudaEventRecord(h->ev0, st));
-    awegpu_eval_kernel<<<grid, N_THREADS, SMEM_DOUBLES * sizeof(double), st>>>(
-        h->dp, B, W, P, ldp, p_off, G, jv, (flags & AWEGPU_JAC_BATCH_MINOR) ? 1 : 0);
+#define LAUNCH(F, M)                                                                                               \
+    do {                                                                                                           \
+        awegpu_coll_kernel<F, M><<<gc, COLL_THREADS, coll_smem_bytes<F>(), st>>>(h->dp, B, W, P, ldp, p_off, G, jv);   \
+        awegpu_shoot_kernel<F, M><<<gs, SHOOT_THREADS, shoot_smem_bytes<F>(), st>>>(h->dp, B, W, P, ldp, p_off, G, jv); \
+    } while (0)
+    if (full && !bm) LAUNCH(true, false);
+    else if (full && bm) LAUNCH(true, true);
+    else if (!full && !bm) LAUNCH(false, false);
+    else LAUNCH(false, true);
+#undef LAUNCH
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
-    h->launches += 1;
+    h->launches += 2;
     h->last_ms = -2.f;
     return 0;
 }

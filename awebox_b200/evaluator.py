@@ -148,6 +148,10 @@ class Evaluator(object):
             flags |= cabi.AWEGPU_SKIP_JAC
         if stream is None:
             stream = torch.cuda.current_stream(W.device).cuda_stream
+        if not stream:
+            # torch's default stream is the legacy NULL stream; the C ABI reads NULL as "the handle's own
+            # stream", so name the legacy stream explicitly (cudaStreamLegacy) to stay ordered with torch
+            stream = 1
         rc = self.lib.awegpu_eval_batch(self.handle, B, W.data_ptr(), P.data_ptr(), G.data_ptr(),
                                         Jv.data_ptr() if Jv is not None else None, flags, C.c_void_p(stream))
         self._check(rc, 'awegpu_eval_batch')

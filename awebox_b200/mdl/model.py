@@ -407,7 +407,8 @@ class NodeModel(object):
         for kite in arch.kite_nodes:
             lab = arch.node_label(kite)
             if dof == 6:
-                f_earth, m_body = self.six_dof_aero(kite)
+                with S.region('aero%d' % kite):
+                    f_earth, m_body = self.six_dof_aero(kite)
                 moments[lab] = gamma * self.si('u', 'm_fict' + lab) + m_body
             else:
                 f_earth = self.three_dof_aero(kite)
@@ -539,24 +540,25 @@ class NodeModel(object):
         s_grid = np.linspace(0.5 * ds, 1 - 0.5 * ds, n_elements)
         f_up, f_low = S.zeros(3), S.zeros(3)
         for e in range(n_elements):
-            lo_phi, up_phi = float(e) / float(n_elements), float(e + 1) / float(n_elements)
-            q_l = q_bot + (q_top - q_bot) * lo_phi
-            q_u = q_bot + (q_top - q_bot) * up_phi
-            dq_l = dq_bot + (dq_top - dq_bot) * lo_phi
-            dq_u = dq_bot + (dq_top - dq_bot) * up_phi
-            zz = ((q_u + q_l) / 2.)[2]
-            ua = self.wind_velocity(zz) - (dq_u + dq_l) / 2.
-            eps = 1.e-6
-            ua_norm = self.smooth_norm(ua, eps)
-            ehat = ua / ua_norm
-            tether = q_u - q_l
-            length_sq = S.dot(tether, tether)
-            length_par = S.dot(tether, ehat)
-            length_perp = self.smooth_sqrt(length_sq - S.power(length_par, 2.), eps ** 2.)
-            drag_mag = cd * 0.5 * self.density(zz) * ua_norm * diam * length_perp
-            drag = S.vec([drag_mag * ua[i] for i in range(3)])
-            f_up = f_up + float(s_grid[e]) * drag
-            f_low = f_low + float(1 - s_grid[e]) * drag
+            with S.region('tether%d_elem%d' % (upper, e)):
+                lo_phi, up_phi = float(e) / float(n_elements), float(e + 1) / float(n_elements)
+                q_l = q_bot + (q_top - q_bot) * lo_phi
+                q_u = q_bot + (q_top - q_bot) * up_phi
+                dq_l = dq_bot + (dq_top - dq_bot) * lo_phi
+                dq_u = dq_bot + (dq_top - dq_bot) * up_phi
+                zz = ((q_u + q_l) / 2.)[2]
+                ua = self.wind_velocity(zz) - (dq_u + dq_l) / 2.
+                eps = 1.e-6
+                ua_norm = self.smooth_norm(ua, eps)
+                ehat = ua / ua_norm
+                tether = q_u - q_l
+                length_sq = S.dot(tether, tether)
+                length_par = S.dot(tether, ehat)
+                length_perp = self.smooth_sqrt(length_sq - S.power(length_par, 2.), eps ** 2.)
+                drag_mag = cd * 0.5 * self.density(zz) * ua_norm * diam * length_perp
+                drag = S.vec([drag_mag * ua[i] for i in range(3)])
+                f_up = f_up + float(s_grid[e]) * drag
+                f_low = f_low + float(1 - s_grid[e]) * drag
         return f_low, f_up
 
     # ---- 6-DOF kite aerodynamics (six_dof_kite.py:52-84,165-202; stability_derivatives.py:41-228;

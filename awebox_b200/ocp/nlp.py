@@ -178,6 +178,26 @@ class OcpProblem(object):
         self.coll_out = []
         for i in range(self.n_eq):
             self.coll_out.append(('res', i))
+        #   ('Xc', i, m, r): d r_i/d X_r[m] through xdot (plus the direct part when r is the node's own
+        #   block and (i, m) is also a direct dependency);  ('Xo', i, m): direct-only dependency.
+        #   Order: state component m outermost, so that everything derived from d r/d x_m and
+        #   d r/d xdot_m is emitted together (short live ranges in the generated code).
+        for mm in range(self.n_x):
+            for i in range(self.n_eq):
+                if mm in eq_split[i]['x'] and mm not in eq_split[i]['xdot']:
+                    self.coll_out.append(('Xo', i, mm))
+            for r in range(d + 1):
+                for i in range(self.n_eq):
+                    if mm in eq_split[i]['xdot']:
+                        self.coll_out.append(('Xc', i, mm, r))
+        for c in range(self.n_u):
+            for i in range(self.n_eq):
+                if c in eq_split[i]['u']:
+                    self.coll_out.append(('u', i, c))
+        for c in range(self.n_z):
+            for i in range(self.n_eq):
+                if c in eq_split[i]['z']:
+                    self.coll_out.append(('z', i, c))
         for t in range(self.n_theta):
             for i in range(self.n_eq):
                 direct = t in eq_split[i]['theta']
@@ -188,27 +208,6 @@ class OcpProblem(object):
             for i in range(self.n_eq):
                 if c in eq_split[i]['phi']:
                     self.coll_out.append(('phi', i, c))
-        #   ('Xc', i, m, r): d r_i/d X_r[m] through xdot (plus the direct part when r is the node's own
-        #   block and (i, m) is also a direct dependency);  ('Xo', i, m): direct-only dependency
-        for r in range(d + 1):
-            for mm in range(self.n_x):
-                for i in range(self.n_eq):
-                    if mm in eq_split[i]['xdot']:
-                        self.coll_out.append(('Xc', i, mm, r))
-            if r == 0:
-                for mm in range(self.n_x):
-                    for i in range(self.n_eq):
-                        if mm in eq_split[i]['x'] and mm not in eq_split[i]['xdot']:
-                            self.coll_out.append(('Xo', i, mm))
-            if r == 0:
-                for c in range(self.n_u):
-                    for i in range(self.n_eq):
-                        if c in eq_split[i]['u']:
-                            self.coll_out.append(('u', i, c))
-        for c in range(self.n_z):
-            for i in range(self.n_eq):
-                if c in eq_split[i]['z']:
-                    self.coll_out.append(('z', i, c))
         self.eq_split = eq_split
 
         # ---- shooting-node local outputs: residual rows then direct entries

@@ -1,0 +1,283 @@
+"""Instruction scheduling and register / scratch allocation for the emitted node functions.
+
+The node functions are straight-line FP64 programs of several thousand operations whose natural
+(depth-first) order keeps ~500 values alive at once — far more than the 255 32-bit registers of an
+sm_100a thread.  Left to ptxas, the excess goes to local memory (L1/L2 traffic, which made kernel v1
+L2-bound).  This module is the code generator's own back end:
+
+* ``order``      — emission order: depth-first from the outputs in their (column-major) output
+                   order, with the export values of every scheduling region (``sym.region``) visited
+                   first so that the values private to a region die inside it;
+* ``allocate``   — a Belady (furthest-next-use) register allocation over ``n_regs`` FP64 registers
+                   with a look-ahead window for reloads, explicit spill stores / reloads to numbered
+                   scratch slots, leaf (input) loads on demand, and output statements in output order.
+
+The result is a list of abstract instructions that ``codegen`` prints with macros
+(``SPILL_ST/SPILL_LD`` = per-thread shared-memory scratch in the CUDA kernels).  Build-time only.
+"""
+from . import sym as S
+
+
+def is_op(n):
+    return n.op not in (S.CONST, S.SYM)
+
+
+def is_leaf(n):
+    return n.op == S.SYM
+
+
+def operands(n):
+    """distinct non-constant operands of an op node."""
+    out = []
+    if n.a is not None and n.a.op != S.CONST:
+        out.append(n.a)
+    if n.b is not None and n.b.op != S.CONST and n.b is not n.a:
+        out.append(n.b)
+    return out
+
+
+def order(outputs):
+    """-> list of op nodes, dependencies first."""
+    ops = [n for n in S.topo(outputs) if is_op(n)]
+    users = {}
+    for n in ops:
+        for c in operands(n):
+            users.setdefault(c.idx, []).append(n)
+    outset = set(e.idx for e in outputs)
+    regions = sorted(set(n.reg for n in ops if n.reg != 0))
+    roots = []
+    for r in regions:
+        name = S.region_name(r)
+        if not name.startswith('tether'):
+            continue            # only additive, mutually independent regions are worth front-loading
+        roots += [n for n in ops if n.reg == r and (n.idx in outset or any(u.reg != r for u in users.get(n.idx, [])))]
+    seq = [n for n in S.topo(roots + list(outputs)) if is_op(n)]
+    assert len(seq) == len(ops)
+    return seq
+
+
+class Program(object):
+    """abstract instruction list:
+        ('leaf', reg, node)         reg <- load of an input leaf
+        ('op', reg, node, srcs)     reg <- node.op(srcs...)   srcs: register numbers or Expr constants
+        ('st', slot, reg)           scratch[slot] <- reg
+        ('ld', reg, slot)           reg <- scratch[slot]
+        ('out', n, src)             output n <- register number or constant Expr
+    """
+
+    def __init__(self):
+        self.ins = []
+        self.n_regs = 0
+        self.n_slots = 0
+        self.stats = {}
+
+
+def allocate(outputs, n_regs, lookahead=12, seq=None):
+    seq = order(outputs) if seq is None else seq
+    # ---- schedule with output statements in output order
+    pos_of = {n.idx: i for i, n in enumerate(seq)}
+    sched = []          # ('op', node) | ('out', n, expr)
+    out_iter = 0
+    n_out = len(outputs)
+
+    def ready(e, upto):
+        return (not is_op(e)) or pos_of[e.idx] <= upto
+
+    for i, n in enumerate(seq):
+        sched.append(('op', n))
+        while out_iter < n_out and ready(outputs[out_iter], i):
+            sched.append(('out', out_iter, outputs[out_iter]))
+            out_iter += 1
+    if not seq:
+        while out_iter < n_out:
+            sched.append(('out', out_iter, outputs[out_iter]))
+            out_iter += 1
+    assert out_iter == n_out
+
+    def srcs_of(item):
+        if item[0] == 'op':
+            return operands(item[1])
+        e = item[2]
+        return [] if e.op == S.CONST else [e]
+
+    uses = {}
+    for i, item in enumerate(sched):
+        for v in srcs_of(item):
+            uses.setdefault(v.idx, []).append(i)
+    ptr = {}
+
+    def next_use(v, i):
+        """first use position >= i (inf if none)."""
+        u = uses.get(v)
+        if not u:
+            return 1 << 30
+        p = ptr.get(v, 0)
+        while p < len(u) and u[p] < i:
+            p += 1
+        ptr[v] = p
+        return u[p] if p < len(u) else 1 << 30
+
+    prog = Program()
+    ins = prog.ins
+    reg_of = {}                 # value idx -> register
+    val_in = [None] * n_regs    # register -> value idx
+    free_regs = list(range(n_regs - 1, -1, -1))
+    node_of = {}
+    slot_of = {}                # value idx -> scratch slot (while stored)
+    free_slots = []
+    n_slots = [0]
+    counts = {'st': 0, 'ld': 0, 'leaf': 0, 'op': 0}
+    peak_slots = [0]
+
+    def take_slot():
+        if free_slots:
+            free_slots.sort(reverse=True)
+            return free_slots.pop()
+        n_slots[0] += 1
+        return n_slots[0] - 1
+
+    def evict(i, pinned):
+        best, best_use = None, -1
+        for r in range(n_regs):
+            v = val_in[r]
+            if v is None or v in pinned:
+                continue
+            nu = next_use(v, i)
+            if nu > best_use:
+                best, best_use = r, nu
+        if best is None:
+            raise RuntimeError('register allocation failed: %d registers are not enough' % n_regs)
+        v = val_in[best]
+        if best_use < (1 << 30) and is_op(node_of[v]) and v not in slot_of:
+            s = take_slot()
+            slot_of[v] = s
+            ins.append(('st', s, best))
+            counts['st'] += 1
+            peak_slots[0] = max(peak_slots[0], len(slot_of))
+        del reg_of[v]
+        val_in[best] = None
+        return best
+
+    def get_reg(i, pinned):
+        if free_regs:
+            return free_regs.pop()
+        return evict(i, pinned)
+
+    def bring(v_node, i, pinned):
+        v = v_node.idx
+        if v in reg_of:
+            return
+        node_of[v] = v_node
+        r = get_reg(i, pinned)
+        if is_leaf(v_node):
+            ins.append(('leaf', r, v_node))
+            counts['leaf'] += 1
+        else:
+            ins.append(('ld', r, slot_of[v]))
+            counts['ld'] += 1
+        reg_of[v] = r
+        val_in[r] = v
+
+    def release_dead(vals, i):
+        for v_node in vals:
+            v = v_node.idx
+            if next_use(v, i + 1) == (1 << 30):
+                r = reg_of.pop(v, None)
+                if r is not None:
+                    val_in[r] = None
+                    free_regs.append(r)
+                s = slot_of.pop(v, None)
+                if s is not None:
+                    free_slots.append(s)
+
+    n_sched = len(sched)
+    for i, item in enumerate(sched):
+        # values needed in the look-ahead window are pinned; reloads for the far end are issued now
+        window = sched[i:min(n_sched, i + lookahead + 1)]
+        pinned = set()
+        for it in window:
+            for v in srcs_of(it):
+                pinned.add(v.idx)
+        if i + lookahead < n_sched:
+            for v in srcs_of(sched[i + lookahead]):
+                produced_later = is_op(v) and v.idx not in reg_of and v.idx not in slot_of
+                if not produced_later:
+                    bring(v, i, pinned)
+        src = srcs_of(item)
+        for v in src:
+            if v.idx not in reg_of:
+                bring(v, i, pinned)
+        if item[0] == 'op':
+            n = item[1]
+            node_of[n.idx] = n
+            regs = []
+            for c in (n.a, n.b):
+                if c is None:
+                    continue
+                regs.append(c if c.op == S.CONST else reg_of[c.idx])
+            release_dead(src, i)
+            if next_use(n.idx, i + 1) == (1 << 30):
+                # dead value (cannot happen for a reachable node) — still needs a destination
+                pass
+            r = get_reg(i + 1, pinned)
+            reg_of[n.idx] = r
+            val_in[r] = n.idx
+            ins.append(('op', r, n, regs))
+            counts['op'] += 1
+        else:
+            e = item[2]
+            ins.append(('out', item[1], e if e.op == S.CONST else reg_of[e.idx]))
+            release_dead(src, i)
+    prog.n_regs = n_regs
+    prog.n_slots = n_slots[0]
+    prog.stats = dict(counts, n_slots=n_slots[0], peak_live_slots=peak_slots[0], n_regs=n_regs, lookahead=lookahead)
+    return prog
+
+
+def interpret(prog, leaf_value, n_out):
+    """reference interpreter of an allocated program (host-side test of the allocator)."""
+    import math
+    regs = [None] * prog.n_regs
+    scratch = {}
+    out = [None] * n_out
+
+    def val(s):
+        return s.val if isinstance(s, S.Expr) else regs[s]
+
+    for it in prog.ins:
+        k = it[0]
+        if k == 'leaf':
+            regs[it[1]] = leaf_value(it[2])
+        elif k == 'ld':
+            regs[it[1]] = scratch[it[2]]
+        elif k == 'st':
+            scratch[it[1]] = regs[it[2]]
+        elif k == 'out':
+            out[it[1]] = val(it[2])
+        else:
+            n, srcs = it[2], it[3]
+            a = val(srcs[0])
+            b = val(srcs[1]) if len(srcs) > 1 else None
+            op = n.op
+            if op == S.ADD: r = a + b
+            elif op == S.SUB: r = a - b
+            elif op == S.MUL: r = a * b
+            elif op == S.DIV: r = a / b
+            elif op == S.NEG: r = -a
+            elif op == S.SQRT: r = math.sqrt(a)
+            elif op == S.RSQRT: r = 1.0 / math.sqrt(a)
+            elif op in (S.POW, S.POWC): r = math.pow(a, b)
+            elif op == S.SIN: r = math.sin(a)
+            elif op == S.COS: r = math.cos(a)
+            elif op == S.TAN: r = math.tan(a)
+            elif op == S.ATAN: r = math.atan(a)
+            elif op == S.ASIN: r = math.asin(a)
+            elif op == S.ACOS: r = math.acos(a)
+            elif op == S.ATAN2: r = math.atan2(a, b)
+            elif op == S.EXP: r = math.exp(a)
+            elif op == S.LOG: r = math.log(a)
+            elif op == S.FABS: r = abs(a)
+            elif op == S.SIGN: r = float((a > 0) - (a < 0))
+            else: raise NotImplementedError(op)
+            regs[it[1]] = r
+    return out

@@ -27,15 +27,19 @@ _NAMES = {ADD: '+', SUB: '-', MUL: '*', DIV: '/', NEG: 'neg', SQRT: 'sqrt', POWC
 
 _table = {}
 _count = [0]
+# scheduling region of newly created nodes (see ``region``); 0 = no region
+_region = [0]
+_region_names = ['']
 
 
 class Expr(object):
-    __slots__ = ('op', 'a', 'b', 'val', 'name', 'idx', '__weakref__')
+    __slots__ = ('op', 'a', 'b', 'val', 'name', 'idx', 'reg', '__weakref__')
     __array_priority__ = 100.0
 
     def __init__(self, op, a=None, b=None, val=None, name=None):
         self.op, self.a, self.b, self.val, self.name = op, a, b, val, name
         self.idx = _count[0]
+        self.reg = _region[0]
         _count[0] += 1
 
     # ---- arithmetic (numpy object arrays broadcast elementwise; numpy scalars defer to us)
@@ -74,6 +78,30 @@ class Expr(object):
 
     def __deepcopy__(self, memo):
         return self
+
+
+class region(object):
+    """``with region('tether_elem_3'):`` — every node first created inside the block is tagged with a
+    new region id.  Regions are a hint for the code generator's scheduler only (nodes of one region are
+    emitted together, so the values private to the region die inside it); ``jacobian`` gives the
+    derivative nodes of a tagged node the same tag.  Nested blocks: innermost wins."""
+
+    def __init__(self, name):
+        _region_names.append(name)
+        self.rid = len(_region_names) - 1
+
+    def __enter__(self):
+        self.prev = _region[0]
+        _region[0] = self.rid
+        return self
+
+    def __exit__(self, *a):
+        _region[0] = self.prev
+        return False
+
+
+def region_name(rid):
+    return _region_names[rid]
 
 
 def _bc(o, f):
@@ -378,6 +406,7 @@ def jacobian(exprs, xs):
         db = D.get(n.b.idx) if n.b is not None else None
         if not da and not db:
             continue
+        saved, _region[0] = _region[0], n.reg
         pa, pb = partials(n)
         d = {}
         if da and not pa.is_zero():
@@ -387,6 +416,7 @@ def jacobian(exprs, xs):
             for j, v in db.items():
                 t = mul(pb, v)
                 d[j] = add(d[j], t) if j in d else t
+        _region[0] = saved
         d = {j: v for j, v in d.items() if not v.is_zero()}
         if d:
             D[n.idx] = d
@@ -442,10 +472,13 @@ def substitute(exprs, mapping):
             continue
         if n.op in (CONST, SYM):
             env[n.idx] = n
-        elif n.b is None:
+            continue
+        saved, _region[0] = _region[0], n.reg
+        if n.b is None:
             env[n.idx] = _rebuild(n.op, env[n.a.idx], None)
         else:
             env[n.idx] = _rebuild(n.op, env[n.a.idx], env[n.b.idx])
+        _region[0] = saved
     return [env[e.idx] for e in flat]
 
 

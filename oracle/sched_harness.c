@@ -1,0 +1,88 @@
+/* sched_harness.c — CPU harness for the SCHEDULED node programs (k_*.inc).  TEST INFRASTRUCTURE.
+ *
+ * The CUDA kernels include k_coll.inc / k_shoot.inc (register-allocated, explicit scratch traffic,
+ * staged outputs; awebox_b200/schedule.py).  This file compiles the very same text for the host with
+ * array-backed macros, so that the allocator and the emission can be checked against the plain
+ * emission (node_coll.inc / node_shoot.inc, used by awebox_oracle.c) without a GPU.
+ *
+ *   gcc -O1 -ffp-contract=off -shared -fPIC -I<gen dir> oracle/sched_harness.c
+ */
+#include <math.h>
+#include <string.h>
+#include "model_defs.h"
+
+#define RSQRT(x) (1.0 / sqrt(x))
+#define SIGN(x) (((x) > 0.0) - ((x) < 0.0))
+#define N_D AWE_D
+#define N_X AWE_N_X
+
+#define LD_XR(reg, r, m) reg = xr[(r) * N_X + (m)]
+#define LD_XO(reg, m) reg = xo[m]
+#define LD_XD(reg, m) reg = xd[m]
+#define LD_U(reg, c) reg = u[c]
+#define LD_Z(reg, c) reg = z[c]
+#define LD_P(reg, i) reg = p[i]
+#define LD_CC(reg, r) reg = cc[r]
+#define LD_ITF(reg) reg = itf
+#define LD_TH(reg, t) reg = th[t]
+#define LD_OWN(reg, r) reg = (own_r == (r)) ? 1.0 : 0.0
+#define SPILL_ST(slot, reg) hot[slot] = reg
+#define SPILL_LD(reg, slot) reg = hot[slot]
+#define OVF_ST(slot, reg) cold[slot] = reg
+#define OVF_LD(reg, slot) reg = cold[slot]
+#define SYNC_HINT()
+#define OUT(n, val) out[n] = (val)
+#define FLUSH(c, cnt)
+
+/* xr [(d+1)*n_x] state blocks of the interval, xo [n_x] own block, u, z, th, p [n_param],
+ * cc [d+1], itf, own_r in 1..d */
+void sched_coll(const double *xr, const double *xo, const double *u, const double *z, const double *th,
+                const double *p, const double *cc, double itf, int own_r, double *out, int full)
+{
+    double hot[512], cold[512];
+    const double *xd = 0;
+    (void)xd;
+    if (full) {
+#include "k_coll.inc"
+    } else {
+#include "k_coll_res.inc"
+    }
+}
+
+void sched_shoot(const double *xo, const double *xd, const double *u, const double *z, const double *th,
+                 const double *p, double *out, int full)
+{
+    double hot[512], cold[512];
+    const double *xr = 0, *cc = 0;
+    const double itf = 0.0;
+    const int own_r = -1;
+    (void)xr, (void)cc, (void)itf, (void)own_r;
+    if (full) {
+#include "k_shoot.inc"
+    } else {
+#include "k_shoot_res.inc"
+    }
+}
+
+/* plain emission, same calling convention as awebox_oracle.c */
+#undef OUT
+#define VIN(i) v[i]
+#define PIN(i) p[i]
+#define CCIN(r) cc[r]
+#define OWNIN(r) own[r]
+#define ITF itf
+#define OUT(n, val) out[n] = (val)
+void plain_coll(const double *v, const double *p, const double *cc, const double *own, double itf, double *out)
+{
+#include "node_coll.inc"
+}
+void plain_shoot(const double *v, const double *p, double *out)
+{
+#include "node_shoot.inc"
+}
+int harness_dims(int *n_coll_out, int *n_shoot_out)
+{
+    *n_coll_out = AWE_N_COLL_OUT;
+    *n_shoot_out = AWE_N_SHOOT_OUT;
+    return 0;
+}
