@@ -35,7 +35,8 @@ def _fmt(v):
 # between two CTA-wide re-convergence points (instruction-cache locality)
 N_REGS = 100
 LOOKAHEAD = 8
-HOT_SLOTS = 176
+HOT_SLOTS = 86
+CHUNK = 16          # outputs staged per flush
 SYNC_EVERY = 512
 
 
@@ -43,9 +44,9 @@ def _rhs(op, a, b):
     if op == S.ADD: return '%s + %s' % (a, b)
     if op == S.SUB: return '%s - %s' % (a, b)
     if op == S.MUL: return '%s * %s' % (a, b)
-    if op == S.DIV: return '%s / %s' % (a, b)
+    if op == S.DIV: return 'DIVF(%s, %s)' % (a, b)
     if op == S.NEG: return '-%s' % a
-    if op == S.SQRT: return 'sqrt(%s)' % a
+    if op == S.SQRT: return 'SQRTF(%s)' % a
     if op == S.RSQRT: return 'RSQRT(%s)' % a
     if op in (S.POWC, S.POW): return 'pow(%s, %s)' % (a, b)
     if op == S.ATAN2: return 'atan2(%s, %s)' % (a, b)
@@ -176,7 +177,7 @@ class NodeCode(object):
         self.k_coll = S.substitute(self.coll_exprs, coll_map)
         self.k_shoot = S.substitute(self.shoot_exprs, shoot_map)
 
-    def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=32):
+    def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=CHUNK):
         """-> (text, stats): register-allocated straight-line code (awebox_b200/schedule.py) printed
         with statement macros:
             LD_XR(reg, r, m) LD_XO(reg, m) LD_XD(reg, m) LD_U(reg, c) LD_Z(reg, c) LD_TH(reg, t)
@@ -310,6 +311,7 @@ class NodeCode(object):
             up = name.upper()
             kdefs += '#define AWE_%s_HOT %d\n#define AWE_%s_COLD %d\n#define AWE_%s_CHUNKS %d\n' % (
                 up, st['hot_slots'], up, st['cold_slots'], up, st['chunks'])
+        kdefs += '#define AWE_CHUNK %d\n' % CHUNK
         files['model_defs.h'] = head + kdefs
         return files, stats
 

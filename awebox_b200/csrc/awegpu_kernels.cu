@@ -51,8 +51,10 @@
 
 // per-thread constants kept in shared memory: cc[0..d], 1/t_f, theta[0..n_theta)
 #define N_CST (N_D + 2 + N_TH)
+// output staging: AWE_CHUNK outputs x 32 instances per warp, row stride odd (conflict-free both ways)
 #define STG_STRIDE 33
-#define STG_DOUBLES (32 * STG_STRIDE)
+#define STG_DOUBLES (AWE_CHUNK * STG_STRIDE)
+#define CTAS_PER_SM 2
 
 struct DevProblem {
     int n_v, n_p, n_g, n_k, n_theta0, n_phi, v_phi, p_theta0;
@@ -67,8 +69,44 @@ struct DevProblem {
 __constant__ double c_coeff_coll[(N_D + 1) * (N_D + 1)];
 __constant__ double c_coeff_cont[N_D + 1];
 
-#define RSQRT(x) rsqrt(x)
 #define SIGN(x) ((double)(((x) > 0.0) - ((x) < 0.0)))
+// Reciprocal / reciprocal square root from the MUFU seed (>= 20 bits) and two Newton steps, without
+// the special-case paths of the CUDA library versions (their arguments here are norms, squared
+// norms + eps, densities, times: finite, normal and positive).  Division and square root get one
+// extra residual correction, which leaves them within 1 ulp of the correctly rounded result.
+__device__ __forceinline__ double rcp_nr(const double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double div_nr(const double a, const double b)
+{
+    const double r = rcp_nr(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+__device__ __forceinline__ double rsqrt_nr(const double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(y * 0.5, e, y);
+    e = fma(-x * y, y, 1.0);
+    return fma(y * 0.5, e, y);
+}
+__device__ __forceinline__ double sqrt_nr(const double x)
+{
+    const double y = rsqrt_nr(x);
+    const double s = x * y;
+    return fma(fma(-s, s, x), 0.5 * y, s);
+}
+#define RSQRT(x) rsqrt_nr(x)
+#define SQRTF(x) sqrt_nr(x)
+#define DIVF(a, b) div_nr(a, b)
 
 // ---- statement macros of the generated code -------------------------------------------------------
 // inputs: asm volatile so that the compiler neither merges the generator's reloads into one
@@ -105,19 +143,24 @@ __constant__ double c_coeff_cont[N_D + 1];
                     G[(size_t)(-2 - code_) * B + b] = (val);                   \
             }                                                                  \
         } else                                                                 \
-            stg[((n) & 31) * STG_STRIDE + lane] = (val);                       \
+            stg[((n) % AWE_CHUNK) * STG_STRIDE + lane] = (val);                       \
     } while (0)
 #define FLUSH(c, cnt)                                                          \
     do {                                                                       \
-        if (!BATCH_MINOR) flush_chunk(stg, dest + (c) * 32, cnt, lane, n_valid, g_tile, j_tile, n_g, nnz); \
+        if (!BATCH_MINOR) flush_chunk(stg, dest + (c) * AWE_CHUNK, cnt, lane, n_valid, g_tile, j_tile, n_g, nnz); \
     } while (0)
 
+// lane = (instance group, output): output o = lane % AWE_CHUNK of the chunk, instances i = lane / AWE_CHUNK,
+// + 32 / AWE_CHUNK, ...: every store instruction writes AWE_CHUNK neighbouring outputs of 32 / AWE_CHUNK
+// instances
 __device__ __forceinline__ void flush_chunk(double *stg, const int *__restrict__ dest, const int cnt, const int lane,
                                             const int n_valid, double *__restrict__ g_tile, double *__restrict__ j_tile,
                                             const int n_g, const long long nnz)
 {
+    constexpr int GROUPS = 32 / AWE_CHUNK;
     __syncwarp();
-    const int code = lane < cnt ? __ldg(dest + lane) : -1;
+    const int o = lane % AWE_CHUNK, i0 = lane / AWE_CHUNK;
+    const int code = o < cnt ? __ldg(dest + o) : -1;
     double *p = nullptr;
     size_t stride = 0;
     if (code >= 0) {
@@ -126,16 +169,16 @@ __device__ __forceinline__ void flush_chunk(double *stg, const int *__restrict__
         p = g_tile + (-2 - code), stride = (size_t)n_g;
     }
     if (p) {
-        const double *src = stg + lane * STG_STRIDE;
+        const double *src = stg + o * STG_STRIDE;
 #pragma unroll 4
-        for (int i = 0; i < n_valid; ++i) p[(size_t)i * stride] = src[i];
+        for (int i = i0; i < n_valid; i += GROUPS) p[(size_t)i * stride] = src[i];
     }
     __syncwarp();
 }
 
 // --------------------------------------------------------------------------- collocation nodes
 template <bool FULL, bool BATCH_MINOR>
-__global__ void __launch_bounds__(COLL_THREADS, 1)
+__global__ void __launch_bounds__(COLL_THREADS, CTAS_PER_SM)
 awegpu_coll_kernel(const DevProblem pr, const int B, const double *__restrict__ W, const double *__restrict__ P,
                    const long long ldp, const int p_off, double *__restrict__ G, double *__restrict__ Jv)
 {
@@ -186,7 +229,7 @@ awegpu_coll_kernel(const DevProblem pr, const int B, const double *__restrict__ 
 
 // --------------------------------------------------------------------------- shooting nodes
 template <bool FULL, bool BATCH_MINOR>
-__global__ void __launch_bounds__(SHOOT_THREADS, 1)
+__global__ void __launch_bounds__(SHOOT_THREADS, CTAS_PER_SM)
 awegpu_shoot_kernel(const DevProblem pr, const int B, const double *__restrict__ W, const double *__restrict__ P,
                     const long long ldp, const int p_off, double *__restrict__ G, double *__restrict__ Jv)
 {
@@ -245,8 +288,8 @@ awegpu_shoot_kernel(const DevProblem pr, const int B, const double *__restrict__
                 G[(size_t)(row_cont + m) * B + b] = pr.cscale * (__ldg(w_slab + OFF_XNEXT + m) - xf);
             }
     } else {
-        for (int m0 = 0; m0 < N_X; m0 += 32) {
-            const int cnt = min(32, N_X - m0);
+        for (int m0 = 0; m0 < N_X; m0 += AWE_CHUNK) {
+            const int cnt = min(AWE_CHUNK, N_X - m0);
             for (int m = m0; m < m0 + cnt; ++m) {
                 double xf = c_coeff_cont[0] * __ldg(w_slab + OFF_X0 + m);
 #pragma unroll
@@ -254,10 +297,13 @@ awegpu_shoot_kernel(const DevProblem pr, const int B, const double *__restrict__
                 stg[(m - m0) * STG_STRIDE + lane] = pr.cscale * (__ldg(w_slab + OFF_XNEXT + m) - xf);
             }
             __syncwarp();
-            if (lane < cnt) {
-                double *p = g_tile + row_cont + m0 + lane;
-                const double *src = stg + lane * STG_STRIDE;
-                for (int i = 0; i < n_valid; ++i) p[(size_t)i * n_g] = src[i];
+            {
+                const int o = lane % AWE_CHUNK;
+                if (o < cnt) {
+                    double *p = g_tile + row_cont + m0 + o;
+                    const double *src = stg + o * STG_STRIDE;
+                    for (int i = lane / AWE_CHUNK; i < n_valid; i += 32 / AWE_CHUNK) p[(size_t)i * n_g] = src[i];
+                }
             }
             __syncwarp();
         }

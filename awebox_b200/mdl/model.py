@@ -106,6 +106,7 @@ def generate_structure(spec, arch):
 
 
 VAR_TYPES = ['x', 'xdot', 'u', 'z', 'theta']
+SIMPLIFY_REELOUT = True
 
 
 class NodeModel(object):
@@ -336,8 +337,12 @@ class NodeModel(object):
             else:
                 dq_parent = self.si('x', 'dq' + arch.parent_label(node))
                 q_parent = self.si('x', 'q' + arch.parent_label(node))
-            e_kin = e_kin + 0.5 * seg['seg_mass'] / 3 * (S.dot(dq_node, dq_node) + S.dot(dq_parent, dq_parent)
-                                                       + S.dot(dq_node, dq_parent))
+            if node == 1 and SIMPLIFY_REELOUT:
+                # dq_parent = reelout * ehat with |ehat| = 1:  dq_parent.dq_parent = dq_node.dq_parent = reelout^2
+                e_kin = e_kin + 0.5 * seg['seg_mass'] / 3 * (S.dot(dq_node, dq_node) + 2. * (reelout * reelout))
+            else:
+                e_kin = e_kin + 0.5 * seg['seg_mass'] / 3 * (S.dot(dq_node, dq_node) + S.dot(dq_parent, dq_parent)
+                                                           + S.dot(dq_node, dq_parent))
             if node in arch.kite_nodes:
                 m_k = self.par('geometry', 'm_k')
                 e_kin = e_kin + 0.5 * m_k * S.dot(dq_node, dq_node)
@@ -596,9 +601,11 @@ class NodeModel(object):
                 if key not in self._pidx:
                     continue
                 stack = self.params[self._pidx[key]]
-                contrib = S.ZERO
-                for l in range(len(stack)):
-                    contrib = contrib + stack[l] * (inputs[iname] * S.power(alpha, float(l)))
+                # sum_l stack[l] * (input * alpha^l), evaluated as input * Horner(alpha)
+                poly = stack[len(stack) - 1]
+                for l in range(len(stack) - 2, -1, -1):
+                    poly = poly * alpha + stack[l]
+                contrib = poly if iname == '0' else inputs[iname] * poly
                 if cname in ('Cl', 'Cm', 'Cn') and iname in ('deltaa', 'deltae', 'deltar'):
                     contrib = self.par('aero', 'moment_factor') * contrib
                 total = total + contrib

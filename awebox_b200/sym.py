@@ -369,8 +369,8 @@ def partials(n):
     if op == NEG: return MONE, None
     if op == SQRT: return div(const(0.5), n), None
     if op == RSQRT: return mul(const(-0.5), div(n, a)), None
-    if op == POWC: return mul(b, power(a, const(b.val - 1.0))), ZERO
-    if op == POW: return mul(b, power(a, sub(b, ONE))), mul(log(a), n)
+    if op == POWC: return mul(b, div(n, a)), ZERO
+    if op == POW: return mul(b, div(n, a)), mul(log(a), n)       # b a^(b-1) as b a^b / a: reuses the value
     if op == SIN: return cos(a), None
     if op == COS: return neg(sin(a)), None
     if op == TAN: return add(ONE, mul(n, n)), None

@@ -31,6 +31,8 @@
 #include "model_defs.h"
 
 #define RSQRT(x) (1.0 / sqrt(x))
+#define DIVF(a, b) ((a) / (b))
+#define SQRTF(x) sqrt(x)
 #define SIGN(x) (((x) > 0.0) - ((x) < 0.0))
 
 #define VIN(i) v[i]

@@ -94,9 +94,11 @@ def test_layouts_and_parameter_modes_agree():
     G2, J2 = ev.eval(W, P[:, ocp.p_theta0:])             # theta0-only parameter block
     assert np.array_equal(G1, G2) and np.array_equal(J1, J2)
     G3, J3 = ev.eval(W, P, batch_minor=True)             # [n_g, B] / [nnz, B]
-    assert np.array_equal(G3.T, G1) and np.array_equal(J3.T, J1)
-    G4, _ = ev.eval(W, P, jac=False)
-    assert np.array_equal(G4, G1)
+    assert_parity(ocp, np.ascontiguousarray(G3.T), np.ascontiguousarray(J3.T), G0, J0)
+    G4, _ = ev.eval(W, P, jac=False)                     # residual-only kernels (their own schedule)
+    assert np.all(np.abs(G4 - G0) <= 1e-12 * np.maximum(1.0, np.abs(G0)))
+    G5, _ = ev.eval(W, P, jac=False, batch_minor=True)
+    assert np.all(np.abs(G5.T - G0) <= 1e-12 * np.maximum(1.0, np.abs(G0)))
 
 
 def test_reference_style_single_instance_calls():
