@@ -33,11 +33,11 @@ def _fmt(v):
 # back-end parameters of the CUDA emission (awebox_b200/schedule.py): FP64 registers handed to the
 # allocator, reload look-ahead (statements), shared-memory scratch slots per thread, statements
 # between two CTA-wide re-convergence points (instruction-cache locality)
-N_REGS = 100
-LOOKAHEAD = 8
-HOT_SLOTS = 86
-CHUNK = 16          # outputs staged per flush
-SYNC_EVERY = 512
+N_REGS = 48          # FP64 values the allocator keeps in registers (-> ~128 registers per thread)
+LOOKAHEAD = 8        # statements between a scratch reload and its first use
+HOT_SLOTS = 1 << 20  # no cold tier: the grouped programs need only a few dozen scratch slots
+CHUNK = 16           # outputs staged per flush
+GROUP_OPS = 1400     # operation budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
 
 
 def _rhs(op, a, b):
@@ -132,22 +132,22 @@ class NodeCode(object):
 
     # ------------------------------------------------------------------ kernel-side expressions
     def _kernel_exprs(self):
-        """The same outputs over the leaves the CUDA kernels actually read: the state blocks X_r of
-        the interval (``XR(r,m)``), the node's own block (``XO(m)``), ``UIN/ZIN/THIN/PIN`` and the per-lane
-        collocation coefficients, with ``xdot_m = sum_r cc_r X_r[m]`` (awebox/ocp/collocation.py:225,
-        239-250) part of the graph so that the scheduler sees the contraction."""
+        """The same outputs over the leaves the CUDA node kernels read from the gathered node-input
+        records (awebox_b200/csrc/awegpu_kernels.cu): ``XO(m)`` state block of the node, ``XD(m)`` its
+        time derivative (collocation nodes: contracted by the gather kernel, awebox/ocp/collocation.py:
+        225, 239-250; shooting nodes: the lifted xdot variables), ``UIN/ZIN/THIN/PIN`` and the per-lane
+        collocation coefficients ``CCIN/OWNIN/ITF`` of the chain rule."""
         ocp, m = self.ocp, self.ocp.model
         rng, d = ocp.rng, ocp.d
         leaf = {}
         self.k_leaf = leaf              # sym idx -> macro text
         xo = [S.sym('XO(%d)' % i) for i in range(ocp.n_x)]
-        xr = [[S.sym('XR(%d,%d)' % (r, i)) for i in range(ocp.n_x)] for r in range(d + 1)]
         xd = [S.sym('XD(%d)' % i) for i in range(ocp.n_x)]
         ui = [S.sym('UIN(%d)' % i) for i in range(ocp.n_u)]
         zi = [S.sym('ZIN(%d)' % i) for i in range(ocp.n_z)]
         th = [S.sym('THIN(%d)' % i) for i in range(ocp.n_theta)]
         pi = [S.sym('PIN(%d)' % i) for i in range(m.n_param)]
-        for group in (xo, xd, ui, zi, th, pi) + tuple(xr):
+        for group in (xo, xd, ui, zi, th, pi):
             for v in group:
                 leaf[v.idx] = v.name
         for r in range(d + 1):
@@ -157,6 +157,7 @@ class NodeCode(object):
         base = {}
         for i in range(ocp.n_x):
             base[m.vars[rng['x'][0] + i]] = xo[i]
+            base[m.vars[rng['xdot'][0] + i]] = xd[i]
         for i in range(ocp.n_u):
             base[m.vars[rng['u'][0] + i]] = ui[i]
         for i in range(ocp.n_z):
@@ -165,19 +166,40 @@ class NodeCode(object):
             base[m.vars[rng['theta'][0] + i]] = th[i]
         for i in range(m.n_param):
             base[m.params[i]] = pi[i]
-        coll_map = dict(base)
-        for i in range(ocp.n_x):
-            e = S.ZERO
-            for r in range(d + 1):
-                e = e + self.cc[r] * xr[r][i]
-            coll_map[m.vars[rng['xdot'][0] + i]] = e
-        shoot_map = dict(base)
-        for i in range(ocp.n_x):
-            shoot_map[m.vars[rng['xdot'][0] + i]] = xd[i]
-        self.k_coll = S.substitute(self.coll_exprs, coll_map)
-        self.k_shoot = S.substitute(self.shoot_exprs, shoot_map)
+        self.k_coll = S.substitute(self.coll_exprs, base)
+        self.k_shoot = S.substitute(self.shoot_exprs, base)
 
-    def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=CHUNK):
+    @staticmethod
+    def partition(exprs, limit):
+        """Split the output list into consecutive groups whose operation cones stay below ``limit``
+        operations.  Every group becomes a separate small program that recomputes what it shares with
+        the others: the programs of one group then fit the 32 KB instruction cache of an SM and need
+        few registers, which is what the hardware wants.  -> [(first, last+1)]"""
+        def cone(e, acc):
+            stack = [e]
+            while stack:
+                n = stack.pop()
+                if n.idx in acc or not SCH.is_op(n):
+                    continue
+                acc.add(n.idx)
+                if n.a is not None:
+                    stack.append(n.a)
+                if n.b is not None:
+                    stack.append(n.b)
+            return acc
+        groups, cur, first = [], set(), 0
+        for i, e in enumerate(exprs):
+            c = cone(e, set())
+            u = cur | c
+            if len(u) > limit and i > first:
+                groups.append((first, i))
+                cur, first = c, i
+            else:
+                cur = u
+        groups.append((first, len(exprs)))
+        return groups
+
+    def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=CHUNK, first=0):
         """-> (text, stats): register-allocated straight-line code (awebox_b200/schedule.py) printed
         with statement macros:
             LD_XR(reg, r, m) LD_XO(reg, m) LD_XD(reg, m) LD_U(reg, c) LD_Z(reg, c) LD_TH(reg, t)
@@ -226,15 +248,13 @@ class NodeCode(object):
                 lines.append('%s_ST(%d, r%d);' % (t, idx, it[2]))
             elif k == 'out':
                 n = it[1]
-                lines.append('OUT(%d, %s);' % (n, src(it[2])))
+                lines.append('OUT(%d, %s);' % (n % chunk, src(it[2])))
                 if (n + 1) % chunk == 0 or n + 1 == n_out:
-                    lines.append('FLUSH(%d, %d);' % (n // chunk, n % chunk + 1))
+                    lines.append('FLUSH(%d, %d);' % (first + (n // chunk) * chunk, n % chunk + 1))
             else:
                 r, n, srcs = it[1], it[2], it[3]
                 lines.append('r%d = %s;' % (r, _rhs(n.op, src(srcs[0]), src(srcs[1]) if len(srcs) > 1 else None)))
                 n_stmt += 1
-                if n_stmt % SYNC_EVERY == 0:
-                    lines.append('SYNC_HINT();')
         stats = dict(prog.stats)
         stats.update(S.count_ops(exprs))
         stats.update(outputs=n_out, chunks=(n_out + chunk - 1) // chunk, hot_slots=n_hot, cold_slots=n_cold,
@@ -299,18 +319,27 @@ class NodeCode(object):
         banner = '// generated by awebox_b200/codegen.py from spec "%s" -- do not edit\n' % ocp.spec.name
         files = {'model_defs.h': head, 'node_coll.inc': banner + coll, 'node_shoot.inc': banner + shoot}
         stats = {'coll': cs, 'shoot': ss}
-        # ---- CUDA emission: scheduled + register-allocated; full (g + jac_g) and residual-only variants
+        # ---- CUDA emission: grouped, scheduled, register-allocated programs; full (g + jac_g) and
+        #      residual-only variants.  File layout: ``case <g>: { ...program... } break;``
         n_sh = len(ocp.shoot_rows)
         variants = {'k_coll': self.k_coll, 'k_shoot': self.k_shoot,
                     'k_coll_res': self.k_coll[:ocp.n_eq], 'k_shoot_res': self.k_shoot[:n_sh]}
         kdefs = ''
         for name, exprs in variants.items():
-            text, st = self.emit_scheduled(exprs)
+            groups = self.partition(exprs, GROUP_OPS)
+            text, gstats = '', []
+            for g, (a, b) in enumerate(groups):
+                body, st = self.emit_scheduled(exprs[a:b], first=a)
+                text += 'case %d: {\n%s} break;\n' % (g, body)
+                st['first'], st['last'] = a, b
+                gstats.append(st)
             files[name + '.inc'] = banner + text
-            stats[name] = st
+            stats[name] = {'groups': gstats, 'n_groups': len(groups),
+                           'ops_total': sum(flops(st) for st in gstats),
+                           'hot_slots': max(st['hot_slots'] for st in gstats)}
             up = name.upper()
-            kdefs += '#define AWE_%s_HOT %d\n#define AWE_%s_COLD %d\n#define AWE_%s_CHUNKS %d\n' % (
-                up, st['hot_slots'], up, st['cold_slots'], up, st['chunks'])
+            kdefs += '#define AWE_%s_GROUPS %d\n#define AWE_%s_HOT %d\n#define AWE_%s_OPS %d\n' % (
+                up, len(groups), up, stats[name]['hot_slots'], up, stats[name]['ops_total'])
         kdefs += '#define AWE_CHUNK %d\n' % CHUNK
         files['model_defs.h'] = head + kdefs
         return files, stats

@@ -1,23 +1,25 @@
 // awegpu_kernels.cu — sm_100a kernels and C ABI (include/awegpu.h) of the collocation g / jac_g
-// evaluator.  Compiled once per model spec: the node arithmetic comes from the generated, already
+// evaluator.  Compiled once per model spec: the node arithmetic comes from the generated, grouped,
 // scheduled and register-allocated k_*.inc files (awebox_b200/codegen.py, awebox_b200/schedule.py);
 // everything else here is hand-written.
 //
-// Work decomposition:
-//   coll kernel   grid = (ceil(B/32), n_k), block = 32*d threads
-//                 warp j = collocation node (k, j), lane = OCP instance of the 32-instance tile
-//   shoot kernel  grid = (ceil(B/32), ceil(n_k/4)), block = 128 threads
-//                 warp  = shooting node of interval k = 4*blockIdx.y + warp, lane = instance; also
-//                 writes the continuity rows, the constant Jacobian entries of its interval and the
-//                 periodicity rows (k = n_k-1)
-// One CTA per SM, 255 registers per thread.  Each thread runs a straight-line FP64 program of ~8600
-// operations whose working set (~420 FP64 values) does not fit the register file: the generator's
-// Belady allocation keeps 100 values in registers and moves the rest through numbered scratch slots —
-// the hot tier is a per-thread column of shared memory (slot-major, lane-minor: conflict-free), the
-// cold tier goes to local memory.  Inputs are read where the schedule needs them straight from W
-// (L1-cached sectors); results are staged 32 outputs x 32 instances at a time in shared memory and
-// written instance-major with lane = output, so that entries that are adjacent in the CCS value array
-// leave the SM in the same store instruction.
+// Pipeline per chunk of OCP instances, all on one stream:
+//   1. awegpu_gather_kernel   grid (tiles, n_k): stages the interval slab of 32 instances in shared
+//        memory and writes the node-input records lane-contiguously (record entry i of the 32
+//        instances of a tile = one 256-byte line), contracts the collocation polynomial
+//        xdot_kj = (sum_r C[r,j] X_r) / (h t_f), writes the continuity / periodicity rows of g and the
+//        constant Jacobian entries.
+//   2. awegpu_node_kernel<coll>   grid (ceil(tiles*n_k*d / 4), groups): warp = one collocation node of a
+//        tile, lane = instance, blockIdx.y = program group.
+//   3. awegpu_node_kernel<shoot>  the same for the shooting nodes (equality subset + path inequalities).
+// A program group is a straight-line FP64 program of <= ~1400 operations that produces a consecutive
+// range of the node's outputs and recomputes what it shares with the other groups.  That keeps every
+// program below the 32 KB instruction cache of the SM (the monolithic ~9000-operation program was
+// instruction-fetch bound: one 256-byte fetch from L2 per 16 instructions, ~280 cycles each, see
+// profiles/) and its working set at ~50 registers + a few dozen scratch slots, so that 12-16 warps are
+// resident per SM.  Results are staged AWE_CHUNK outputs x 32 instances at a time in shared memory and
+// written instance-major with lane = output, so that neighbours in the CCS value array leave the SM in
+// one store instruction.
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
@@ -34,10 +36,11 @@
 #define N_U AWE_N_U
 #define N_Z AWE_N_Z
 #define N_TH AWE_N_THETA
+#define N_PHI AWE_N_PHI
 #define N_D AWE_D
-#define COLL_THREADS (32 * N_D)
-#define SHOOT_WARPS 4
-#define SHOOT_THREADS (32 * SHOOT_WARPS)
+#define NODE_WARPS 4
+#define NODE_THREADS (32 * NODE_WARPS)
+#define GATHER_THREADS 128
 
 // offsets inside the interval slab of V (awebox/ocp/var_struct.py:49-93)
 #define OFF_X0 0
@@ -48,13 +51,16 @@
 #define OFF_CZ(j) (OFF_CX(j) + N_X)
 #define OFF_XNEXT (2 * N_X + N_U + N_Z + N_D * (N_X + N_Z))
 #define OFF_XR(r) ((r) == 0 ? OFF_X0 : OFF_CX((r) - 1))
-
-// per-thread constants kept in shared memory: cc[0..d], 1/t_f, theta[0..n_theta)
-#define N_CST (N_D + 2 + N_TH)
+#define SLAB_W OFF_XNEXT                    /* slab entries that go into the record */
+#define SLAB_ALL (OFF_XNEXT + N_X)          /* + x_{k+1} (continuity rows) */
+#define SLAB_STRIDE (SLAB_ALL | 1)
+// node-input record of one (tile, interval): [slab (SLAB_W) | theta (N_TH) | phi (N_PHI)] x 32 lanes
+#define REC_TH SLAB_W
+#define REC_PHI (SLAB_W + N_TH)
+#define REC (SLAB_W + N_TH + N_PHI)
 // output staging: AWE_CHUNK outputs x 32 instances per warp, row stride odd (conflict-free both ways)
 #define STG_STRIDE 33
 #define STG_DOUBLES (AWE_CHUNK * STG_STRIDE)
-#define CTAS_PER_SM 2
 
 struct DevProblem {
     int n_v, n_p, n_g, n_k, n_theta0, n_phi, v_phi, p_theta0;
@@ -64,6 +70,13 @@ struct DevProblem {
     const int *coll_dest, *shoot_dest, *const_slot, *const_begin;
     const double *const_val;
     double cscale;
+};
+
+// side buffers of one chunk (device memory owned by the handle)
+struct Scratch {
+    double *rec;      // [tiles][n_k][REC][32]
+    double *xdc;      // [tiles][n_k][d][N_X][32]
+    double *pt;       // [tiles][n_theta0][32]
 };
 
 __constant__ double c_coeff_coll[(N_D + 1) * (N_D + 1)];
@@ -109,45 +122,34 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define DIVF(a, b) div_nr(a, b)
 
 // ---- statement macros of the generated code -------------------------------------------------------
-// inputs: asm volatile so that the compiler neither merges the generator's reloads into one
-// long-lived register nor hoists them; the address is base register + immediate
+// asm volatile: the compiler must neither merge the generator's reloads into one long-lived register
+// nor hoist them.  Record entries of the 32 lanes are 256 bytes apart: base register + immediate.
 #define LDG_(reg, ptr) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(reg) : "l"(ptr))
 #define LDS_(reg, addr) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(reg) : "r"(addr))
 #define STS_(addr, reg) asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(reg))
-#define LD_XR(reg, r, m) LDG_(reg, w_slab + (OFF_XR(r) + (m)))
-#define LD_XO(reg, m) LDG_(reg, w_own + (m))
-#define LD_XD(reg, m) LDG_(reg, w_slab + (OFF_XDOT + (m)))
-#define LD_U(reg, c) LDG_(reg, w_slab + (OFF_U + (c)))
-#define LD_Z(reg, c) LDG_(reg, w_z + (c))
-#define LD_P(reg, i) LDG_(reg, ((i) < AWE_N_THETA0 ? p_th0 + (i) : w_phi + ((i) - AWE_N_THETA0)))
-#define LD_CC(reg, r) LDS_(reg, cst_addr + (r) * (8 * NTHR))
-#define LD_ITF(reg) LDS_(reg, cst_addr + (N_D + 1) * (8 * NTHR))
-#define LD_TH(reg, t) LDS_(reg, cst_addr + (N_D + 2 + (t)) * (8 * NTHR))
-#define LD_OWN(reg, r) reg = (own_r == (r)) ? 1.0 : 0.0
-#define SPILL_ST(slot, reg) STS_(scr_addr + (slot) * (8 * NTHR), reg)
-#define SPILL_LD(reg, slot) LDS_(reg, scr_addr + (slot) * (8 * NTHR))
-#define OVF_ST(slot, reg) ovf[slot] = reg
-#define OVF_LD(reg, slot) reg = ovf[slot]
-#define SYNC_HINT() __syncthreads()
+#define LD_XO(reg, m) LDG_(reg, w_own + (m) * 32)
+#define LD_XD(reg, m) LDG_(reg, w_xd + (m) * 32)
+#define LD_U(reg, c) LDG_(reg, w_rec + (OFF_U + (c)) * 32)
+#define LD_Z(reg, c) LDG_(reg, w_z + (c) * 32)
+#define LD_TH(reg, t) LDG_(reg, w_rec + (REC_TH + (t)) * 32)
+#define LD_P(reg, i) LDG_(reg, ((i) < AWE_N_THETA0 ? w_pt + (i) * 32 : w_rec + (REC_PHI + (i) - AWE_N_THETA0) * 32))
+#define LD_CC(reg, r) reg = c_coeff_coll[(r) * (N_D + 1) + j1] * itf_nk
+#define LD_ITF(reg) reg = itf
+#define LD_OWN(reg, r) reg = (j1 == (r)) ? 1.0 : 0.0
+#define SPILL_ST(slot, reg) STS_(scr_addr + (slot) * (8 * NODE_THREADS), reg)
+#define SPILL_LD(reg, slot) LDS_(reg, scr_addr + (slot) * (8 * NODE_THREADS))
+#define OVF_ST(slot, reg) SPILL_ST(slot, reg)
+#define OVF_LD(reg, slot) SPILL_LD(reg, slot)
 
-// staged output: OUT parks the value of output n for this lane's instance, FLUSH writes one chunk of
-// up to 32 outputs for the 32 instances of the tile with lane = output
-#define OUT(n, val)                                                            \
-    do {                                                                       \
-        if (BATCH_MINOR) {                                                     \
-            const int code_ = __ldg(dest + (n));                               \
-            if (valid) {                                                       \
-                if (code_ >= 0) {                                              \
-                    if (Jv) Jv[(size_t)code_ * B + b] = (val);                 \
-                } else if (code_ <= -2)                                        \
-                    G[(size_t)(-2 - code_) * B + b] = (val);                   \
-            }                                                                  \
-        } else                                                                 \
-            stg[((n) % AWE_CHUNK) * STG_STRIDE + lane] = (val);                       \
-    } while (0)
-#define FLUSH(c, cnt)                                                          \
-    do {                                                                       \
-        if (!BATCH_MINOR) flush_chunk(stg, dest + (c) * AWE_CHUNK, cnt, lane, n_valid, g_tile, j_tile, n_g, nnz); \
+// staged output: OUT parks value number n of the current chunk for this lane's instance, FLUSH writes
+// the chunk (outputs first .. first+cnt-1 of the node) for the 32 instances of the tile
+#define OUT(n, val) stg[(n) * STG_STRIDE + lane] = (val)
+#define FLUSH(first, cnt)                                                                                   \
+    do {                                                                                                    \
+        if (BATCH_MINOR)                                                                                    \
+            flush_chunk_bm(stg, dest + (first), cnt, lane, valid, G, Jv, (size_t)B, (size_t)b);             \
+        else                                                                                                \
+            flush_chunk(stg, dest + (first), cnt, lane, n_valid, g_tile, j_tile, n_g, nnz);                 \
     } while (0)
 
 // lane = (instance group, output): output o = lane % AWE_CHUNK of the chunk, instances i = lane / AWE_CHUNK,
@@ -176,176 +178,212 @@ __device__ __forceinline__ void flush_chunk(double *stg, const int *__restrict__
     __syncwarp();
 }
 
-// --------------------------------------------------------------------------- collocation nodes
-template <bool FULL, bool BATCH_MINOR>
-__global__ void __launch_bounds__(COLL_THREADS, CTAS_PER_SM)
-awegpu_coll_kernel(const DevProblem pr, const int B, const double *__restrict__ W, const double *__restrict__ P,
-                   const long long ldp, const int p_off, double *__restrict__ G, double *__restrict__ Jv)
+// batch-minor layout (Jv[slot * B + b], G[row * B + b]): lane = instance, already coalesced
+__device__ __forceinline__ void flush_chunk_bm(double *stg, const int *__restrict__ dest, const int cnt, const int lane,
+                                               const bool valid, double *__restrict__ G, double *__restrict__ Jv,
+                                               const size_t B, const size_t b)
 {
-    constexpr int NTHR = COLL_THREADS;
-    constexpr int HOT = FULL ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT;
-    constexpr int COLD = FULL ? AWE_K_COLL_COLD : AWE_K_COLL_RES_COLD;
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x, lane = tid & 31, j = tid >> 5;
-    const int k = blockIdx.y, b0 = blockIdx.x * TILE;
-    const int b_raw = b0 + lane;
-    const bool valid = b_raw < B;
-    const int b = valid ? b_raw : B - 1;          // surplus lanes of a ragged tile recompute the last instance
-    const int n_valid = min(TILE, B - b0);
-    const int n_g = pr.n_g;
-    const long long nnz = pr.nnz;
-    double *stg = smem + (size_t)(HOT + N_CST) * NTHR + j * STG_DOUBLES;
-    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
-    const unsigned cst_addr = (unsigned)__cvta_generic_to_shared(smem + (size_t)HOT * NTHR + tid);
-    double ovf[COLD > 0 ? COLD : 1];
-
-    const double *w = W + (size_t)b * pr.n_v;
-    const double *w_slab = w + __ldg(pr.x_base + k * (N_D + 1));
-    const double *w_own = w_slab + OFF_CX(j);
-    const double *w_z = w_own + N_X;
-    const double *w_phi = w + pr.v_phi;
-    const double *p_th0 = P + (size_t)b * ldp + p_off;
-    const int own_r = j + 1;
-    {
-        // per-lane constants: cc[r] = C[r, j+1] / h / t_f (awebox/ocp/collocation.py:225), 1/t_f, theta
-        const double itf = 1.0 / __ldg(w + __ldg(pr.tf_idx + k));
-        double *cst = smem + (size_t)HOT * NTHR + tid;
-#pragma unroll
-        for (int r = 0; r <= N_D; ++r) cst[r * NTHR] = c_coeff_coll[r * (N_D + 1) + (j + 1)] * (double)pr.n_k * itf;
-        cst[(N_D + 1) * NTHR] = itf;
-#pragma unroll
-        for (int t = 0; t < N_TH; ++t) cst[(N_D + 2 + t) * NTHR] = __ldg(w + __ldg(pr.theta_idx + k * N_TH + t));
-    }
-    const int *dest = pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
-    double *g_tile = G + (size_t)b0 * n_g;
-    double *j_tile = Jv ? Jv + (size_t)b0 * nnz : nullptr;
     __syncwarp();
-    if (FULL) {
-#include "k_coll.inc"
-    } else {
-#include "k_coll_res.inc"
+    for (int o = 0; o < cnt; ++o) {
+        const int code = __ldg(dest + o);
+        const double v = stg[o * STG_STRIDE + lane];
+        if (!valid) continue;
+        if (code >= 0) {
+            if (Jv) Jv[(size_t)code * B + b] = v;
+        } else if (code <= -2)
+            G[(size_t)(-2 - code) * B + b] = v;
     }
+    __syncwarp();
 }
 
-// --------------------------------------------------------------------------- shooting nodes
-template <bool FULL, bool BATCH_MINOR>
-__global__ void __launch_bounds__(SHOOT_THREADS, CTAS_PER_SM)
-awegpu_shoot_kernel(const DevProblem pr, const int B, const double *__restrict__ W, const double *__restrict__ P,
-                    const long long ldp, const int p_off, double *__restrict__ G, double *__restrict__ Jv)
+// --------------------------------------------------------------------------- gather
+// grid (tiles of the chunk, n_k); b_base = first instance of the chunk
+template <bool BATCH_MINOR>
+__global__ void __launch_bounds__(GATHER_THREADS)
+awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const double *__restrict__ W,
+                     const double *__restrict__ P, const long long ldp, const int p_off, double *__restrict__ G,
+                     double *__restrict__ Jv)
 {
-    constexpr int NTHR = SHOOT_THREADS;
-    constexpr int HOT = FULL ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT;
-    constexpr int COLD = FULL ? AWE_K_SHOOT_COLD : AWE_K_SHOOT_RES_COLD;
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int k_raw = blockIdx.y * SHOOT_WARPS + wid;
-    const bool k_ok = k_raw < pr.n_k;
-    const int k = k_ok ? k_raw : pr.n_k - 1;
-    const int b0 = blockIdx.x * TILE;
-    const int b_raw = b0 + lane;
-    const bool valid = k_ok && b_raw < B;
-    const int b = b_raw < B ? b_raw : B - 1;
-    const int n_valid = k_ok ? min(TILE, B - b0) : 0;
-    const int n_g = pr.n_g;
-    const long long nnz = pr.nnz;
-    double *stg = smem + (size_t)(HOT + N_CST) * NTHR + wid * STG_DOUBLES;
-    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
-    const unsigned cst_addr = (unsigned)__cvta_generic_to_shared(smem + (size_t)HOT * NTHR + tid);
-    double ovf[COLD > 0 ? COLD : 1];
-
-    const double *w = W + (size_t)b * pr.n_v;
-    const double *w_slab = w + __ldg(pr.x_base + k * (N_D + 1));
-    const double *w_own = w_slab + OFF_X0;
-    const double *w_z = w_slab + OFF_Z;
-    const double *w_phi = w + pr.v_phi;
-    const double *p_th0 = P + (size_t)b * ldp + p_off;
-    {
-        double *cst = smem + (size_t)HOT * NTHR + tid;
-#pragma unroll
-        for (int t = 0; t < N_TH; ++t) cst[(N_D + 2 + t) * NTHR] = __ldg(w + __ldg(pr.theta_idx + k * N_TH + t));
+    extern __shared__ double slab[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, k = blockIdx.y;
+    const int b0 = b_base + tile * TILE;
+    const int n_valid = min(TILE, B - b0);
+    const int x0 = __ldg(pr.x_base + k * (N_D + 1));
+    // surplus lanes of a ragged tile replicate the last instance (their results are never stored)
+    for (int e = tid; e < TILE * SLAB_ALL; e += GATHER_THREADS) {
+        const int u = e / SLAB_ALL, o = e - u * SLAB_ALL;
+        const int b = min(b0 + u, B - 1);
+        slab[u * SLAB_STRIDE + o] = __ldg(W + (size_t)b * pr.n_v + x0 + o);
     }
-    const int *dest = pr.shoot_dest + (size_t)k * pr.n_shoot_out;
-    double *g_tile = G + (size_t)b0 * n_g;
-    double *j_tile = Jv ? Jv + (size_t)b0 * nnz : nullptr;
-    __syncwarp();
+    __syncthreads();
+    const int bl = min(b0 + lane, B - 1);
+    const double *wl = W + (size_t)bl * pr.n_v;
+    // ---- record: slab | theta | phi, entry-major, lane-minor
+    double *rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32;
+    for (int e = tid; e < REC * 32; e += GATHER_THREADS) {
+        const int i = e >> 5;
+        double v;
+        if (i < SLAB_W)
+            v = slab[lane * SLAB_STRIDE + i];
+        else if (i < REC_PHI)
+            v = __ldg(wl + __ldg(pr.theta_idx + k * N_TH + (i - REC_TH)));
+        else
+            v = __ldg(wl + pr.v_phi + (i - REC_PHI));
+        rec[e] = v;
+    }
+    // ---- xdot_kj = (sum_r C[r, j+1] X_r) / h / t_f      (awebox/ocp/collocation.py:225, 239-250)
     {
-        const int own_r = -1;
-        (void)own_r;
-        if (FULL) {
-#include "k_shoot.inc"
-        } else {
-#include "k_shoot_res.inc"
+        const double itf_nk = (double)pr.n_k / __ldg(wl + __ldg(pr.tf_idx + k));
+        const double *s = slab + lane * SLAB_STRIDE;
+        for (int j = warp; j < N_D; j += GATHER_THREADS / 32) {
+            double *xd = sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
+            for (int m = 0; m < N_X; ++m) {
+                double xp = 0.0;
+#pragma unroll
+                for (int r = 0; r <= N_D; ++r) xp = fma(c_coeff_coll[r * (N_D + 1) + (j + 1)] * itf_nk, s[OFF_XR(r) + m], xp);
+                xd[m * 32] = xp;
+            }
         }
+    }
+    // ---- theta0, lane-contiguous (one copy per tile)
+    if (k == 0) {
+        double *pt = sc.pt + (size_t)tile * pr.n_theta0 * 32;
+        const double *pl = P + (size_t)bl * ldp + p_off;
+        for (int e = tid; e < pr.n_theta0 * 32; e += GATHER_THREADS) pt[e] = __ldg(pl + (e >> 5));
     }
     // ---- continuity rows  x_{k+1} - sum_r D[r] X_r   (awebox/ocp/collocation.py:319-336)
     const int row_cont = __ldg(pr.row_cont + k);
     if (BATCH_MINOR) {
-        if (valid)
-            for (int m = 0; m < N_X; ++m) {
-                double xf = c_coeff_cont[0] * __ldg(w_slab + OFF_X0 + m);
+        if (lane < n_valid)
+            for (int m = warp; m < N_X; m += GATHER_THREADS / 32) {
+                const double *s = slab + lane * SLAB_STRIDE;
+                double xf = 0.0;
 #pragma unroll
-                for (int r = 1; r <= N_D; ++r) xf += c_coeff_cont[r] * __ldg(w_slab + OFF_CX(r - 1) + m);
-                G[(size_t)(row_cont + m) * B + b] = pr.cscale * (__ldg(w_slab + OFF_XNEXT + m) - xf);
+                for (int r = 0; r <= N_D; ++r) xf = fma(c_coeff_cont[r], s[OFF_XR(r) + m], xf);
+                G[(size_t)(row_cont + m) * B + b0 + lane] = pr.cscale * (s[OFF_XNEXT + m] - xf);
             }
     } else {
-        for (int m0 = 0; m0 < N_X; m0 += AWE_CHUNK) {
-            const int cnt = min(AWE_CHUNK, N_X - m0);
-            for (int m = m0; m < m0 + cnt; ++m) {
-                double xf = c_coeff_cont[0] * __ldg(w_slab + OFF_X0 + m);
+        // lane = state component: the N_X rows of one instance are contiguous in g
+        for (int u = warp; u < n_valid; u += GATHER_THREADS / 32) {
+            const double *s = slab + u * SLAB_STRIDE;
+            for (int m = lane; m < N_X; m += 32) {
+                double xf = 0.0;
 #pragma unroll
-                for (int r = 1; r <= N_D; ++r) xf += c_coeff_cont[r] * __ldg(w_slab + OFF_CX(r - 1) + m);
-                stg[(m - m0) * STG_STRIDE + lane] = pr.cscale * (__ldg(w_slab + OFF_XNEXT + m) - xf);
+                for (int r = 0; r <= N_D; ++r) xf = fma(c_coeff_cont[r], s[OFF_XR(r) + m], xf);
+                G[(size_t)(b0 + u) * pr.n_g + row_cont + m] = pr.cscale * (s[OFF_XNEXT + m] - xf);
             }
-            __syncwarp();
-            {
-                const int o = lane % AWE_CHUNK;
-                if (o < cnt) {
-                    double *p = g_tile + row_cont + m0 + o;
-                    const double *src = stg + o * STG_STRIDE;
-                    for (int i = lane / AWE_CHUNK; i < n_valid; i += 32 / AWE_CHUNK) p[(size_t)i * n_g] = src[i];
-                }
-            }
-            __syncwarp();
         }
     }
     // ---- constant Jacobian entries owned by this interval (continuity; periodicity on the last one):
-    //      the value does not depend on the instance, lane = entry
-    if (Jv && k_ok) {
+    //      the value does not depend on the instance, thread = entry
+    if (Jv) {
         const int e1 = __ldg(pr.const_begin + k + 1);
-        for (int e = __ldg(pr.const_begin + k) + lane; e < e1; e += 32) {
+        for (int e = __ldg(pr.const_begin + k) + tid; e < e1; e += GATHER_THREADS) {
             const int slot = __ldg(pr.const_slot + e);
             const double v = __ldg(pr.const_val + e);
             if (BATCH_MINOR) {
                 for (int i = 0; i < n_valid; ++i) Jv[(size_t)slot * B + b0 + i] = v;
             } else {
-                for (int i = 0; i < n_valid; ++i) j_tile[(size_t)i * nnz + slot] = v;
+                for (int i = 0; i < n_valid; ++i) Jv[(size_t)(b0 + i) * pr.nnz + slot] = v;
             }
         }
     }
     // ---- periodicity rows  x_0 - x_{n_k-1, d-1}           (awebox/ocp/operation.py:245-267)
-    if (k_raw == pr.n_k - 1 && valid) {
-        for (int n = 0; n < pr.n_periodic; ++n) {
-            const int m = __ldg(pr.periodic_idx + n);
-            const double v = pr.cscale * (__ldg(w + pr.x_first + m) - __ldg(w_slab + OFF_CX(N_D - 1) + m));
-            if (BATCH_MINOR)
-                G[(size_t)(pr.row_periodic + n) * B + b] = v;
-            else
-                G[(size_t)b * n_g + pr.row_periodic + n] = v;
+    if (k == pr.n_k - 1) {
+        for (int u = warp; u < n_valid; u += GATHER_THREADS / 32) {
+            const double *w0 = W + (size_t)(b0 + u) * pr.n_v + pr.x_first;
+            const double *s = slab + u * SLAB_STRIDE + OFF_CX(N_D - 1);
+            for (int n = lane; n < pr.n_periodic; n += 32) {
+                const int m = __ldg(pr.periodic_idx + n);
+                const double v = pr.cscale * (__ldg(w0 + m) - s[m]);
+                if (BATCH_MINOR)
+                    G[(size_t)(pr.row_periodic + n) * B + b0 + u] = v;
+                else
+                    G[(size_t)(b0 + u) * pr.n_g + pr.row_periodic + n] = v;
+            }
         }
     }
 }
 
-template <bool FULL>
-static constexpr size_t coll_smem_bytes()
+// --------------------------------------------------------------------------- node programs
+// warp = one node of one tile, lane = instance, blockIdx.y = program group
+template <bool SHOOT, bool FULL, bool BATCH_MINOR>
+__global__ void __launch_bounds__(NODE_THREADS, AWE_NODE_CTAS)
+awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const int n_items,
+                   double *__restrict__ G, double *__restrict__ Jv)
 {
-    return sizeof(double) * ((size_t)((FULL ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT) + N_CST) * COLL_THREADS + N_D * STG_DOUBLES);
+    constexpr int HOT = SHOOT ? (FULL ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT) : (FULL ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT);
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int item = blockIdx.x * NODE_WARPS + wid;
+    if (item >= n_items) return;
+    const int group = blockIdx.y;
+    int tile, k, j;
+    if (SHOOT) {
+        j = -1, k = item % pr.n_k, tile = item / pr.n_k;
+    } else {
+        j = item % N_D, k = (item / N_D) % pr.n_k, tile = item / (N_D * pr.n_k);
+    }
+    const int j1 = j + 1;
+    const int b0 = b_base + tile * TILE;
+    const int b = b0 + lane;
+    const bool valid = b < B;
+    const int n_valid = min(TILE, B - b0);
+    const int n_g = pr.n_g;
+    const long long nnz = pr.nnz;
+    double *stg = smem + (size_t)HOT * NODE_THREADS + wid * STG_DOUBLES;
+    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
+
+    const double *w_rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32 + lane;
+    const double *w_own = SHOOT ? w_rec + OFF_X0 * 32 : w_rec + OFF_CX(j) * 32;
+    const double *w_z = SHOOT ? w_rec + OFF_Z * 32 : w_own + N_X * 32;
+    const double *w_xd = SHOOT ? w_rec + OFF_XDOT * 32
+                               : sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
+    const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
+    const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
+    const double itf_nk = itf * (double)pr.n_k;
+    (void)itf_nk;
+    const int *dest = SHOOT ? pr.shoot_dest + (size_t)k * pr.n_shoot_out
+                            : pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
+    double *g_tile = G + (size_t)b0 * n_g;
+    double *j_tile = Jv ? Jv + (size_t)b0 * nnz : nullptr;
+    if (SHOOT) {
+        if (FULL) {
+            switch (group) {
+#include "k_shoot.inc"
+            }
+        } else {
+            switch (group) {
+#include "k_shoot_res.inc"
+            }
+        }
+    } else {
+        if (FULL) {
+            switch (group) {
+#include "k_coll.inc"
+            }
+        } else {
+            switch (group) {
+#include "k_coll_res.inc"
+            }
+        }
+    }
 }
-template <bool FULL>
-static constexpr size_t shoot_smem_bytes()
+
+template <bool SHOOT, bool FULL>
+static constexpr size_t node_smem_bytes()
 {
-    return sizeof(double) *
-           ((size_t)((FULL ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT) + N_CST) * SHOOT_THREADS + SHOOT_WARPS * STG_DOUBLES);
+    return sizeof(double) * ((size_t)(SHOOT ? (FULL ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT)
+                                            : (FULL ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT)) * NODE_THREADS +
+                             NODE_WARPS * STG_DOUBLES);
 }
+template <bool SHOOT, bool FULL>
+static constexpr int node_groups()
+{
+    return SHOOT ? (FULL ? AWE_K_SHOOT_GROUPS : AWE_K_SHOOT_RES_GROUPS) : (FULL ? AWE_K_COLL_GROUPS : AWE_K_COLL_RES_GROUPS);
+}
+static constexpr size_t gather_smem_bytes() { return sizeof(double) * TILE * SLAB_STRIDE; }
 
 // =========================================================================== host side / C ABI
 struct awegpu_handle {
@@ -364,6 +402,9 @@ struct awegpu_handle {
     double *hW = nullptr, *hP = nullptr, *hG = nullptr, *hJ = nullptr;
     size_t capW = 0, capP = 0, capG = 0, capJ = 0, hcapW = 0, hcapP = 0, hcapG = 0, hcapJ = 0;
     cudaStream_t stream2 = nullptr;
+    // node-input records of one chunk of instances (see awegpu_gather_kernel)
+    Scratch sc{};
+    int chunk_tiles = 0;
     // casadi sparsity buffers
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
     std::vector<double> scratch_g;
@@ -421,6 +462,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     if (g_casadi == h) g_casadi = nullptr;
     for (void *p : h->dev_allocs) cudaFree(p);
     cudaFree(h->dW), cudaFree(h->dP), cudaFree(h->dG), cudaFree(h->dJ);
+    cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt);
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -504,15 +546,33 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
 #define SET_SMEM(kern, bytes) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
-    SET_SMEM((awegpu_coll_kernel<true, false>), coll_smem_bytes<true>());
-    SET_SMEM((awegpu_coll_kernel<true, true>), coll_smem_bytes<true>());
-    SET_SMEM((awegpu_coll_kernel<false, false>), coll_smem_bytes<false>());
-    SET_SMEM((awegpu_coll_kernel<false, true>), coll_smem_bytes<false>());
-    SET_SMEM((awegpu_shoot_kernel<true, false>), shoot_smem_bytes<true>());
-    SET_SMEM((awegpu_shoot_kernel<true, true>), shoot_smem_bytes<true>());
-    SET_SMEM((awegpu_shoot_kernel<false, false>), shoot_smem_bytes<false>());
-    SET_SMEM((awegpu_shoot_kernel<false, true>), shoot_smem_bytes<false>());
+#define SET_NODE(S_, F_)                                                              \
+    SET_SMEM((awegpu_node_kernel<S_, F_, false>), (node_smem_bytes<S_, F_>()));       \
+    SET_SMEM((awegpu_node_kernel<S_, F_, true>), (node_smem_bytes<S_, F_>()))
+    SET_NODE(false, true);
+    SET_NODE(false, false);
+    SET_NODE(true, true);
+    SET_NODE(true, false);
+    SET_SMEM(awegpu_gather_kernel<false>, gather_smem_bytes());
+    SET_SMEM(awegpu_gather_kernel<true>, gather_smem_bytes());
+#undef SET_NODE
 #undef SET_SMEM
+    {
+        // chunk of instances whose node-input records stay L2-resident while the program groups
+        // stream over them (AWEGPU_CHUNK_TILES overrides; 16 tiles = 512 instances)
+        const char *env = getenv("AWEGPU_CHUNK_TILES");
+        int ct = env ? atoi(env) : 0;
+        if (ct <= 0) {
+            const size_t per_tile = sizeof(double) * 32 * ((size_t)nk * (REC + (size_t)dd * N_X) + p->n_theta0);
+            ct = (int)((48u << 20) / per_tile);
+            if (ct < 1) ct = 1;
+            if (ct > 64) ct = 64;
+        }
+        h->chunk_tiles = ct;
+        CK(cudaMalloc((void **)&h->sc.rec, sizeof(double) * 32 * (size_t)ct * nk * REC));
+        CK(cudaMalloc((void **)&h->sc.xdc, sizeof(double) * 32 * (size_t)ct * nk * dd * N_X));
+        CK(cudaMalloc((void **)&h->sc.pt, sizeof(double) * 32 * (size_t)ct * p->n_theta0));
+    }
     // host copies of pointers are not kept: null them so nobody dereferences caller memory later
     h->host.x_base = h->host.x_next = h->host.u_base = h->host.xdot_base = h->host.z_base = nullptr;
     return 0;
@@ -564,21 +624,34 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
     double *jv = (flags & AWEGPU_SKIP_JAC) ? nullptr : Jv;
     const bool full = jv != nullptr, bm = (flags & AWEGPU_JAC_BATCH_MINOR) != 0;
     const int tiles = (B + TILE - 1) / TILE;
-    dim3 gc(tiles, h->dp.n_k), gs(tiles, (h->dp.n_k + SHOOT_WARPS - 1) / SHOOT_WARPS);
+    const DevProblem &dp = h->dp;
     CK(cudaEventRecord(h->ev0, st));
-#define LAUNCH(F, M)                                                                                               \
-    do {                                                                                                           \
-        awegpu_coll_kernel<F, M><<<gc, COLL_THREADS, coll_smem_bytes<F>(), st>>>(h->dp, B, W, P, ldp, p_off, G, jv);   \
-        awegpu_shoot_kernel<F, M><<<gs, SHOOT_THREADS, shoot_smem_bytes<F>(), st>>>(h->dp, B, W, P, ldp, p_off, G, jv); \
+#define LAUNCH_NODES(F, M)                                                                                          \
+    do {                                                                                                            \
+        const int nc_ = ct * dp.n_k * N_D, ns_ = ct * dp.n_k;                                                       \
+        awegpu_node_kernel<false, F, M><<<dim3((nc_ + NODE_WARPS - 1) / NODE_WARPS, node_groups<false, F>()),       \
+                                          NODE_THREADS, node_smem_bytes<false, F>(), st>>>(dp, h->sc, B, b_base, nc_, G, jv); \
+        awegpu_node_kernel<true, F, M><<<dim3((ns_ + NODE_WARPS - 1) / NODE_WARPS, node_groups<true, F>()),         \
+                                         NODE_THREADS, node_smem_bytes<true, F>(), st>>>(dp, h->sc, B, b_base, ns_, G, jv);   \
     } while (0)
-    if (full && !bm) LAUNCH(true, false);
-    else if (full && bm) LAUNCH(true, true);
-    else if (!full && !bm) LAUNCH(false, false);
-    else LAUNCH(false, true);
-#undef LAUNCH
+    for (int t0 = 0; t0 < tiles; t0 += h->chunk_tiles) {
+        const int ct = (tiles - t0 < h->chunk_tiles) ? (tiles - t0) : h->chunk_tiles;
+        const int b_base = t0 * TILE;
+        if (bm)
+            awegpu_gather_kernel<true><<<dim3(ct, dp.n_k), GATHER_THREADS, gather_smem_bytes(), st>>>(
+                dp, h->sc, B, b_base, W, P, ldp, p_off, G, jv);
+        else
+            awegpu_gather_kernel<false><<<dim3(ct, dp.n_k), GATHER_THREADS, gather_smem_bytes(), st>>>(
+                dp, h->sc, B, b_base, W, P, ldp, p_off, G, jv);
+        if (full && !bm) LAUNCH_NODES(true, false);
+        else if (full && bm) LAUNCH_NODES(true, true);
+        else if (!full && !bm) LAUNCH_NODES(false, false);
+        else LAUNCH_NODES(false, true);
+        h->launches += 3;
+    }
+#undef LAUNCH_NODES
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
-    h->launches += 2;
     h->last_ms = -2.f;
     return 0;
 }

@@ -18,7 +18,6 @@
 #define N_D AWE_D
 #define N_X AWE_N_X
 
-#define LD_XR(reg, r, m) reg = xr[(r) * N_X + (m)]
 #define LD_XO(reg, m) reg = xo[m]
 #define LD_XD(reg, m) reg = xd[m]
 #define LD_U(reg, c) reg = u[c]
@@ -33,36 +32,50 @@
 #define OVF_ST(slot, reg) cold[slot] = reg
 #define OVF_LD(reg, slot) reg = cold[slot]
 #define SYNC_HINT()
-#define OUT(n, val) out[n] = (val)
-#define FLUSH(c, cnt)
+#define OUT(n, val) stg_[n] = (val)
+#define FLUSH(first, cnt) do { int q_; for (q_ = 0; q_ < (cnt); ++q_) out[(first) + q_] = stg_[q_]; } while (0)
 
-/* xr [(d+1)*n_x] state blocks of the interval, xo [n_x] own block, u, z, th, p [n_param],
- * cc [d+1], itf, own_r in 1..d */
-void sched_coll(const double *xr, const double *xo, const double *u, const double *z, const double *th,
+/* xo [n_x] state block of the node, xd [n_x] its time derivative, u, z, th, p [n_param], cc [d+1], itf,
+ * j1 = own block index in 1..d (collocation) */
+#define RUN_GROUPS(FILE_, NGROUPS_)              \
+    for (group = 0; group < (NGROUPS_); ++group) \
+        switch (group) {                         \
+            FILE_                                \
+        }
+
+void sched_coll(const double *xo, const double *xd, const double *u, const double *z, const double *th,
                 const double *p, const double *cc, double itf, int own_r, double *out, int full)
 {
-    double hot[512], cold[512];
-    const double *xd = 0;
-    (void)xd;
+    double hot[512], cold[512], stg_[64];
+    int group;
     if (full) {
+        for (group = 0; group < AWE_K_COLL_GROUPS; ++group) switch (group) {
 #include "k_coll.inc"
+            }
     } else {
+        for (group = 0; group < AWE_K_COLL_RES_GROUPS; ++group) switch (group) {
 #include "k_coll_res.inc"
+            }
     }
 }
 
 void sched_shoot(const double *xo, const double *xd, const double *u, const double *z, const double *th,
                  const double *p, double *out, int full)
 {
-    double hot[512], cold[512];
-    const double *xr = 0, *cc = 0;
+    double hot[512], cold[512], stg_[64];
+    const double *cc = 0;
     const double itf = 0.0;
     const int own_r = -1;
-    (void)xr, (void)cc, (void)itf, (void)own_r;
+    int group;
+    (void)cc, (void)itf, (void)own_r;
     if (full) {
+        for (group = 0; group < AWE_K_SHOOT_GROUPS; ++group) switch (group) {
 #include "k_shoot.inc"
+            }
     } else {
+        for (group = 0; group < AWE_K_SHOOT_RES_GROUPS; ++group) switch (group) {
 #include "k_shoot_res.inc"
+            }
     }
 }
 

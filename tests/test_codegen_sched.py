@@ -60,10 +60,9 @@ def test_scheduled_collocation_program_matches_plain_emission(harness, j):
     n_out = len(ocp.coll_out)
     a, b, c = np.zeros(n_out), np.zeros(n_out), np.zeros(n_out)
     harness.plain_coll(_ptr(v), _ptr(p), _ptr(cc), _ptr(own), 1.0 / tf, _ptr(a))
-    harness.sched_coll(_ptr(np.ascontiguousarray(xr.reshape(-1))), _ptr(xo), _ptr(u), _ptr(z), _ptr(th), _ptr(p),
-                       _ptr(cc), 1.0 / tf, j + 1, _ptr(b), 1)
-    harness.sched_coll(_ptr(np.ascontiguousarray(xr.reshape(-1))), _ptr(xo), _ptr(u), _ptr(z), _ptr(th), _ptr(p),
-                       _ptr(cc), 1.0 / tf, j + 1, _ptr(c), 0)
+    xdot = np.ascontiguousarray(xdot)
+    harness.sched_coll(_ptr(xo), _ptr(xdot), _ptr(u), _ptr(z), _ptr(th), _ptr(p), _ptr(cc), 1.0 / tf, j + 1, _ptr(b), 1)
+    harness.sched_coll(_ptr(xo), _ptr(xdot), _ptr(u), _ptr(z), _ptr(th), _ptr(p), _ptr(cc), 1.0 / tf, j + 1, _ptr(c), 0)
     scale = np.maximum(1.0, np.abs(a))
     assert np.max(np.abs(a - b) / scale) < 1e-11
     assert np.max(np.abs(a[:ocp.n_eq] - c[:ocp.n_eq]) / scale[:ocp.n_eq]) < 1e-11
