@@ -37,7 +37,16 @@ N_REGS = 48          # FP64 values the allocator keeps in registers (-> ~128 reg
 LOOKAHEAD = 8        # statements between a scratch reload and its first use
 HOT_SLOTS = 1 << 20  # no cold tier: the grouped programs need only a few dozen scratch slots
 CHUNK = 16           # outputs staged per flush
-GROUP_OPS = 1400     # operation budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
+GROUP_OPS = 1400     # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
+MAX_EXPORTS = 64     # intermediate values computed once per node by the pre-stage and re-read by the groups
+EXPORT_MIN_GAIN = 40
+EXPORT_LOAD_COST = 4
+MAX_STAGES = 3       # main programs + two levels of export pre-stages
+
+
+# rough SASS instruction count per operation (program size budget / export heuristic)
+OP_WEIGHT = {S.POW: 60, S.POWC: 60, S.EXP: 30, S.LOG: 30, S.SIN: 30, S.COS: 30, S.TAN: 40, S.ATAN: 40, S.ATAN2: 50,
+             S.ASIN: 40, S.ACOS: 40, S.DIV: 8, S.SQRT: 9, S.RSQRT: 7}
 
 
 def _rhs(op, a, b):
@@ -170,36 +179,101 @@ class NodeCode(object):
         self.k_shoot = S.substitute(self.shoot_exprs, base)
 
     @staticmethod
-    def partition(exprs, limit):
-        """Split the output list into consecutive groups whose operation cones stay below ``limit``
-        operations.  Every group becomes a separate small program that recomputes what it shares with
-        the others: the programs of one group then fit the 32 KB instruction cache of an SM and need
-        few registers, which is what the hardware wants.  -> [(first, last+1)]"""
-        def cone(e, acc):
-            stack = [e]
-            while stack:
-                n = stack.pop()
-                if n.idx in acc or not SCH.is_op(n):
-                    continue
-                acc.add(n.idx)
-                if n.a is not None:
-                    stack.append(n.a)
-                if n.b is not None:
-                    stack.append(n.b)
-            return acc
-        groups, cur, first = [], set(), 0
-        for i, e in enumerate(exprs):
-            c = cone(e, set())
-            u = cur | c
-            if len(u) > limit and i > first:
-                groups.append((first, i))
-                cur, first = c, i
-            else:
-                cur = u
-        groups.append((first, len(exprs)))
-        return groups
+    def plan(exprs, limit=None, max_exports=None, min_gain=None):
+        """Split a node function into small programs.
 
-    def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=CHUNK, first=0):
+        * the outputs are cut into consecutive *groups* whose operation cones weigh at most ``limit``
+          (weights ~ SASS instructions: 1 per FP64 operation, more for division, roots, pow): one group =
+          one straight-line program that fits the SM's 32 KB instruction cache and needs few registers;
+          what two groups share is recomputed in both;
+        * *exports* are intermediate values that are too expensive to recompute in every group (the
+          wind / density power laws, norms, aerodynamic angles ...): they are computed once per node by
+          a pre-stage program, stored lane-contiguously, and read back as inputs.  Chosen greedily by
+          (groups sharing the value - 1) x (weight of its cone) minus the cost of the extra loads.
+
+        -> (export nodes in dependency order, [(first, last+1)] output groups)"""
+        limit = GROUP_OPS if limit is None else limit
+        max_exports = MAX_EXPORTS if max_exports is None else max_exports
+        min_gain = EXPORT_MIN_GAIN if min_gain is None else min_gain
+        order = [n for n in S.topo(exprs) if SCH.is_op(n)]
+        pos = {n.idx: i for i, n in enumerate(order)}
+        wgt = [OP_WEIGHT.get(n.op, 1) for n in order]
+        exported = set()
+        out_idx = set(e.idx for e in exprs)
+
+        def cones():
+            c = [0] * len(order)
+            for i, n in enumerate(order):
+                if n.idx in exported:
+                    continue
+                v = 1 << i
+                for ch in (n.a, n.b):
+                    if ch is not None and SCH.is_op(ch) and ch.idx not in exported:
+                        v |= c[pos[ch.idx]]
+                c[i] = v
+            return c
+
+        def wsum(bits):
+            t = 0
+            while bits:
+                low = bits & -bits
+                t += wgt[low.bit_length() - 1]
+                bits ^= low
+            return t
+
+        def partition(c):
+            groups, cur, first = [], 0, 0
+            for i, e in enumerate(exprs):
+                ce = c[pos[e.idx]] if (SCH.is_op(e) and e.idx not in exported) else 0
+                u = cur | ce
+                if wsum(u) > limit and i > first:
+                    groups.append((first, i, cur))
+                    cur, first = ce, i
+                else:
+                    cur = u
+            groups.append((first, len(exprs), cur))
+            return groups
+
+        # full cones (no export cut): what the pre-stage has to compute for an export
+        full = [0] * len(order)
+        for i, n in enumerate(order):
+            v = 1 << i
+            for ch in (n.a, n.b):
+                if ch is not None and SCH.is_op(ch):
+                    v |= full[pos[ch.idx]]
+            full[i] = v
+        pre_bits = 0
+        while True:
+            c = cones()
+            groups = partition(c)
+            if len(exported) >= max_exports:
+                break
+            use = [0] * len(order)
+            for g in groups:
+                bits = g[2]
+                while bits:
+                    low = bits & -bits
+                    use[low.bit_length() - 1] += 1
+                    bits ^= low
+            best, best_gain = None, 0
+            for i, n in enumerate(order):
+                if use[i] < 2 or n.idx in exported or n.idx in out_idx:
+                    continue
+                saved = (use[i] - 1) * wsum(c[i])
+                if saved <= best_gain:
+                    continue
+                gain = saved - wsum(full[i] & ~pre_bits) - EXPORT_LOAD_COST * (use[i] + 1)
+                if gain > best_gain:
+                    best, best_gain = i, gain
+            if best is None or best_gain < min_gain:
+                break
+            exported.add(order[best].idx)
+            pre_bits |= full[best]
+        exports = [n for n in order if n.idx in exported]
+        return exports, [(a, b) for a, b, _ in groups]
+
+    def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=CHUNK, first=0,
+                       export=False, leaf_names=None):
         """-> (text, stats): register-allocated straight-line code (awebox_b200/schedule.py) printed
         with statement macros:
             LD_XR(reg, r, m) LD_XO(reg, m) LD_XD(reg, m) LD_U(reg, c) LD_Z(reg, c) LD_TH(reg, t)
@@ -232,7 +306,7 @@ class NodeCode(object):
         for it in prog.ins:
             k = it[0]
             if k == 'leaf':
-                name = self.k_leaf[it[2].idx]
+                name = (leaf_names or self.k_leaf)[it[2].idx]
                 if '(' in name:
                     kind, args = name[:-1].split('(')
                     lines.append('LD_%s(r%d, %s);' % (kind.replace('IN', ''), it[1], args))
@@ -248,6 +322,9 @@ class NodeCode(object):
                 lines.append('%s_ST(%d, r%d);' % (t, idx, it[2]))
             elif k == 'out':
                 n = it[1]
+                if export:
+                    lines.append('EXOUT(%d, %s);' % (first + n, src(it[2])))
+                    continue
                 lines.append('OUT(%d, %s);' % (n % chunk, src(it[2])))
                 if (n + 1) % chunk == 0 or n + 1 == n_out:
                     lines.append('FLUSH(%d, %d);' % (first + (n // chunk) * chunk, n % chunk + 1))
@@ -326,20 +403,59 @@ class NodeCode(object):
                     'k_coll_res': self.k_coll[:ocp.n_eq], 'k_shoot_res': self.k_shoot[:n_sh]}
         kdefs = ''
         for name, exprs in variants.items():
-            groups = self.partition(exprs, GROUP_OPS)
-            text, gstats = '', []
-            for g, (a, b) in enumerate(groups):
-                body, st = self.emit_scheduled(exprs[a:b], first=a)
-                text += 'case %d: {\n%s} break;\n' % (g, body)
-                st['first'], st['last'] = a, b
-                gstats.append(st)
-            files[name + '.inc'] = banner + text
-            stats[name] = {'groups': gstats, 'n_groups': len(groups),
-                           'ops_total': sum(flops(st) for st in gstats),
-                           'hot_slots': max(st['hot_slots'] for st in gstats)}
+            # stage 0 = the outputs; stage s+1 = the exports stage s (and the stages before it) read.
+            # Executed in the order MAX_STAGES-1 .. 0, one launch per stage.
+            stages, ex_index, ex_nodes = [], {}, []
+            cur = list(exprs)
+            for level in range(MAX_STAGES):
+                exports, groups = self.plan(cur, max_exports=0 if level == MAX_STAGES - 1 else None)
+                new = [n for n in exports if n.idx not in ex_index]
+                for n in new:
+                    ex_index[n.idx] = len(ex_nodes)
+                    ex_nodes.append(n)
+                stages.append((cur, groups))
+                if not new:
+                    break
+                cur = new
+            leaf_names = dict(self.k_leaf)
+            ex_syms = [S.sym('EXIN(%d)' % i) for i in range(len(ex_nodes))]
+            for v in ex_syms:
+                leaf_names[v.idx] = v.name
+            sstats = []
+            first_export = 0
+            for level in range(MAX_STAGES):
+                text, gstats = '', []
+                if level < len(stages):
+                    outs, groups = stages[level]
+                    # everything exported by a deeper stage is an input leaf here
+                    deeper = set()
+                    for lv in range(level + 1, len(stages)):
+                        deeper.update(n.idx for n in stages[lv][0])
+                    mapping = {n: ex_syms[ex_index[n.idx]] for n in ex_nodes if n.idx in deeper}
+                    g_exprs = S.substitute(outs, mapping) if mapping else outs
+                    for g, (a, b) in enumerate(groups):
+                        if level == 0:
+                            body, st = self.emit_scheduled(g_exprs[a:b], first=a, leaf_names=leaf_names)
+                        else:
+                            body, st = self.emit_scheduled(g_exprs[a:b], first=ex_index[outs[a].idx], export=True,
+                                                           leaf_names=leaf_names)
+                            assert [ex_index[n.idx] for n in outs[a:b]] == list(range(ex_index[outs[a].idx],
+                                                                                      ex_index[outs[a].idx] + b - a))
+                        text += 'case %d: {\n%s} break;\n' % (g, body)
+                        st['first'], st['last'] = a, b
+                        gstats.append(st)
+                files['%s_s%d.inc' % (name, level)] = banner + text
+                sstats.append(gstats)
+            allg = [st for gs in sstats for st in gs]
+            hot = max(st['hot_slots'] for st in allg)
+            stats[name] = {'stages': sstats, 'n_exports': len(ex_nodes),
+                           'ops_total': sum(flops(st) for st in allg), 'hot_slots': hot}
             up = name.upper()
-            kdefs += '#define AWE_%s_GROUPS %d\n#define AWE_%s_HOT %d\n#define AWE_%s_OPS %d\n' % (
-                up, len(groups), up, stats[name]['hot_slots'], up, stats[name]['ops_total'])
+            kdefs += '#define AWE_%s_EXPORTS %d\n#define AWE_%s_HOT %d\n#define AWE_%s_OPS %d\n' % (
+                up, len(ex_nodes), up, hot, up, stats[name]['ops_total'])
+            for level in range(MAX_STAGES):
+                kdefs += '#define AWE_%s_S%d_GROUPS %d\n' % (up, level, len(sstats[level]))
+        kdefs += '#define AWE_MAX_STAGES %d\n' % MAX_STAGES
         kdefs += '#define AWE_CHUNK %d\n' % CHUNK
         files['model_defs.h'] = head + kdefs
         return files, stats

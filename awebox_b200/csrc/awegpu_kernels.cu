@@ -77,6 +77,8 @@ struct Scratch {
     double *rec;      // [tiles][n_k][REC][32]
     double *xdc;      // [tiles][n_k][d][N_X][32]
     double *pt;       // [tiles][n_theta0][32]
+    double *exc;      // [tiles][n_k][d][AWE_K_COLL_EXPORTS][32]   values exported by the pre-stage programs
+    double *exs;      // [tiles][n_k][AWE_K_SHOOT_EXPORTS][32]
 };
 
 __constant__ double c_coeff_coll[(N_D + 1) * (N_D + 1)];
@@ -133,6 +135,8 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define LD_Z(reg, c) LDG_(reg, w_z + (c) * 32)
 #define LD_TH(reg, t) LDG_(reg, w_rec + (REC_TH + (t)) * 32)
 #define LD_P(reg, i) LDG_(reg, ((i) < AWE_N_THETA0 ? w_pt + (i) * 32 : w_rec + (REC_PHI + (i) - AWE_N_THETA0) * 32))
+#define LD_EX(reg, i) LDG_(reg, w_ex + (i) * 32)
+#define EXOUT(i, val) w_ex[(i) * 32] = (val)
 #define LD_CC(reg, r) reg = c_coeff_coll[(r) * (N_D + 1) + j1] * itf_nk
 #define LD_ITF(reg) reg = itf
 #define LD_OWN(reg, r) reg = (j1 == (r)) ? 1.0 : 0.0
@@ -307,13 +311,20 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
 }
 
 // --------------------------------------------------------------------------- node programs
-// warp = one node of one tile, lane = instance, blockIdx.y = program group
-template <bool SHOOT, bool FULL, bool BATCH_MINOR>
+// warp = one node of one tile, lane = instance, blockIdx.y = program group of stage STAGE.
+// Stage 0 produces the node's outputs; stages >= 1 produce exported intermediates (run first).
+#define EXPORTS_OF(SHOOT, FULL) \
+    ((SHOOT) ? ((FULL) ? AWE_K_SHOOT_EXPORTS : AWE_K_SHOOT_RES_EXPORTS) : ((FULL) ? AWE_K_COLL_EXPORTS : AWE_K_COLL_RES_EXPORTS))
+#define HOT_OF(SHOOT, FULL) \
+    ((SHOOT) ? ((FULL) ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT) : ((FULL) ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT))
+
+template <bool SHOOT, bool FULL, int STAGE, bool BATCH_MINOR>
 __global__ void __launch_bounds__(NODE_THREADS, AWE_NODE_CTAS)
 awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const int n_items,
                    double *__restrict__ G, double *__restrict__ Jv)
 {
-    constexpr int HOT = SHOOT ? (FULL ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT) : (FULL ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT);
+    constexpr int HOT = HOT_OF(SHOOT, FULL);
+    constexpr int NEX = EXPORTS_OF(SHOOT, FULL);
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int item = blockIdx.x * NODE_WARPS + wid;
@@ -341,47 +352,93 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
     const double *w_xd = SHOOT ? w_rec + OFF_XDOT * 32
                                : sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
     const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
+    double *w_ex = (SHOOT ? sc.exs : sc.exc) + (size_t)item * (NEX > 0 ? NEX : 1) * 32 + lane;
     const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
     const double itf_nk = itf * (double)pr.n_k;
-    (void)itf_nk;
+    (void)itf_nk, (void)w_ex, (void)valid, (void)n_valid, (void)stg, (void)scr_addr;
     const int *dest = SHOOT ? pr.shoot_dest + (size_t)k * pr.n_shoot_out
                             : pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
     double *g_tile = G + (size_t)b0 * n_g;
     double *j_tile = Jv ? Jv + (size_t)b0 * nnz : nullptr;
-    if (SHOOT) {
-        if (FULL) {
+    (void)dest, (void)g_tile, (void)j_tile;
+#define RUN(FILE_)           \
+    switch (group) {         \
+        FILE_                \
+    }
+    if (SHOOT && FULL) {
+        if (STAGE == 0) {
             switch (group) {
-#include "k_shoot.inc"
+#include "k_shoot_s0.inc"
+            }
+        } else if (STAGE == 1) {
+            switch (group) {
+#include "k_shoot_s1.inc"
             }
         } else {
             switch (group) {
-#include "k_shoot_res.inc"
+#include "k_shoot_s2.inc"
+            }
+        }
+    } else if (SHOOT && !FULL) {
+        if (STAGE == 0) {
+            switch (group) {
+#include "k_shoot_res_s0.inc"
+            }
+        } else if (STAGE == 1) {
+            switch (group) {
+#include "k_shoot_res_s1.inc"
+            }
+        } else {
+            switch (group) {
+#include "k_shoot_res_s2.inc"
+            }
+        }
+    } else if (!SHOOT && FULL) {
+        if (STAGE == 0) {
+            switch (group) {
+#include "k_coll_s0.inc"
+            }
+        } else if (STAGE == 1) {
+            switch (group) {
+#include "k_coll_s1.inc"
+            }
+        } else {
+            switch (group) {
+#include "k_coll_s2.inc"
             }
         }
     } else {
-        if (FULL) {
+        if (STAGE == 0) {
             switch (group) {
-#include "k_coll.inc"
+#include "k_coll_res_s0.inc"
+            }
+        } else if (STAGE == 1) {
+            switch (group) {
+#include "k_coll_res_s1.inc"
             }
         } else {
             switch (group) {
-#include "k_coll_res.inc"
+#include "k_coll_res_s2.inc"
             }
         }
     }
+#undef RUN
 }
 
 template <bool SHOOT, bool FULL>
 static constexpr size_t node_smem_bytes()
 {
-    return sizeof(double) * ((size_t)(SHOOT ? (FULL ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT)
-                                            : (FULL ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT)) * NODE_THREADS +
-                             NODE_WARPS * STG_DOUBLES);
+    return sizeof(double) * ((size_t)HOT_OF(SHOOT, FULL) * NODE_THREADS + NODE_WARPS * STG_DOUBLES);
 }
-template <bool SHOOT, bool FULL>
+template <bool SHOOT, bool FULL, int STAGE>
 static constexpr int node_groups()
 {
-    return SHOOT ? (FULL ? AWE_K_SHOOT_GROUPS : AWE_K_SHOOT_RES_GROUPS) : (FULL ? AWE_K_COLL_GROUPS : AWE_K_COLL_RES_GROUPS);
+    return SHOOT ? (FULL ? (STAGE == 0 ? AWE_K_SHOOT_S0_GROUPS : STAGE == 1 ? AWE_K_SHOOT_S1_GROUPS : AWE_K_SHOOT_S2_GROUPS)
+                         : (STAGE == 0 ? AWE_K_SHOOT_RES_S0_GROUPS
+                                       : STAGE == 1 ? AWE_K_SHOOT_RES_S1_GROUPS : AWE_K_SHOOT_RES_S2_GROUPS))
+                 : (FULL ? (STAGE == 0 ? AWE_K_COLL_S0_GROUPS : STAGE == 1 ? AWE_K_COLL_S1_GROUPS : AWE_K_COLL_S2_GROUPS)
+                         : (STAGE == 0 ? AWE_K_COLL_RES_S0_GROUPS
+                                       : STAGE == 1 ? AWE_K_COLL_RES_S1_GROUPS : AWE_K_COLL_RES_S2_GROUPS));
 }
 static constexpr size_t gather_smem_bytes() { return sizeof(double) * TILE * SLAB_STRIDE; }
 
@@ -462,7 +519,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     if (g_casadi == h) g_casadi = nullptr;
     for (void *p : h->dev_allocs) cudaFree(p);
     cudaFree(h->dW), cudaFree(h->dP), cudaFree(h->dG), cudaFree(h->dJ);
-    cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt);
+    cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -546,9 +603,13 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
 #define SET_SMEM(kern, bytes) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
-#define SET_NODE(S_, F_)                                                              \
-    SET_SMEM((awegpu_node_kernel<S_, F_, false>), (node_smem_bytes<S_, F_>()));       \
-    SET_SMEM((awegpu_node_kernel<S_, F_, true>), (node_smem_bytes<S_, F_>()))
+#define SET_NODE1(S_, F_, T_)                                                             \
+    SET_SMEM((awegpu_node_kernel<S_, F_, T_, false>), (node_smem_bytes<S_, F_>()));       \
+    SET_SMEM((awegpu_node_kernel<S_, F_, T_, true>), (node_smem_bytes<S_, F_>()))
+#define SET_NODE(S_, F_) \
+    SET_NODE1(S_, F_, 0);  \
+    SET_NODE1(S_, F_, 1);  \
+    SET_NODE1(S_, F_, 2)
     SET_NODE(false, true);
     SET_NODE(false, false);
     SET_NODE(true, true);
@@ -556,6 +617,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     SET_SMEM(awegpu_gather_kernel<false>, gather_smem_bytes());
     SET_SMEM(awegpu_gather_kernel<true>, gather_smem_bytes());
 #undef SET_NODE
+#undef SET_NODE1
 #undef SET_SMEM
     {
         // chunk of instances whose node-input records stay L2-resident while the program groups
@@ -563,8 +625,9 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         const char *env = getenv("AWEGPU_CHUNK_TILES");
         int ct = env ? atoi(env) : 0;
         if (ct <= 0) {
-            const size_t per_tile = sizeof(double) * 32 * ((size_t)nk * (REC + (size_t)dd * N_X) + p->n_theta0);
-            ct = (int)((48u << 20) / per_tile);
+            const size_t per_tile = sizeof(double) * 32 * ((size_t)nk * (REC + (size_t)dd * (N_X + AWE_K_COLL_EXPORTS) +
+                                                                         AWE_K_SHOOT_EXPORTS) + p->n_theta0);
+            ct = (int)((64u << 20) / per_tile);
             if (ct < 1) ct = 1;
             if (ct > 64) ct = 64;
         }
@@ -572,6 +635,10 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         CK(cudaMalloc((void **)&h->sc.rec, sizeof(double) * 32 * (size_t)ct * nk * REC));
         CK(cudaMalloc((void **)&h->sc.xdc, sizeof(double) * 32 * (size_t)ct * nk * dd * N_X));
         CK(cudaMalloc((void **)&h->sc.pt, sizeof(double) * 32 * (size_t)ct * p->n_theta0));
+        constexpr size_t nec = AWE_K_COLL_EXPORTS > AWE_K_COLL_RES_EXPORTS ? AWE_K_COLL_EXPORTS : AWE_K_COLL_RES_EXPORTS;
+        constexpr size_t nes = AWE_K_SHOOT_EXPORTS > AWE_K_SHOOT_RES_EXPORTS ? AWE_K_SHOOT_EXPORTS : AWE_K_SHOOT_RES_EXPORTS;
+        CK(cudaMalloc((void **)&h->sc.exc, sizeof(double) * 32 * (size_t)ct * nk * dd * (nec ? nec : 1)));
+        CK(cudaMalloc((void **)&h->sc.exs, sizeof(double) * 32 * (size_t)ct * nk * (nes ? nes : 1)));
     }
     // host copies of pointers are not kept: null them so nobody dereferences caller memory later
     h->host.x_base = h->host.x_next = h->host.u_base = h->host.xdot_base = h->host.z_base = nullptr;
@@ -626,13 +693,23 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
     const int tiles = (B + TILE - 1) / TILE;
     const DevProblem &dp = h->dp;
     CK(cudaEventRecord(h->ev0, st));
-#define LAUNCH_NODES(F, M)                                                                                          \
-    do {                                                                                                            \
-        const int nc_ = ct * dp.n_k * N_D, ns_ = ct * dp.n_k;                                                       \
-        awegpu_node_kernel<false, F, M><<<dim3((nc_ + NODE_WARPS - 1) / NODE_WARPS, node_groups<false, F>()),       \
-                                          NODE_THREADS, node_smem_bytes<false, F>(), st>>>(dp, h->sc, B, b_base, nc_, G, jv); \
-        awegpu_node_kernel<true, F, M><<<dim3((ns_ + NODE_WARPS - 1) / NODE_WARPS, node_groups<true, F>()),         \
-                                         NODE_THREADS, node_smem_bytes<true, F>(), st>>>(dp, h->sc, B, b_base, ns_, G, jv);   \
+#define LAUNCH_STAGE(S_, F, T_, M, n_)                                                                            \
+    do {                                                                                                          \
+        if (node_groups<S_, F, T_>() > 0) {                                                                       \
+            awegpu_node_kernel<S_, F, T_, M><<<dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>()), \
+                                               NODE_THREADS, node_smem_bytes<S_, F>(), st>>>(dp, h->sc, B, b_base, n_, G, jv); \
+            h->launches += 1;                                                                                     \
+        }                                                                                                         \
+    } while (0)
+#define LAUNCH_NODES(F, M)                                \
+    do {                                                  \
+        const int nc_ = ct * dp.n_k * N_D, ns_ = ct * dp.n_k; \
+        LAUNCH_STAGE(false, F, 2, M, nc_);                \
+        LAUNCH_STAGE(true, F, 2, M, ns_);                 \
+        LAUNCH_STAGE(false, F, 1, M, nc_);                \
+        LAUNCH_STAGE(true, F, 1, M, ns_);                 \
+        LAUNCH_STAGE(false, F, 0, M, nc_);                \
+        LAUNCH_STAGE(true, F, 0, M, ns_);                 \
     } while (0)
     for (int t0 = 0; t0 < tiles; t0 += h->chunk_tiles) {
         const int ct = (tiles - t0 < h->chunk_tiles) ? (tiles - t0) : h->chunk_tiles;
@@ -647,9 +724,10 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
         else if (full && bm) LAUNCH_NODES(true, true);
         else if (!full && !bm) LAUNCH_NODES(false, false);
         else LAUNCH_NODES(false, true);
-        h->launches += 3;
+        h->launches += 1;
     }
 #undef LAUNCH_NODES
+#undef LAUNCH_STAGE
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, st));
     h->last_ms = -2.f;

@@ -27,6 +27,8 @@
 #define LD_ITF(reg) reg = itf
 #define LD_TH(reg, t) reg = th[t]
 #define LD_OWN(reg, r) reg = (own_r == (r)) ? 1.0 : 0.0
+#define LD_EX(reg, i) reg = ex_[i]
+#define EXOUT(i, val) ex_[i] = (val)
 #define SPILL_ST(slot, reg) hot[slot] = reg
 #define SPILL_LD(reg, slot) reg = hot[slot]
 #define OVF_ST(slot, reg) cold[slot] = reg
@@ -46,15 +48,28 @@
 void sched_coll(const double *xo, const double *xd, const double *u, const double *z, const double *th,
                 const double *p, const double *cc, double itf, int own_r, double *out, int full)
 {
-    double hot[512], cold[512], stg_[64];
+    double hot[512], cold[512], stg_[64], ex_[1024];
     int group;
+    (void)cold;
     if (full) {
-        for (group = 0; group < AWE_K_COLL_GROUPS; ++group) switch (group) {
-#include "k_coll.inc"
+        for (group = 0; group < AWE_K_COLL_S2_GROUPS; ++group) switch (group) {
+#include "k_coll_s2.inc"
+            }
+        for (group = 0; group < AWE_K_COLL_S1_GROUPS; ++group) switch (group) {
+#include "k_coll_s1.inc"
+            }
+        for (group = 0; group < AWE_K_COLL_S0_GROUPS; ++group) switch (group) {
+#include "k_coll_s0.inc"
             }
     } else {
-        for (group = 0; group < AWE_K_COLL_RES_GROUPS; ++group) switch (group) {
-#include "k_coll_res.inc"
+        for (group = 0; group < AWE_K_COLL_RES_S2_GROUPS; ++group) switch (group) {
+#include "k_coll_res_s2.inc"
+            }
+        for (group = 0; group < AWE_K_COLL_RES_S1_GROUPS; ++group) switch (group) {
+#include "k_coll_res_s1.inc"
+            }
+        for (group = 0; group < AWE_K_COLL_RES_S0_GROUPS; ++group) switch (group) {
+#include "k_coll_res_s0.inc"
             }
     }
 }
@@ -62,19 +77,31 @@ void sched_coll(const double *xo, const double *xd, const double *u, const doubl
 void sched_shoot(const double *xo, const double *xd, const double *u, const double *z, const double *th,
                  const double *p, double *out, int full)
 {
-    double hot[512], cold[512], stg_[64];
+    double hot[512], cold[512], stg_[64], ex_[1024];
     const double *cc = 0;
     const double itf = 0.0;
     const int own_r = -1;
     int group;
-    (void)cc, (void)itf, (void)own_r;
+    (void)cc, (void)itf, (void)own_r, (void)cold;
     if (full) {
-        for (group = 0; group < AWE_K_SHOOT_GROUPS; ++group) switch (group) {
-#include "k_shoot.inc"
+        for (group = 0; group < AWE_K_SHOOT_S2_GROUPS; ++group) switch (group) {
+#include "k_shoot_s2.inc"
+            }
+        for (group = 0; group < AWE_K_SHOOT_S1_GROUPS; ++group) switch (group) {
+#include "k_shoot_s1.inc"
+            }
+        for (group = 0; group < AWE_K_SHOOT_S0_GROUPS; ++group) switch (group) {
+#include "k_shoot_s0.inc"
             }
     } else {
-        for (group = 0; group < AWE_K_SHOOT_RES_GROUPS; ++group) switch (group) {
-#include "k_shoot_res.inc"
+        for (group = 0; group < AWE_K_SHOOT_RES_S2_GROUPS; ++group) switch (group) {
+#include "k_shoot_res_s2.inc"
+            }
+        for (group = 0; group < AWE_K_SHOOT_RES_S1_GROUPS; ++group) switch (group) {
+#include "k_shoot_res_s1.inc"
+            }
+        for (group = 0; group < AWE_K_SHOOT_RES_S0_GROUPS; ++group) switch (group) {
+#include "k_shoot_res_s0.inc"
             }
     }
 }
