@@ -35,6 +35,7 @@ def _fmt(v):
 # between two CTA-wide re-convergence points (instruction-cache locality)
 N_REGS = 48          # FP64 values the allocator keeps in registers (-> ~128 registers per thread)
 LOOKAHEAD = 8        # statements between a scratch reload and its first use
+LEAF_LOOKAHEAD = 40  # statements between an input load (global memory, L2 latency) and its first use
 HOT_SLOTS = 1 << 20  # no cold tier: the grouped programs need only a few dozen scratch slots
 CHUNK = 16           # outputs staged per flush
 GROUP_OPS = 1400     # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
@@ -273,7 +274,7 @@ class NodeCode(object):
         return exports, [(a, b) for a, b, _ in groups]
 
     def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=CHUNK, first=0,
-                       export=False, leaf_names=None):
+                       export=False, leaf_names=None, q0=0):
         """-> (text, stats): register-allocated straight-line code (awebox_b200/schedule.py) printed
         with statement macros:
             LD_XR(reg, r, m) LD_XO(reg, m) LD_XD(reg, m) LD_U(reg, c) LD_Z(reg, c) LD_TH(reg, t)
@@ -282,7 +283,7 @@ class NodeCode(object):
             OVF_ST(slot, reg) OVF_LD(reg, slot)                           cold scratch tier
             OUT(n, value) FLUSH(chunk, count) SYNC_HINT()                 staged outputs
         Scratch slots are ranked by access count; the ``hot_slots`` busiest go to the hot tier."""
-        prog = SCH.allocate(exprs, n_regs, lookahead)
+        prog = SCH.allocate(exprs, n_regs, lookahead, leaf_lookahead=LEAF_LOOKAHEAD)
         access = {}
         for it in prog.ins:
             if it[0] == 'ld':
@@ -296,6 +297,8 @@ class NodeCode(object):
         n_hot = min(len(ranked), hot_slots)
         n_cold = max(0, len(ranked) - hot_slots)
         lines = ['double ' + ', '.join('r%d' % i for i in range(prog.n_regs)) + ';']
+        if not export:
+            lines.append('FLUSH_PREP(%d, %d);' % (q0, first))
 
         def src(s_):
             return _fmt(s_.val) if isinstance(s_, S.Expr) else 'r%d' % s_
@@ -327,7 +330,10 @@ class NodeCode(object):
                     continue
                 lines.append('OUT(%d, %s);' % (n % chunk, src(it[2])))
                 if (n + 1) % chunk == 0 or n + 1 == n_out:
-                    lines.append('FLUSH(%d, %d);' % (first + (n // chunk) * chunk, n % chunk + 1))
+                    last_chunk = n + 1 == n_out
+                    lines.append('FLUSH(%d, %d, %d, %d, %d);' % (
+                        q0 + n // chunk, first + (n // chunk) * chunk, n % chunk + 1,
+                        -1 if last_chunk else q0 + n // chunk + 1, first + (n // chunk + 1) * chunk))
             else:
                 r, n, srcs = it[1], it[2], it[3]
                 lines.append('r%d = %s;' % (r, _rhs(n.op, src(srcs[0]), src(srcs[1]) if len(srcs) > 1 else None)))
@@ -433,9 +439,15 @@ class NodeCode(object):
                         deeper.update(n.idx for n in stages[lv][0])
                     mapping = {n: ex_syms[ex_index[n.idx]] for n in ex_nodes if n.idx in deeper}
                     g_exprs = S.substitute(outs, mapping) if mapping else outs
+                    q0 = 0
+                    chunk_first, chunk_cnt = [], []
                     for g, (a, b) in enumerate(groups):
                         if level == 0:
-                            body, st = self.emit_scheduled(g_exprs[a:b], first=a, leaf_names=leaf_names)
+                            body, st = self.emit_scheduled(g_exprs[a:b], first=a, leaf_names=leaf_names, q0=q0)
+                            for c0 in range(a, b, CHUNK):
+                                chunk_first.append(c0)
+                                chunk_cnt.append(min(CHUNK, b - c0))
+                            q0 += (b - a + CHUNK - 1) // CHUNK
                         else:
                             body, st = self.emit_scheduled(g_exprs[a:b], first=ex_index[outs[a].idx], export=True,
                                                            leaf_names=leaf_names)
@@ -446,6 +458,8 @@ class NodeCode(object):
                         gstats.append(st)
                 files['%s_s%d.inc' % (name, level)] = banner + text
                 sstats.append(gstats)
+                if level == 0:
+                    chunks0 = (chunk_first, chunk_cnt)
             allg = [st for gs in sstats for st in gs]
             hot = max(st['hot_slots'] for st in allg)
             stats[name] = {'stages': sstats, 'n_exports': len(ex_nodes),
@@ -455,6 +469,10 @@ class NodeCode(object):
                 up, len(ex_nodes), up, hot, up, stats[name]['ops_total'])
             for level in range(MAX_STAGES):
                 kdefs += '#define AWE_%s_S%d_GROUPS %d\n' % (up, level, len(sstats[level]))
+            kdefs += '#define AWE_%s_NCHUNKS %d\n' % (up, len(chunks0[0]))
+            kdefs += 'static const int awe_%s_chunk_first[] = {%s};\n' % (name, ', '.join(map(str, chunks0[0])))
+            kdefs += 'static const int awe_%s_chunk_cnt[] = {%s};\n' % (name, ', '.join(map(str, chunks0[1])))
+            stats[name]['n_chunks'] = len(chunks0[0])
         kdefs += '#define AWE_MAX_STAGES %d\n' % MAX_STAGES
         kdefs += '#define AWE_CHUNK %d\n' % CHUNK
         files['model_defs.h'] = head + kdefs

@@ -27,6 +27,8 @@
 #include <string>
 #include <vector>
 #include <mutex>
+#include <algorithm>
+#include <utility>
 
 #include "awegpu.h"
 #include "model_defs.h"
@@ -68,6 +70,10 @@ struct DevProblem {
     int n_coll_out, n_shoot_out, n_shoot_eq, n_ineq, n_periodic, row_periodic, x_last, x_first;
     const int *x_base, *theta_idx, *tf_idx, *row_cont, *periodic_idx;
     const int *coll_dest, *shoot_dest, *const_slot, *const_begin;
+    // interval-cooperative flush of the collocation kernel: for interval k and output chunk q, the
+    // N_D * AWE_CHUNK staged values of the interval's nodes sorted by destination
+    const int *coop_dst;      // [n_k][AWE_K_COLL_NCHUNKS][N_D * AWE_CHUNK]  destination code (-1: none, at the end)
+    const int *coop_src;      // same shape: staged value index  j * AWE_CHUNK + o
     const double *const_val;
     double cscale;
 };
@@ -127,6 +133,7 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 // asm volatile: the compiler must neither merge the generator's reloads into one long-lived register
 // nor hoist them.  Record entries of the 32 lanes are 256 bytes apart: base register + immediate.
 #define LDG_(reg, ptr) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(reg) : "l"(ptr))
+#define LDGI_(reg, ptr) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(reg) : "l"(ptr))
 #define LDS_(reg, addr) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(reg) : "r"(addr))
 #define STS_(addr, reg) asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(reg))
 #define LD_XO(reg, m) LDG_(reg, w_own + (m) * 32)
@@ -146,38 +153,86 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define OVF_LD(reg, slot) SPILL_LD(reg, slot)
 
 // staged output: OUT parks value number n of the current chunk for this lane's instance, FLUSH writes
-// the chunk (outputs first .. first+cnt-1 of the node) for the 32 instances of the tile
+// chunk q (outputs first .. first+cnt-1 of the node) for the 32 instances of the tile and prefetches
+// the destination table of the next chunk
+#define COOP_E ((N_D * AWE_CHUNK + 31) / 32)
 #define OUT(n, val) stg[(n) * STG_STRIDE + lane] = (val)
-#define FLUSH(first, cnt)                                                                                   \
-    do {                                                                                                    \
-        if (BATCH_MINOR)                                                                                    \
-            flush_chunk_bm(stg, dest + (first), cnt, lane, valid, G, Jv, (size_t)B, (size_t)b);             \
-        else                                                                                                \
-            flush_chunk(stg, dest + (first), cnt, lane, n_valid, g_tile, j_tile, n_g, nnz);                 \
+#define FLUSH_PREP(q, first)                                                                         \
+    do {                                                                                             \
+        if (COOP) {                                                                                  \
+            _Pragma("unroll") for (int e_ = 0; e_ < COOP_E; ++e_)                                    \
+            {                                                                                        \
+                LDGI_(fl_code[e_], coop_dst + (q) * (N_D * AWE_CHUNK) + e_ * 32 + lane);             \
+                LDGI_(fl_src[e_], coop_src + (q) * (N_D * AWE_CHUNK) + e_ * 32 + lane);              \
+            }                                                                                        \
+        } else if (!BATCH_MINOR)                                                                     \
+            LDGI_(fl_code[0], dest + (first) + lane % AWE_CHUNK);                                    \
     } while (0)
+#define FLUSH(q, first, cnt, q_next, first_next)                                                     \
+    do {                                                                                             \
+        if (COOP) {                                                                                  \
+            flush_coop(smem + (size_t)HOT * NODE_THREADS, fl_code, fl_src, lane, wid, n_valid, g_tile, j_tile, n_g, nnz); \
+            if ((q_next) >= 0) FLUSH_PREP(q_next, first_next);                                       \
+        } else if (BATCH_MINOR)                                                                      \
+            flush_chunk_bm(stg, dest + (first), cnt, lane, valid, G, Jv, (size_t)B, (size_t)b);      \
+        else {                                                                                       \
+            flush_chunk(stg, fl_code[0], cnt, lane, n_valid, g_tile, j_tile, n_g, nnz);              \
+            if ((q_next) >= 0) FLUSH_PREP(q_next, first_next);                                       \
+        }                                                                                            \
+    } while (0)
+
+// interval-cooperative flush: the N_D warps of the CTA are the N_D collocation nodes of one interval of
+// the same 32 instances.  Their staged chunks together cover a (nearly) contiguous range of the CCS
+// value array; lane = position in that range (destination-sorted table), warp w writes instances
+// w, w + N_D, ...: every store instruction writes 32 neighbouring entries of one instance.
+__device__ __forceinline__ void flush_coop(const double *stg_cta, const int (&code)[COOP_E], const int (&src)[COOP_E],
+                                           const int lane, const int wid, const int n_valid, double *__restrict__ g_tile,
+                                           double *__restrict__ j_tile, const int n_g, const int nnz)
+{
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < COOP_E; ++e) {
+        // one base pointer, 32-bit element offsets (a tile spans < 2^31 elements of g / jac values)
+        const bool is_j = code[e] >= 0;
+        double *base = is_j ? j_tile : g_tile;
+        const int step = (is_j ? nnz : n_g) * N_D;
+        int off = (is_j ? code[e] : -2 - code[e]) + wid * (is_j ? nnz : n_g);
+        const double *s = stg_cta + src[e] * STG_STRIDE + wid;
+        if (code[e] != -1 && base != nullptr) {
+#pragma unroll 1
+            for (int i = wid; i < n_valid; i += N_D) {
+                __stcs(base + off, *s);
+                off += step;
+                s += N_D;
+            }
+        }
+    }
+    __syncthreads();
+}
 
 // lane = (instance group, output): output o = lane % AWE_CHUNK of the chunk, instances i = lane / AWE_CHUNK,
 // + 32 / AWE_CHUNK, ...: every store instruction writes AWE_CHUNK neighbouring outputs of 32 / AWE_CHUNK
 // instances
-__device__ __forceinline__ void flush_chunk(double *stg, const int *__restrict__ dest, const int cnt, const int lane,
+__device__ __forceinline__ void flush_chunk(double *stg, const int code_in, const int cnt, const int lane,
                                             const int n_valid, double *__restrict__ g_tile, double *__restrict__ j_tile,
-                                            const int n_g, const long long nnz)
+                                            const int n_g, const int nnz)
 {
     constexpr int GROUPS = 32 / AWE_CHUNK;
     __syncwarp();
     const int o = lane % AWE_CHUNK, i0 = lane / AWE_CHUNK;
-    const int code = o < cnt ? __ldg(dest + o) : -1;
-    double *p = nullptr;
-    size_t stride = 0;
-    if (code >= 0) {
-        if (j_tile) p = j_tile + code, stride = (size_t)nnz;
-    } else if (code <= -2) {
-        p = g_tile + (-2 - code), stride = (size_t)n_g;
-    }
-    if (p) {
-        const double *src = stg + o * STG_STRIDE;
-#pragma unroll 4
-        for (int i = i0; i < n_valid; i += GROUPS) p[(size_t)i * stride] = src[i];
+    const int code = o < cnt ? code_in : -1;
+    const bool is_j = code >= 0;
+    double *base = is_j ? j_tile : g_tile;
+    const int step = (is_j ? nnz : n_g) * GROUPS;
+    int off = (is_j ? code : -2 - code) + i0 * (is_j ? nnz : n_g);
+    const double *s = stg + o * STG_STRIDE + i0;
+    if (code != -1 && base != nullptr) {
+#pragma unroll 1
+        for (int i = i0; i < n_valid; i += GROUPS) {
+            __stcs(base + off, *s);
+            off += step;
+            s += GROUPS;
+        }
     }
     __syncwarp();
 }
@@ -193,9 +248,9 @@ __device__ __forceinline__ void flush_chunk_bm(double *stg, const int *__restric
         const double v = stg[o * STG_STRIDE + lane];
         if (!valid) continue;
         if (code >= 0) {
-            if (Jv) Jv[(size_t)code * B + b] = v;
+            if (Jv) __stcs(Jv + (size_t)code * B + b, v);
         } else if (code <= -2)
-            G[(size_t)(-2 - code) * B + b] = v;
+            __stcs(G + (size_t)(-2 - code) * B + b, v);
     }
     __syncwarp();
 }
@@ -325,6 +380,8 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
 {
     constexpr int HOT = HOT_OF(SHOOT, FULL);
     constexpr int NEX = EXPORTS_OF(SHOOT, FULL);
+    // the cooperative flush needs the CTA to be exactly the N_D nodes of one interval
+    constexpr bool COOP = !SHOOT && FULL && STAGE == 0 && !BATCH_MINOR && N_D == NODE_WARPS;
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int item = blockIdx.x * NODE_WARPS + wid;
@@ -342,7 +399,7 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
     const bool valid = b < B;
     const int n_valid = min(TILE, B - b0);
     const int n_g = pr.n_g;
-    const long long nnz = pr.nnz;
+    const int nnz = (int)pr.nnz;
     double *stg = smem + (size_t)HOT * NODE_THREADS + wid * STG_DOUBLES;
     const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
 
@@ -359,8 +416,11 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
     const int *dest = SHOOT ? pr.shoot_dest + (size_t)k * pr.n_shoot_out
                             : pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
     double *g_tile = G + (size_t)b0 * n_g;
-    double *j_tile = Jv ? Jv + (size_t)b0 * nnz : nullptr;
-    (void)dest, (void)g_tile, (void)j_tile;
+    double *j_tile = Jv ? Jv + (size_t)b0 * (size_t)nnz : nullptr;
+    const int *coop_dst = pr.coop_dst + (size_t)k * AWE_K_COLL_NCHUNKS * (N_D * AWE_CHUNK);
+    const int *coop_src = pr.coop_src + (size_t)k * AWE_K_COLL_NCHUNKS * (N_D * AWE_CHUNK);
+    int fl_code[COOP_E], fl_src[COOP_E];
+    (void)dest, (void)g_tile, (void)j_tile, (void)coop_dst, (void)coop_src, (void)fl_code, (void)fl_src;
 #define RUN(FILE_)           \
     switch (group) {         \
         FILE_                \
@@ -583,7 +643,30 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
                 n < p->n_shoot_eq                ? -2 - (p->row_shoot[k] + n)
                 : n < p->n_shoot_eq + p->n_ineq ? -2 - (p->row_path[k] + n - p->n_shoot_eq)
                                                 : p->shoot_slot[(size_t)k * p->n_shoot_out + n];
+    // interval-cooperative flush tables (collocation kernel, stage 0)
+    const int per = N_D * AWE_CHUNK;
+    std::vector<int> coop_dst((size_t)nk * AWE_K_COLL_NCHUNKS * per, -1), coop_src((size_t)nk * AWE_K_COLL_NCHUNKS * per, 0);
+    for (int k = 0; k < nk; ++k)
+        for (int q = 0; q < AWE_K_COLL_NCHUNKS; ++q) {
+            std::vector<std::pair<long long, int>> ent;
+            for (int j = 0; j < dd; ++j)
+                for (int o = 0; o < awe_k_coll_chunk_cnt[q]; ++o) {
+                    const int code = coll_dest[((size_t)k * dd + j) * p->n_coll_out + awe_k_coll_chunk_first[q] + o];
+                    if (code == -1) continue;
+                    // g rows first (ascending row), then CCS slots (ascending)
+                    const long long key = code <= -2 ? (long long)(-2 - code) : (1ll << 40) + code;
+                    ent.push_back({key, j * AWE_CHUNK + o});
+                }
+            std::sort(ent.begin(), ent.end());
+            for (size_t e = 0; e < ent.size(); ++e) {
+                const long long key = ent[e].first;
+                coop_dst[((size_t)k * AWE_K_COLL_NCHUNKS + q) * per + e] = key >= (1ll << 40) ? (int)(key - (1ll << 40)) : -2 - (int)key;
+                coop_src[((size_t)k * AWE_K_COLL_NCHUNKS + q) * per + e] = ent[e].second;
+            }
+        }
     int rc = 0;
+    rc |= to_device(h, coop_dst.data(), coop_dst.size(), &d.coop_dst);
+    rc |= to_device(h, coop_src.data(), coop_src.size(), &d.coop_src);
     rc |= to_device(h, p->x_base, (size_t)nk * (dd + 1), &d.x_base);
     rc |= to_device(h, p->theta_idx, (size_t)nk * p->n_theta, &d.theta_idx);
     rc |= to_device(h, p->tf_idx, (size_t)nk, &d.tf_idx);

@@ -72,7 +72,7 @@ class Program(object):
         self.stats = {}
 
 
-def allocate(outputs, n_regs, lookahead=12, seq=None):
+def allocate(outputs, n_regs, lookahead=12, seq=None, leaf_lookahead=None):
     seq = order(outputs) if seq is None else seq
     # ---- schedule with output statements in output order
     pos_of = {n.idx: i for i, n in enumerate(seq)}
@@ -117,6 +117,7 @@ def allocate(outputs, n_regs, lookahead=12, seq=None):
         ptr[v] = p
         return u[p] if p < len(u) else 1 << 30
 
+    leaf_lookahead = lookahead if leaf_lookahead is None else max(lookahead, leaf_lookahead)
     prog = Program()
     ins = prog.ins
     reg_of = {}                 # value idx -> register
@@ -191,13 +192,34 @@ def allocate(outputs, n_regs, lookahead=12, seq=None):
                     free_slots.append(s)
 
     n_sched = len(sched)
+    # opening burst: every input the first window needs is requested before the first operation, so that
+    # the cold misses of a program overlap instead of queueing behind one another
+    if leaf_lookahead > lookahead:
+        first = set()
+        for it in sched[:min(n_sched, leaf_lookahead + 1)]:
+            for v in srcs_of(it):
+                if is_leaf(v):
+                    first.add(v.idx)
+        for it in sched[:min(n_sched, leaf_lookahead + 1)]:
+            for v in srcs_of(it):
+                if is_leaf(v) and len(reg_of) < n_regs - 8:
+                    bring(v, 0, first)
     for i, item in enumerate(sched):
-        # values needed in the look-ahead window are pinned; reloads for the far end are issued now
-        window = sched[i:min(n_sched, i + lookahead + 1)]
+        # values needed in the look-ahead window are pinned; reloads for the far end are issued now.
+        # Input leaves come from global memory (L2 latency): their window is longer than the one of
+        # scratch reloads (shared memory).
         pinned = set()
-        for it in window:
+        for it in sched[i:min(n_sched, i + lookahead + 1)]:
             for v in srcs_of(it):
                 pinned.add(v.idx)
+        for it in sched[i + lookahead + 1:min(n_sched, i + leaf_lookahead + 1)]:
+            for v in srcs_of(it):
+                if is_leaf(v):
+                    pinned.add(v.idx)
+        if i + leaf_lookahead < n_sched and leaf_lookahead > lookahead:
+            for v in srcs_of(sched[i + leaf_lookahead]):
+                if is_leaf(v):
+                    bring(v, i, pinned)
         if i + lookahead < n_sched:
             for v in srcs_of(sched[i + lookahead]):
                 produced_later = is_op(v) and v.idx not in reg_of and v.idx not in slot_of
@@ -230,7 +252,7 @@ def allocate(outputs, n_regs, lookahead=12, seq=None):
             release_dead(src, i)
     prog.n_regs = n_regs
     prog.n_slots = n_slots[0]
-    prog.stats = dict(counts, n_slots=n_slots[0], peak_live_slots=peak_slots[0], n_regs=n_regs, lookahead=lookahead)
+    prog.stats = dict(counts, n_slots=n_slots[0], peak_live_slots=peak_slots[0], n_regs=n_regs, lookahead=lookahead, leaf_lookahead=leaf_lookahead)
     return prog
 
 

@@ -133,6 +133,9 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH, help='instances per GPU')
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--layout', default='instance', choices=['instance', 'batch-minor'],
+                    help='layout of the jac_g value array on the device (diagnostic; the metric uses instance)')
+    ap.add_argument('--no-jac', action='store_true', help='residual only (diagnostic)')
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
@@ -164,6 +167,11 @@ def main():
     dJ = torch.empty((B, ocp.nnz), dtype=torch.float64, device='cuda')
     stream = torch.cuda.current_stream()
 
+    bm = args.layout == 'batch-minor'
+
+    def step():
+        ev.eval_device(dW, dP, dG, None if args.no_jac else dJ, batch_minor=bm)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -171,7 +179,7 @@ def main():
 
     launches0 = ev.launch_count()
     for _ in range(args.warmup):
-        ev.eval_device(dW, dP, dG, dJ)
+        step()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -180,14 +188,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        ev.eval_device(dW, dP, dG, dJ)
+        step()
     e1.record(stream)
     barrier()
     total_ms = e0.elapsed_time(e1)
     gpu_launches = ev.launch_count() - launches1
     # per-launch duration of the one kernel, CUDA events on the launching stream (a few extra launches)
     for _ in range(5):
-        ev.eval_device(dW, dP, dG, dJ)
+        step()
         torch.cuda.synchronize()
         kernel_ms.append(ev.last_eval_ms())
     sampler.stop_flag = True

@@ -35,7 +35,8 @@
 #define OVF_LD(reg, slot) reg = cold[slot]
 #define SYNC_HINT()
 #define OUT(n, val) stg_[n] = (val)
-#define FLUSH(first, cnt) do { int q_; for (q_ = 0; q_ < (cnt); ++q_) out[(first) + q_] = stg_[q_]; } while (0)
+#define FLUSH_PREP(q, first)
+#define FLUSH(q, first, cnt, qn, fn) do { int q_; for (q_ = 0; q_ < (cnt); ++q_) out[(first) + q_] = stg_[q_]; } while (0)
 
 /* xo [n_x] state block of the node, xd [n_x] its time derivative, u, z, th, p [n_param], cc [d+1], itf,
  * j1 = own block index in 1..d (collocation) */
