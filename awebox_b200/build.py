@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '--shared', '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-diag-suppress', '177', '-DAWE_NODE_CTAS=3']
+              '--shared', '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-diag-suppress', '177']
 
 
 def gen_dir(spec_name):
@@ -57,14 +57,14 @@ def find_nvcc():
     return nvcc
 
 
-def compile_cuda(spec_name, force=False, verbose=False, extra_flags=()):
+def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None):
     os.makedirs(LIBDIR, exist_ok=True)
     g = gen_dir(spec_name)
     srcs = [os.path.join(CSRC, 'awegpu_kernels.cu')]
     deps = srcs + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
         [os.path.join(g, f) for f in sorted(os.listdir(g)) if f.endswith(('.h', '.inc'))] + \
         [os.path.join(ROOT, 'include', 'awegpu.h')]
-    out = lib_path(spec_name)
+    out = out or lib_path(spec_name)
     stamp = out + '.sha256'
     digest = _digest(deps) + ''.join(extra_flags)
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == digest:

@@ -34,6 +34,9 @@
 #include "model_defs.h"
 
 #define TILE 32
+#ifndef AWE_NODE_CTAS
+#define AWE_NODE_CTAS 3          /* resident CTAs (of 4 warps) per SM the node kernels are compiled for */
+#endif
 #define N_X AWE_N_X
 #define N_U AWE_N_U
 #define N_Z AWE_N_Z
@@ -132,8 +135,16 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 // ---- statement macros of the generated code -------------------------------------------------------
 // asm volatile: the compiler must neither merge the generator's reloads into one long-lived register
 // nor hoist them.  Record entries of the 32 lanes are 256 bytes apart: base register + immediate.
+#ifdef AWE_VOLATILE_LD
+#define LDG_(reg, ptr) asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(reg) : "l"(ptr))
+#else
 #define LDG_(reg, ptr) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(reg) : "l"(ptr))
+#endif
+#ifdef AWE_VOLATILE_LD
+#define LDGI_(reg, ptr) asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(reg) : "l"(ptr))
+#else
 #define LDGI_(reg, ptr) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(reg) : "l"(ptr))
+#endif
 #define LDS_(reg, addr) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(reg) : "r"(addr))
 #define STS_(addr, reg) asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(reg))
 #define LD_XO(reg, m) LDG_(reg, w_own + (m) * 32)
@@ -141,7 +152,7 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define LD_U(reg, c) LDG_(reg, w_rec + (OFF_U + (c)) * 32)
 #define LD_Z(reg, c) LDG_(reg, w_z + (c) * 32)
 #define LD_TH(reg, t) LDG_(reg, w_rec + (REC_TH + (t)) * 32)
-#define LD_P(reg, i) LDG_(reg, ((i) < AWE_N_THETA0 ? w_pt + (i) * 32 : w_rec + (REC_PHI + (i) - AWE_N_THETA0) * 32))
+#define LD_P(reg, i) LDG_(reg, ((i) < AWE_N_THETA0 ? w_pt + (i) * p_es : w_rec + (REC_PHI + (i) - AWE_N_THETA0) * 32))
 #define LD_EX(reg, i) LDG_(reg, w_ex + (i) * 32)
 #define EXOUT(i, val) w_ex[(i) * 32] = (val)
 #define LD_CC(reg, r) reg = c_coeff_coll[(r) * (N_D + 1) + j1] * itf_nk
@@ -156,6 +167,9 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 // chunk q (outputs first .. first+cnt-1 of the node) for the 32 instances of the tile and prefetches
 // the destination table of the next chunk
 #define COOP_E ((N_D * AWE_CHUNK + 31) / 32)
+#ifndef AWE_EXP_NO_FLUSH
+#define AWE_EXP_NO_FLUSH 0
+#endif
 #define OUT(n, val) stg[(n) * STG_STRIDE + lane] = (val)
 #define FLUSH_PREP(q, first)                                                                         \
     do {                                                                                             \
@@ -171,7 +185,7 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define FLUSH(q, first, cnt, q_next, first_next)                                                     \
     do {                                                                                             \
         if (COOP) {                                                                                  \
-            flush_coop(smem + (size_t)HOT * NODE_THREADS, fl_code, fl_src, lane, wid, n_valid, g_tile, j_tile, n_g, nnz); \
+            if (!AWE_EXP_NO_FLUSH) flush_coop(smem + (size_t)HOT * NODE_THREADS, fl_code, fl_src, lane, wid, n_valid, g_tile, j_tile, n_g, nnz); \
             if ((q_next) >= 0) FLUSH_PREP(q_next, first_next);                                       \
         } else if (BATCH_MINOR)                                                                      \
             flush_chunk_bm(stg, dest + (first), cnt, lane, valid, G, Jv, (size_t)B, (size_t)b);      \
@@ -201,7 +215,9 @@ __device__ __forceinline__ void flush_coop(const double *stg_cta, const int (&co
         if (code[e] != -1 && base != nullptr) {
 #pragma unroll 1
             for (int i = wid; i < n_valid; i += N_D) {
+#ifndef AWE_EXP_NO_STORE
                 __stcs(base + off, *s);
+#endif
                 off += step;
                 s += N_D;
             }
@@ -306,7 +322,7 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
         }
     }
     // ---- theta0, lane-contiguous (one copy per tile)
-    if (k == 0) {
+    if (k == 0 && ldp != 0) {
         double *pt = sc.pt + (size_t)tile * pr.n_theta0 * 32;
         const double *pl = P + (size_t)bl * ldp + p_off;
         for (int e = tid; e < pr.n_theta0 * 32; e += GATHER_THREADS) pt[e] = __ldg(pl + (e >> 5));
@@ -376,7 +392,7 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
 template <bool SHOOT, bool FULL, int STAGE, bool BATCH_MINOR>
 __global__ void __launch_bounds__(NODE_THREADS, AWE_NODE_CTAS)
 awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const int n_items,
-                   double *__restrict__ G, double *__restrict__ Jv)
+                   const double *__restrict__ p_shared, const int ilv, double *__restrict__ G, double *__restrict__ Jv)
 {
     constexpr int HOT = HOT_OF(SHOOT, FULL);
     constexpr int NEX = EXPORTS_OF(SHOOT, FULL);
@@ -384,9 +400,22 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
     constexpr bool COOP = !SHOOT && FULL && STAGE == 0 && !BATCH_MINOR && N_D == NODE_WARPS;
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int item = blockIdx.x * NODE_WARPS + wid;
+    // CTA order: blocks of `ilv` consecutive CTA-items, all groups of a block before the next block, so
+    // that the groups that read the same inputs and write into the same sectors run close in time
+    int cta_item, group;
+    {
+        const int n_groups = gridDim.y, n_cta_items = gridDim.x;
+        const int lin = blockIdx.y * n_cta_items + blockIdx.x;          // hardware dispatch order
+        if (ilv > 0) {
+            const int per_block = ilv * n_groups;
+            const int blk = lin / per_block, rem = lin - blk * per_block;
+            const int blk_items = min(ilv, n_cta_items - blk * ilv);   // the last block may be short
+            group = rem / blk_items, cta_item = blk * ilv + rem % blk_items;
+        } else
+            group = blockIdx.y, cta_item = blockIdx.x;
+    }
+    const int item = cta_item * NODE_WARPS + wid;
     if (item >= n_items) return;
-    const int group = blockIdx.y;
     int tile, k, j;
     if (SHOOT) {
         j = -1, k = item % pr.n_k, tile = item / pr.n_k;
@@ -408,7 +437,10 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
     const double *w_z = SHOOT ? w_rec + OFF_Z * 32 : w_own + N_X * 32;
     const double *w_xd = SHOOT ? w_rec + OFF_XDOT * 32
                                : sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
-    const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
+    // theta0: one vector shared by all instances (read in place, same address in every lane), or the
+    // lane-contiguous copy the gather kernel made of the per-instance vectors
+    const double *w_pt = p_shared ? p_shared : sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
+    const int p_es = p_shared ? 1 : 32;
     double *w_ex = (SHOOT ? sc.exs : sc.exc) + (size_t)item * (NEX > 0 ? NEX : 1) * 32 + lane;
     const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
     const double itf_nk = itf * (double)pr.n_k;
@@ -521,7 +553,8 @@ struct awegpu_handle {
     cudaStream_t stream2 = nullptr;
     // node-input records of one chunk of instances (see awegpu_gather_kernel)
     Scratch sc{};
-    int chunk_tiles = 0;
+    int chunk_tiles = 0, scratch_tiles = 0;
+    int interleave = 1;      // tiles per block of the group-interleaved stage-0 order (0: group-major)
     // casadi sparsity buffers
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
     std::vector<double> scratch_g;
@@ -708,20 +741,15 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         const char *env = getenv("AWEGPU_CHUNK_TILES");
         int ct = env ? atoi(env) : 0;
         if (ct <= 0) {
+            // default: the whole batch in one pass, capped by the memory the side buffers may take (2 GiB)
             const size_t per_tile = sizeof(double) * 32 * ((size_t)nk * (REC + (size_t)dd * (N_X + AWE_K_COLL_EXPORTS) +
                                                                          AWE_K_SHOOT_EXPORTS) + p->n_theta0);
-            ct = (int)((64u << 20) / per_tile);
+            ct = (int)(((size_t)2 << 30) / per_tile);
             if (ct < 1) ct = 1;
-            if (ct > 64) ct = 64;
         }
         h->chunk_tiles = ct;
-        CK(cudaMalloc((void **)&h->sc.rec, sizeof(double) * 32 * (size_t)ct * nk * REC));
-        CK(cudaMalloc((void **)&h->sc.xdc, sizeof(double) * 32 * (size_t)ct * nk * dd * N_X));
-        CK(cudaMalloc((void **)&h->sc.pt, sizeof(double) * 32 * (size_t)ct * p->n_theta0));
-        constexpr size_t nec = AWE_K_COLL_EXPORTS > AWE_K_COLL_RES_EXPORTS ? AWE_K_COLL_EXPORTS : AWE_K_COLL_RES_EXPORTS;
-        constexpr size_t nes = AWE_K_SHOOT_EXPORTS > AWE_K_SHOOT_RES_EXPORTS ? AWE_K_SHOOT_EXPORTS : AWE_K_SHOOT_RES_EXPORTS;
-        CK(cudaMalloc((void **)&h->sc.exc, sizeof(double) * 32 * (size_t)ct * nk * dd * (nec ? nec : 1)));
-        CK(cudaMalloc((void **)&h->sc.exs, sizeof(double) * 32 * (size_t)ct * nk * (nes ? nes : 1)));
+        const char *ei = getenv("AWEGPU_INTERLEAVE");
+        h->interleave = ei ? atoi(ei) : 1;
     }
     // host copies of pointers are not kept: null them so nobody dereferences caller memory later
     h->host.x_base = h->host.x_next = h->host.u_base = h->host.xdot_base = h->host.z_base = nullptr;
@@ -751,6 +779,27 @@ extern "C" int awegpu_sparsity(awegpu_handle_t *h, int64_t *colind, int64_t *row
     return 0;
 }
 
+// side buffers for `tiles` tiles (grown on demand, never shrunk; growth synchronises the device)
+static int ensure_scratch(awegpu_handle *h, int tiles)
+{
+    if (tiles <= h->scratch_tiles) return 0;
+    const DevProblem &d = h->dp;
+    constexpr size_t nec = AWE_K_COLL_EXPORTS > AWE_K_COLL_RES_EXPORTS ? AWE_K_COLL_EXPORTS : AWE_K_COLL_RES_EXPORTS;
+    constexpr size_t nes = AWE_K_SHOOT_EXPORTS > AWE_K_SHOOT_RES_EXPORTS ? AWE_K_SHOOT_EXPORTS : AWE_K_SHOOT_RES_EXPORTS;
+    CK(cudaDeviceSynchronize());
+    cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
+    h->sc = Scratch{};
+    h->scratch_tiles = 0;
+    const size_t line = sizeof(double) * 32, t = (size_t)tiles, nk = (size_t)d.n_k;
+    CK(cudaMalloc((void **)&h->sc.rec, line * t * nk * REC));
+    CK(cudaMalloc((void **)&h->sc.xdc, line * t * nk * N_D * N_X));
+    CK(cudaMalloc((void **)&h->sc.pt, line * t * (size_t)d.n_theta0));
+    CK(cudaMalloc((void **)&h->sc.exc, line * t * nk * N_D * (nec ? nec : 1)));
+    CK(cudaMalloc((void **)&h->sc.exs, line * t * nk * (nes ? nes : 1)));
+    h->scratch_tiles = tiles;
+    return 0;
+}
+
 extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W, const double *P, double *G,
                                  double *Jv, int32_t flags, void *stream)
 {
@@ -775,12 +824,18 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
     const bool full = jv != nullptr, bm = (flags & AWEGPU_JAC_BATCH_MINOR) != 0;
     const int tiles = (B + TILE - 1) / TILE;
     const DevProblem &dp = h->dp;
+    {
+        const int rc_ = ensure_scratch(h, tiles < h->chunk_tiles ? tiles : h->chunk_tiles);
+        if (rc_) return rc_;
+    }
+    const double *p_sh = (flags & AWEGPU_P_SHARED) ? P + p_off : nullptr;
     CK(cudaEventRecord(h->ev0, st));
 #define LAUNCH_STAGE(S_, F, T_, M, n_)                                                                            \
     do {                                                                                                          \
         if (node_groups<S_, F, T_>() > 0) {                                                                       \
             awegpu_node_kernel<S_, F, T_, M><<<dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>()), \
-                                               NODE_THREADS, node_smem_bytes<S_, F>(), st>>>(dp, h->sc, B, b_base, n_, G, jv); \
+                                               NODE_THREADS, node_smem_bytes<S_, F>(), st>>>(dp, h->sc, B, b_base, n_, p_sh,           \
+                                                                                             (T_) == 0 ? h->interleave * (((S_) ? dp.n_k : dp.n_k * N_D) + NODE_WARPS - 1) / NODE_WARPS : 0, G, jv); \
             h->launches += 1;                                                                                     \
         }                                                                                                         \
     } while (0)

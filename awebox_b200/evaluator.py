@@ -23,7 +23,7 @@ class AwegpuError(RuntimeError):
 
 
 def load_library(spec_name):
-    path = lib_path(spec_name)
+    path = os.environ.get('AWEGPU_LIB') or lib_path(spec_name)      # AWEGPU_LIB: kernel-tuning experiments
     if not os.path.exists(path):
         raise AwegpuError('CUDA library %s is missing: run `python -m awebox_b200.build %s` '
                           '(there is no CPU fallback)' % (path, spec_name))
