@@ -306,8 +306,12 @@ class NodeCode(object):
         n_stmt = 0
         n_out = len(exprs)
         cold_acc = 0
+        prev_leaf = False
         for it in prog.ins:
             k = it[0]
+            if prev_leaf and k != 'leaf':
+                lines.append('LEAF_FENCE();')      # keeps the loads above from being sunk to their uses
+            prev_leaf = k == 'leaf'
             if k == 'leaf':
                 name = (leaf_names or self.k_leaf)[it[2].idx]
                 if '(' in name:

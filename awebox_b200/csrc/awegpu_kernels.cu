@@ -147,6 +147,9 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #endif
 #define LDS_(reg, addr) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(reg) : "r"(addr))
 #define STS_(addr, reg) asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(reg))
+// ptxas sinks loads towards their first use to save registers, which would undo the generator's
+// look-ahead; it does not move memory operations across a warp barrier
+#define LEAF_FENCE() asm volatile("bar.warp.sync 0xffffffff;" ::: "memory")
 #define LD_XO(reg, m) LDG_(reg, w_own + (m) * 32)
 #define LD_XD(reg, m) LDG_(reg, w_xd + (m) * 32)
 #define LD_U(reg, c) LDG_(reg, w_rec + (OFF_U + (c)) * 32)
@@ -179,8 +182,12 @@ __device__ __forceinline__ double sqrt_nr(const double x)
                 LDGI_(fl_code[e_], coop_dst + (q) * (N_D * AWE_CHUNK) + e_ * 32 + lane);             \
                 LDGI_(fl_src[e_], coop_src + (q) * (N_D * AWE_CHUNK) + e_ * 32 + lane);              \
             }                                                                                        \
+            LEAF_FENCE();                                                                            \
         } else if (!BATCH_MINOR)                                                                     \
+        {                                                                                            \
             LDGI_(fl_code[0], dest + (first) + lane % AWE_CHUNK);                                    \
+            LEAF_FENCE();                                                                            \
+        }                                                                                            \
     } while (0)
 #define FLUSH(q, first, cnt, q_next, first_next)                                                     \
     do {                                                                                             \
@@ -542,7 +549,7 @@ struct awegpu_handle {
     std::vector<void *> dev_allocs;
     std::vector<long long> colind, row;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     float last_ms = -1.f;
     long long launches = 0;
     std::string err;
@@ -550,7 +557,8 @@ struct awegpu_handle {
     double *dW = nullptr, *dP = nullptr, *dG = nullptr, *dJ = nullptr;
     double *hW = nullptr, *hP = nullptr, *hG = nullptr, *hJ = nullptr;
     size_t capW = 0, capP = 0, capG = 0, capJ = 0, hcapW = 0, hcapP = 0, hcapG = 0, hcapJ = 0;
-    cudaStream_t stream2 = nullptr;
+    cudaStream_t stream2 = nullptr, stream_in = nullptr, stream_out = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
     // node-input records of one chunk of instances (see awegpu_gather_kernel)
     Scratch sc{};
     int chunk_tiles = 0, scratch_tiles = 0;
@@ -616,8 +624,13 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_k0) cudaEventDestroy(h->ev_k0);
+    if (h->ev_k1) cudaEventDestroy(h->ev_k1);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream_in) cudaStreamDestroy(h->stream_in);
+    if (h->stream_out) cudaStreamDestroy(h->stream_out);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
 
@@ -718,6 +731,8 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreate(&h->ev_k0));
+    CK(cudaEventCreate(&h->ev_k1));
 #define SET_SMEM(kern, bytes) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
 #define SET_NODE1(S_, F_, T_)                                                             \
     SET_SMEM((awegpu_node_kernel<S_, F_, T_, false>), (node_smem_bytes<S_, F_>()));       \
@@ -830,11 +845,11 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
     }
     const double *p_sh = (flags & AWEGPU_P_SHARED) ? P + p_off : nullptr;
     CK(cudaEventRecord(h->ev0, st));
-#define LAUNCH_STAGE(S_, F, T_, M, n_)                                                                            \
+#define LAUNCH_STAGE(S_, F, T_, M, n_, st_)                                                                       \
     do {                                                                                                          \
         if (node_groups<S_, F, T_>() > 0) {                                                                       \
             awegpu_node_kernel<S_, F, T_, M><<<dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>()), \
-                                               NODE_THREADS, node_smem_bytes<S_, F>(), st>>>(dp, h->sc, B, b_base, n_, p_sh,           \
+                                               NODE_THREADS, node_smem_bytes<S_, F>(), st_>>>(dp, h->sc, B, b_base, n_, p_sh,          \
                                                                                              (T_) == 0 ? h->interleave * (((S_) ? dp.n_k : dp.n_k * N_D) + NODE_WARPS - 1) / NODE_WARPS : 0, G, jv); \
             h->launches += 1;                                                                                     \
         }                                                                                                         \
@@ -842,12 +857,16 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
 #define LAUNCH_NODES(F, M)                                \
     do {                                                  \
         const int nc_ = ct * dp.n_k * N_D, ns_ = ct * dp.n_k; \
-        LAUNCH_STAGE(false, F, 2, M, nc_);                \
-        LAUNCH_STAGE(true, F, 2, M, ns_);                 \
-        LAUNCH_STAGE(false, F, 1, M, nc_);                \
-        LAUNCH_STAGE(true, F, 1, M, ns_);                 \
-        LAUNCH_STAGE(false, F, 0, M, nc_);                \
-        LAUNCH_STAGE(true, F, 0, M, ns_);                 \
+        /* one stream: running the shooting chain beside the collocation chain was measured and */ \
+        /* bought nothing (every kernel fills the SMs on its own)                                */ \
+        LAUNCH_STAGE(false, F, 2, M, nc_, st);            \
+        LAUNCH_STAGE(true, F, 2, M, ns_, st);             \
+        LAUNCH_STAGE(false, F, 1, M, nc_, st);            \
+        LAUNCH_STAGE(true, F, 1, M, ns_, st);             \
+        LAUNCH_STAGE(true, F, 0, M, ns_, st);             \
+        if (t0 == 0) CK(cudaEventRecord(h->ev_k0, st));   \
+        LAUNCH_STAGE(false, F, 0, M, nc_, st);            \
+        if (t0 == 0) CK(cudaEventRecord(h->ev_k1, st));   \
     } while (0)
     for (int t0 = 0; t0 < tiles; t0 += h->chunk_tiles) {
         const int ct = (tiles - t0 < h->chunk_tiles) ? (tiles - t0) : h->chunk_tiles;
@@ -894,6 +913,27 @@ extern "C" float awegpu_last_eval_ms(awegpu_handle_t *h)
 
 extern "C" int64_t awegpu_launch_count(awegpu_handle_t *h) { return h ? h->launches : 0; }
 
+extern "C" float awegpu_last_kernel_ms(awegpu_handle_t *h)
+{
+    if (!h || h->last_ms == -1.f) return -1.f;
+    if (cudaEventSynchronize(h->ev_k1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+extern "C" int awegpu_kernel_info(int32_t *n_groups, int32_t *n_exports, int64_t *ops_coll, int64_t *ops_shoot)
+{
+    if (n_groups) {
+        n_groups[0] = AWE_K_COLL_S0_GROUPS, n_groups[1] = AWE_K_COLL_S1_GROUPS, n_groups[2] = AWE_K_COLL_S2_GROUPS;
+        n_groups[3] = AWE_K_SHOOT_S0_GROUPS, n_groups[4] = AWE_K_SHOOT_S1_GROUPS, n_groups[5] = AWE_K_SHOOT_S2_GROUPS;
+    }
+    if (n_exports) n_exports[0] = AWE_K_COLL_EXPORTS, n_exports[1] = AWE_K_SHOOT_EXPORTS;
+    if (ops_coll) *ops_coll = AWE_K_COLL_OPS;
+    if (ops_shoot) *ops_shoot = AWE_K_SHOOT_OPS;
+    return 0;
+}
+
 static int grow(awegpu_handle *h, double **dev, double **host, size_t *cap, size_t *hcap, size_t need, bool with_host)
 {
     if (need > *cap) {
@@ -929,37 +969,48 @@ extern "C" int awegpu_eval_batch_host(awegpu_handle_t *h, int32_t B, const doubl
              (want_j ? grow(h, &h->dJ, &h->hJ, &h->capJ, &h->hcapJ, nJ, stage) : 0);
     if (rc) return rc;
     if (flags & AWEGPU_HOST_PINNED) {
-        // caller buffers are page-locked: copy straight from / into them, in chunks on two streams so
-        // that H2D of chunk c+1, the kernel of chunk c and D2H of chunk c-1 overlap.
-        if (!h->stream2) CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        // caller buffers are page-locked: copy straight from / into them in chunks, H2D of chunk c+1,
+        // the kernels of chunk c and D2H of chunk c-1 overlapping on three streams.  The kernels of all
+        // chunks run on the handle's stream (they share the side buffers).
+        if (flags & AWEGPU_JAC_BATCH_MINOR) {
+            set_err(h, "AWEGPU_HOST_PINNED supports the instance-major layout only");
+            return 1;
+        }
+        if (!h->stream_in) CK(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
+        if (!h->stream_out) CK(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
         const bool shared = (flags & AWEGPU_P_SHARED) != 0;
         if (shared) CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
         const int chunk = 512;
-        int c = 0;
-        for (int b0 = 0; b0 < B; b0 += chunk, ++c) {
+        const int n_chunks = (B + chunk - 1) / chunk;
+        while ((int)h->ev_pool.size() < 2 * n_chunks) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->ev_pool.push_back(e);
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+            const int b0 = c * chunk;
             const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
-            cudaStream_t st = (c & 1) ? h->stream2 : h->stream;
             CK(cudaMemcpyAsync(h->dW + (size_t)b0 * d.n_v, W + (size_t)b0 * d.n_v, (size_t)nb * d.n_v * sizeof(double),
-                               cudaMemcpyHostToDevice, st));
+                               cudaMemcpyHostToDevice, h->stream_in));
             if (!shared)
                 CK(cudaMemcpyAsync(h->dP + (size_t)b0 * p_len, P + (size_t)b0 * p_len, (size_t)nb * p_len * sizeof(double),
-                                   cudaMemcpyHostToDevice, st));
-            if (flags & AWEGPU_JAC_BATCH_MINOR) {
-                set_err(h, "AWEGPU_HOST_PINNED supports the instance-major layout only");
-                return 1;
-            }
+                                   cudaMemcpyHostToDevice, h->stream_in));
+            CK(cudaEventRecord(h->ev_pool[2 * c], h->stream_in));
+            CK(cudaStreamWaitEvent(h->stream, h->ev_pool[2 * c], 0));
             rc = awegpu_eval_batch(h, nb, h->dW + (size_t)b0 * d.n_v, shared ? h->dP : h->dP + (size_t)b0 * p_len,
-                                   h->dG + (size_t)b0 * d.n_g, want_j ? h->dJ + (size_t)b0 * d.nnz : nullptr, flags, st);
+                                   h->dG + (size_t)b0 * d.n_g, want_j ? h->dJ + (size_t)b0 * d.nnz : nullptr, flags, h->stream);
             if (rc) return rc;
+            CK(cudaEventRecord(h->ev_pool[2 * c + 1], h->stream));
+            CK(cudaStreamWaitEvent(h->stream_out, h->ev_pool[2 * c + 1], 0));
             CK(cudaMemcpyAsync(G + (size_t)b0 * d.n_g, h->dG + (size_t)b0 * d.n_g, (size_t)nb * d.n_g * sizeof(double),
-                               cudaMemcpyDeviceToHost, st));
+                               cudaMemcpyDeviceToHost, h->stream_out));
             if (want_j)
                 CK(cudaMemcpyAsync(Jv + (size_t)b0 * d.nnz, h->dJ + (size_t)b0 * d.nnz, (size_t)nb * d.nnz * sizeof(double),
-                                   cudaMemcpyDeviceToHost, st));
+                                   cudaMemcpyDeviceToHost, h->stream_out));
         }
+        CK(cudaStreamSynchronize(h->stream_in));
         CK(cudaStreamSynchronize(h->stream));
-        CK(cudaStreamSynchronize(h->stream2));
+        CK(cudaStreamSynchronize(h->stream_out));
         return 0;
     }
     memcpy(h->hW, W, nW * sizeof(double));

@@ -44,6 +44,9 @@ def load_library(spec_name):
                                            C.c_int32]
     lib.awegpu_last_eval_ms.restype = C.c_float
     lib.awegpu_last_eval_ms.argtypes = [C.c_void_p]
+    lib.awegpu_last_kernel_ms.restype = C.c_float
+    lib.awegpu_last_kernel_ms.argtypes = [C.c_void_p]
+    lib.awegpu_kernel_info.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.awegpu_launch_count.restype = C.c_int64
     lib.awegpu_launch_count.argtypes = [C.c_void_p]
     lib.awegpu_synchronize.argtypes = [C.c_void_p]
@@ -158,6 +161,17 @@ class Evaluator(object):
 
     def last_eval_ms(self):
         return float(self.lib.awegpu_last_eval_ms(self.handle))
+
+    def last_kernel_ms(self):
+        """device time of the dominant kernel (collocation node programs, output stage) of the last eval."""
+        return float(self.lib.awegpu_last_kernel_ms(self.handle))
+
+    def kernel_info(self):
+        g, e = (C.c_int32 * 6)(), (C.c_int32 * 2)()
+        oc, os_ = C.c_int64(0), C.c_int64(0)
+        self.lib.awegpu_kernel_info(g, e, C.byref(oc), C.byref(os_))
+        return {'groups_coll': list(g[:3]), 'groups_shoot': list(g[3:]), 'exports_coll': int(e[0]),
+                'exports_shoot': int(e[1]), 'ops_coll_node': int(oc.value), 'ops_shoot_node': int(os_.value)}
 
     def launch_count(self):
         return int(self.lib.awegpu_launch_count(self.handle))

@@ -180,10 +180,26 @@ class OcpProblem(object):
             self.coll_out.append(('res', i))
         #   ('Xc', i, m, r): d r_i/d X_r[m] through xdot (plus the direct part when r is the node's own
         #   block and (i, m) is also a direct dependency);  ('Xo', i, m): direct-only dependency.
-        #   Order = column order of V inside the interval (theta, phi, X_0, u, X_1 .. X_d), the node's
-        #   own-block-only entries last: outputs that are neighbours here are neighbours (or share a
-        #   column with the entries of the interval's other nodes) in the CCS value array, which is what
-        #   the interval-cooperative flush of the CUDA kernels needs.
+        #   Order: state component m outermost.  Everything derived from d r/d x_m and d r/d xdot_m is
+        #   emitted together (short live ranges in the generated code), and one output chunk of the d
+        #   nodes of an interval then holds the complete interval part of the CCS columns X_r[m],
+        #   r = 0..d — what the interval-cooperative flush of the CUDA kernels turns into full sectors.
+        for mm in range(self.n_x):
+            for i in range(self.n_eq):
+                if mm in eq_split[i]['x'] and mm not in eq_split[i]['xdot']:
+                    self.coll_out.append(('Xo', i, mm))
+            for r in range(d + 1):
+                for i in range(self.n_eq):
+                    if mm in eq_split[i]['xdot']:
+                        self.coll_out.append(('Xc', i, mm, r))
+        for c in range(self.n_u):
+            for i in range(self.n_eq):
+                if c in eq_split[i]['u']:
+                    self.coll_out.append(('u', i, c))
+        for c in range(self.n_z):
+            for i in range(self.n_eq):
+                if c in eq_split[i]['z']:
+                    self.coll_out.append(('z', i, c))
         for t in range(self.n_theta):
             for i in range(self.n_eq):
                 direct = t in eq_split[i]['theta']
@@ -194,24 +210,6 @@ class OcpProblem(object):
             for i in range(self.n_eq):
                 if c in eq_split[i]['phi']:
                     self.coll_out.append(('phi', i, c))
-        for r in range(d + 1):
-            for mm in range(self.n_x):
-                for i in range(self.n_eq):
-                    if mm in eq_split[i]['xdot']:
-                        self.coll_out.append(('Xc', i, mm, r))
-            if r == 0:
-                for c in range(self.n_u):
-                    for i in range(self.n_eq):
-                        if c in eq_split[i]['u']:
-                            self.coll_out.append(('u', i, c))
-        for mm in range(self.n_x):
-            for i in range(self.n_eq):
-                if mm in eq_split[i]['x'] and mm not in eq_split[i]['xdot']:
-                    self.coll_out.append(('Xo', i, mm))
-        for c in range(self.n_z):
-            for i in range(self.n_eq):
-                if c in eq_split[i]['z']:
-                    self.coll_out.append(('z', i, c))
         self.eq_split = eq_split
 
         # ---- shooting-node local outputs: residual rows then direct entries

@@ -194,10 +194,12 @@ def main():
     total_ms = e0.elapsed_time(e1)
     gpu_launches = ev.launch_count() - launches1
     # per-launch duration of the one kernel, CUDA events on the launching stream (a few extra launches)
+    step_ms = []
     for _ in range(5):
         step()
         torch.cuda.synchronize()
-        kernel_ms.append(ev.last_eval_ms())
+        step_ms.append(ev.last_eval_ms())
+        kernel_ms.append(ev.last_kernel_ms())
     sampler.stop_flag = True
     t = torch.tensor([total_ms], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -233,15 +235,26 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        # dominant kernel: the output stage of the collocation-node programs (awegpu_node_kernel<coll, full,
+        # stage 0>), one launch per step.  Algorithmic bytes of that launch: every collocation node reads
+        # its input column once ([x; xdot; z] per node, [u; theta; phi] per interval) and writes its
+        # residual rows and Jacobian entries once.
         k_ms = float(np.median(kernel_ms))
-        alg_bytes = B * ocp.algorithmic_bytes()
+        s_ms = float(np.median(step_ms))
+        n_nodes = B * ocp.n_k * ocp.d
+        entries = int((ocp.coll_slot >= 0).sum())                       # Jacobian entries of all coll nodes, one instance
+        per_inst = 8 * (entries + ocp.n_k * ocp.d * (ocp.n_eq + 2 * ocp.n_x + ocp.n_z)
+                        + ocp.n_k * (ocp.n_u + ocp.n_theta + ocp.n_phi))
+        alg_bytes = B * per_inst
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        info = ev.kernel_info()
         flops = B * (ocp.n_k * ocp.d * ev.flops_coll + ocp.n_k * ev.flops_shoot)
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get('dram_bytes_per_launch')
+        step_bytes = B * ocp.algorithmic_bytes()
         cpu_v, cpu_dt, cpu_n, cpu_thr = cpu_leg(ocp, os.cpu_count(), args.cpu_seconds, W, p)
         line = {
             'metric': 'collocation-node g+Jacobian evals/s', 'value': value, 'unit': 'node-evals/s',
@@ -250,6 +263,7 @@ def main():
             'config': {'workload': WORKLOAD, 'n_k': N_K, 'd': ocp.d, 'instances_per_gpu': B, 'n_v': ocp.n_v,
                        'n_g': ocp.n_g, 'nnz': int(ocp.nnz), 'jac_layout': 'instance-major CCS values',
                        'l2': 'inputs+outputs per step (3.2 GB) exceed the 126 MB L2; no flush needed',
+                       'kernels_per_step': 'gather + 3 collocation stages + 2 shooting stages',
                        'parallelism': 'batch sharded over %d GPU(s), no data-path collective' % world},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': 'node-evals/s',
@@ -258,9 +272,20 @@ def main():
                     'api': 'awegpu_eval_batch_host (pinned host buffers)'},
             'gpu_launches': int(gpu_launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src, 'kernel': 'awegpu_eval_kernel',
-                         'kernel_ms': k_ms, 'algorithmic_bytes_per_launch': int(alg_bytes),
-                         'fp64_gflops_achieved': flops / (k_ms * 1e-3) / 1e9, 'algorithmic_flops_per_launch': int(flops)},
+                         'traffic': traffic, 'peak_source': peak_src,
+                         'kernel': 'awegpu_node_kernel<coll, full, stage 0> (output stage of the collocation-node programs)',
+                         'kernel_ms': k_ms, 'kernel_share_of_step': k_ms / s_ms,
+                         'algorithmic_bytes_per_launch': int(alg_bytes),
+                         'algorithmic_bytes_per_node': per_inst / (ocp.n_k * ocp.d),
+                         'step': {'ms': s_ms, 'algorithmic_bytes': int(step_bytes),
+                                  'achieved': step_bytes / (s_ms * 1e-3) / 1e9, 'frac': step_bytes / (s_ms * 1e-3) / 1e9 / peak},
+                         'fp64': {'algorithmic_flops_per_step': int(flops),
+                                  'executed_flops_per_step': int(B * (ocp.n_k * ocp.d * info['ops_coll_node']
+                                                                      + ocp.n_k * info['ops_shoot_node'])),
+                                  'gflops_algorithmic': flops / (s_ms * 1e-3) / 1e9,
+                                  'peak_note': 'B200 vector FP64 ~37 TFLOP/s nominal (148 SM x 64 FMA/clk x 1.965 GHz); '
+                                               'not the binding limit'},
+                         'programs': info},
             'cpu_baseline': {'value': cpu_v, 'unit': 'node-evals/s', 'cores': cpu_thr, 'kind': 'port',
                              'sample': '256-instance blocks of the same workload repeated for %.1f s (%d instances)'
                                        % (cpu_dt, cpu_n)},

@@ -100,6 +100,13 @@ int awegpu_eval_batch_host(awegpu_handle_t *h, int32_t B, const double *W, const
 
 /* device time of the most recent eval (ms, CUDA events on the launching stream); <0 if none */
 float awegpu_last_eval_ms(awegpu_handle_t *h);
+/* device time of the dominant kernel (collocation-node programs, output stage) of the first chunk of the
+ * most recent eval with Jacobian (ms, CUDA events on the launching stream); <0 if none */
+float awegpu_last_kernel_ms(awegpu_handle_t *h);
+/* structure of the compiled node programs: groups per stage {coll s0,s1,s2, shoot s0,s1,s2}, exported
+ * intermediates {coll, shoot}, FP64 operations executed per collocation / shooting node (all stages,
+ * recomputation included) */
+int awegpu_kernel_info(int32_t *n_groups /*[6]*/, int32_t *n_exports /*[2]*/, int64_t *ops_coll, int64_t *ops_shoot);
 /* number of kernel launches issued by this handle so far */
 int64_t awegpu_launch_count(awegpu_handle_t *h);
 int awegpu_synchronize(awegpu_handle_t *h);

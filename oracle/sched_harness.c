@@ -27,6 +27,7 @@
 #define LD_ITF(reg) reg = itf
 #define LD_TH(reg, t) reg = th[t]
 #define LD_OWN(reg, r) reg = (own_r == (r)) ? 1.0 : 0.0
+#define LEAF_FENCE()
 #define LD_EX(reg, i) reg = ex_[i]
 #define EXOUT(i, val) ex_[i] = (val)
 #define SPILL_ST(slot, reg) hot[slot] = reg
