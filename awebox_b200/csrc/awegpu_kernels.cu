@@ -78,6 +78,9 @@ struct DevProblem {
     const int *coop_dst;      // [n_k][AWE_K_COLL_NCHUNKS][N_D * AWE_CHUNK]  destination code (-1: none, at the end)
     const int *coop_src;      // same shape: staged value index  j * AWE_CHUNK + o
     const double *const_val;
+    int n_aff, row_aff;
+    const int *aff_begin, *aff_col;
+    const double *aff_coef, *aff_const;
     double cscale;
 };
 
@@ -385,6 +388,19 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
                     G[(size_t)(b0 + u) * pr.n_g + pr.row_periodic + n] = v;
             }
         }
+        // ---- affine rows: t_f bounds of single_reelout (awebox/ocp/constraints.py:147-168), thread = (instance, row)
+        for (int e = tid; e < n_valid * pr.n_aff; e += GATHER_THREADS) {
+            const int u = e / pr.n_aff, n = e - u * pr.n_aff;
+            const double *w = W + (size_t)(b0 + u) * pr.n_v;
+            double a = 0.0;
+            for (int i = __ldg(pr.aff_begin + n); i < __ldg(pr.aff_begin + n + 1); ++i)
+                a += __ldg(pr.aff_coef + i) * __ldg(w + __ldg(pr.aff_col + i));
+            const double v = pr.cscale * (a + __ldg(pr.aff_const + n));
+            if (BATCH_MINOR)
+                G[(size_t)(pr.row_aff + n) * B + b0 + u] = v;
+            else
+                G[(size_t)(b0 + u) * pr.n_g + pr.row_aff + n] = v;
+        }
     }
 }
 
@@ -675,6 +691,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     d.n_coll_out = p->n_coll_out, d.n_shoot_out = p->n_shoot_out, d.n_shoot_eq = p->n_shoot_eq, d.n_ineq = p->n_ineq;
     d.n_periodic = p->n_periodic, d.row_periodic = p->row_periodic, d.x_last = p->x_last, d.x_first = p->x_base[0];
     d.cscale = p->constraint_scale;
+    d.n_aff = p->n_aff, d.row_aff = p->row_aff;
     const int nk = p->n_k, dd = p->d;
     // destination codes of the node-local outputs: >= 0 slot of the CCS value array, -1 none,
     // <= -2 row (-2 - code) of g
@@ -723,6 +740,10 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     rc |= to_device(h, p->const_slot, (size_t)p->n_const, &d.const_slot);
     rc |= to_device(h, p->const_begin, (size_t)nk + 1, &d.const_begin);
     rc |= to_device(h, p->const_val, (size_t)p->n_const, &d.const_val);
+    rc |= to_device(h, p->aff_begin, (size_t)p->n_aff + 1, &d.aff_begin);
+    rc |= to_device(h, p->aff_col, (size_t)(p->n_aff ? p->aff_begin[p->n_aff] : 0), &d.aff_col);
+    rc |= to_device(h, p->aff_coef, (size_t)(p->n_aff ? p->aff_begin[p->n_aff] : 0), &d.aff_coef);
+    rc |= to_device(h, p->aff_const, (size_t)p->n_aff, &d.aff_const);
     if (rc) return rc;
     CK(cudaMemcpyToSymbol(c_coeff_coll, p->coeff_coll, sizeof(double) * (dd + 1) * (dd + 1)));
     CK(cudaMemcpyToSymbol(c_coeff_cont, p->coeff_cont, sizeof(double) * (dd + 1)));

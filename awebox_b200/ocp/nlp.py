@@ -280,9 +280,34 @@ class OcpProblem(object):
             row = self.row_periodic + n
             const_r.append(row), const_c.append(self.v_x[0] + mm), const_v.append(1.0)
             const_r.append(row), const_c.append(last + mm), const_v.append(-1.0)
+        # ---- affine rows  g[row_aff + n] = scale * (sum_i aff_coef[i] * w[aff_col[i]] + aff_const[n]):
+        #      the t_f bound rows of phase_fix='single_reelout' (constraints.py:147-168 with
+        #      ocp_outputs.py:118-141): period = t_f[0] * n_ro / n_k + t_f[1] * (n_k - n_ro) / n_k,
+        #      rows (period - ub) / s and (lb - period) / s,  s = phase_fix_reelout
+        aff_begin, aff_col, aff_coef, aff_const = [0], [], [], []
+        self.row_aff = self.row_tf_bounds if self.single_reelout else self.n_g
         if self.single_reelout:
-            raise NotImplementedError('t_f bound rows of single_reelout are assembled in tf_bounds()')
-        const_begin.append(len(const_r))       # periodicity entries belong to the last interval
+            s_ro = float(self.spec.nlp.get('phase_fix_reelout', 0.7))
+            n_ro = int(round(n_k * s_ro))
+            o_tf, sz_tf = self.v_theta['t_f']
+            assert sz_tf == 2
+            sc_tf = float(self.model.scale('theta', 't_f')[0])
+            lb, ub = [float(b) / sc_tf for b in self.spec.opt('system_bounds.theta.t_f')]
+            w0, w1 = float(n_ro) / n_k, float(n_k - n_ro) / n_k
+            for sign, bound in ((1.0, -ub), (-1.0, lb)):
+                aff_col += [o_tf, o_tf + 1]
+                aff_coef += [sign * w0 / s_ro, sign * w1 / s_ro]
+                aff_const.append(bound / s_ro)
+                aff_begin.append(len(aff_col))
+            for n in range(2):
+                for i in range(aff_begin[n], aff_begin[n + 1]):
+                    const_r.append(self.row_aff + n), const_c.append(aff_col[i]), const_v.append(aff_coef[i])
+        self.aff_begin = np.array(aff_begin, dtype=np.int32)
+        self.aff_col = np.array(aff_col, dtype=np.int32)
+        self.aff_coef = np.array(aff_coef, dtype=float)
+        self.aff_const = np.array(aff_const, dtype=float)
+        self.n_aff = len(aff_const)
+        const_begin.append(len(const_r))       # periodicity / affine-row entries belong to the last interval
         self.const_begin = np.array(const_begin, dtype=np.int32)
         for r_, c_ in zip(const_r, const_c):
             add(r_, c_)

@@ -41,7 +41,7 @@ typedef struct awegpu_problem {
     int32_t p_theta0;               /* offset of theta0 in P */
     int32_t n_coll_out, n_shoot_out;/* node-local output counts (must match the compiled model) */
     int32_t n_shoot_eq, n_ineq;
-    int32_t n_const;                /* constant Jacobian entries (continuity, periodicity) */
+    int32_t n_const;                /* constant Jacobian entries (continuity, periodicity, affine rows) */
     int32_t n_periodic;
     int32_t row_periodic;           /* first periodicity row */
     int32_t x_last;                 /* V offset of coll_var[n_k-1, d-1].x */
@@ -63,6 +63,13 @@ typedef struct awegpu_problem {
     const double  *coeff_cont;      /* [d+1]          l_r(1) */
     const int64_t *colind;          /* [n_v+1] */
     const int64_t *row;             /* [nnz] */
+    /* affine rows  g[row_aff+n] = scale * (sum_{i in [aff_begin[n], aff_begin[n+1])} aff_coef[i] * w[aff_col[i]]
+     * + aff_const[n]): the t_f bound rows of phase_fix='single_reelout' (awebox/ocp/constraints.py:147-168) */
+    int32_t n_aff, row_aff;
+    const int32_t *aff_begin;       /* [n_aff+1] */
+    const int32_t *aff_col;         /* [aff_begin[n_aff]] */
+    const double  *aff_coef;        /* [aff_begin[n_aff]] */
+    const double  *aff_const;       /* [n_aff] */
     double constraint_scale;
 } awegpu_problem_t;
 

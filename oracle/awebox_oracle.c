@@ -115,6 +115,12 @@ static void eval_one(const awegpu_problem_t *pr, const double *w, const double *
     for (n = 0; n < pr->n_periodic; ++n)
         g[pr->row_periodic + n] = pr->constraint_scale *
                                   (w[pr->x_base[0] + pr->periodic_idx[n]] - w[pr->x_last + pr->periodic_idx[n]]);
+    /* ---- affine rows (t_f bounds of single_reelout, awebox/ocp/constraints.py:147-168) */
+    for (n = 0; n < pr->n_aff; ++n) {
+        double a = 0.0;
+        for (r = pr->aff_begin[n]; r < pr->aff_begin[n + 1]; ++r) a += pr->aff_coef[r] * w[pr->aff_col[r]];
+        g[pr->row_aff + n] = pr->constraint_scale * (a + pr->aff_const[n]);
+    }
     if (jv)
         for (n = 0; n < pr->n_const; ++n) jv[pr->const_slot[n]] = pr->const_val[n];
 }
