@@ -39,7 +39,7 @@ LEAF_LOOKAHEAD = 40  # statements between an input load (global memory, L2 laten
 HOT_SLOTS = 1 << 20  # no cold tier: the grouped programs need only a few dozen scratch slots
 CHUNK = 16           # outputs staged per flush
 GROUP_OPS = 1400     # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
-MAX_EXPORTS = 64     # intermediate values computed once per node by the pre-stage and re-read by the groups
+MAX_EXPORTS = 512    # cap on the intermediate values exported per stage (the gain threshold normally stops earlier)
 EXPORT_MIN_GAIN = 40
 EXPORT_LOAD_COST = 4
 MAX_STAGES = 3       # main programs + two levels of export pre-stages
@@ -190,87 +190,106 @@ class NodeCode(object):
         * *exports* are intermediate values that are too expensive to recompute in every group (the
           wind / density power laws, norms, aerodynamic angles ...): they are computed once per node by
           a pre-stage program, stored lane-contiguously, and read back as inputs.  Chosen greedily by
-          (groups sharing the value - 1) x (weight of its cone) minus the cost of the extra loads.
+          (groups sharing the value - 1) x (weight of its cone) minus the cost of the extra loads; every
+          round takes the best candidates whose cones neither contain nor lie inside one another (their
+          gains are independent), so that large models are planned in a few dozen rounds.
+
+        Cones are rows of a packed bit matrix (numpy), weights are summed by matrix products.
 
         -> (export nodes in dependency order, [(first, last+1)] output groups)"""
         limit = GROUP_OPS if limit is None else limit
         max_exports = MAX_EXPORTS if max_exports is None else max_exports
         min_gain = EXPORT_MIN_GAIN if min_gain is None else min_gain
         order = [n for n in S.topo(exprs) if SCH.is_op(n)]
+        n_ops = len(order)
+        if n_ops == 0:
+            return [], [(0, len(exprs))]
         pos = {n.idx: i for i, n in enumerate(order)}
-        wgt = [OP_WEIGHT.get(n.op, 1) for n in order]
-        exported = set()
-        out_idx = set(e.idx for e in exprs)
+        wgt = np.array([OP_WEIGHT.get(n.op, 1) for n in order], dtype=np.float32)
+        nb = (n_ops + 7) // 8
+        child = [[pos[c.idx] for c in (n.a, n.b) if c is not None and SCH.is_op(c)] for n in order]
+        unit = np.zeros((n_ops, nb), dtype=np.uint8)
+        unit[np.arange(n_ops), np.arange(n_ops) // 8] = (128 >> (np.arange(n_ops) % 8)).astype(np.uint8)
+        exported = np.zeros(n_ops, dtype=bool)
+        is_out = np.zeros(n_ops, dtype=bool)
+        for e in exprs:
+            if SCH.is_op(e):
+                is_out[pos[e.idx]] = True
+        out_pos = [pos[e.idx] if SCH.is_op(e) else -1 for e in exprs]
 
-        def cones():
-            c = [0] * len(order)
-            for i, n in enumerate(order):
-                if n.idx in exported:
+        def cones(cut):
+            c = np.zeros((n_ops, nb), dtype=np.uint8)
+            for i in range(n_ops):
+                if cut is not None and cut[i]:
                     continue
-                v = 1 << i
-                for ch in (n.a, n.b):
-                    if ch is not None and SCH.is_op(ch) and ch.idx not in exported:
-                        v |= c[pos[ch.idx]]
-                c[i] = v
+                row = unit[i].copy()
+                for ch in child[i]:
+                    if cut is None or not cut[ch]:
+                        row |= c[ch]
+                c[i] = row
             return c
 
-        def wsum(bits):
-            t = 0
-            while bits:
-                low = bits & -bits
-                t += wgt[low.bit_length() - 1]
-                bits ^= low
-            return t
+        def wsum_rows(rows):
+            """weighted popcount of packed rows [m, nb] -> [m]"""
+            out = np.empty(rows.shape[0], dtype=np.float64)
+            for a0 in range(0, rows.shape[0], 1024):
+                bits = np.unpackbits(rows[a0:a0 + 1024], axis=1)[:, :n_ops]
+                out[a0:a0 + 1024] = bits.astype(np.float32) @ wgt
+            return out
+
+        def wsum(row):
+            return float(np.unpackbits(row)[:n_ops].astype(np.float32) @ wgt)
 
         def partition(c):
-            groups, cur, first = [], 0, 0
-            for i, e in enumerate(exprs):
-                ce = c[pos[e.idx]] if (SCH.is_op(e) and e.idx not in exported) else 0
+            groups, cur, first = [], np.zeros(nb, dtype=np.uint8), 0
+            for i, op in enumerate(out_pos):
+                ce = c[op] if (op >= 0 and not exported[op]) else np.zeros(nb, dtype=np.uint8)
                 u = cur | ce
-                if wsum(u) > limit and i > first:
+                if i > first and wsum(u) > limit:
                     groups.append((first, i, cur))
-                    cur, first = ce, i
+                    cur, first = ce.copy(), i
                 else:
                     cur = u
             groups.append((first, len(exprs), cur))
             return groups
 
-        # full cones (no export cut): what the pre-stage has to compute for an export
-        full = [0] * len(order)
-        for i, n in enumerate(order):
-            v = 1 << i
-            for ch in (n.a, n.b):
-                if ch is not None and SCH.is_op(ch):
-                    v |= full[pos[ch.idx]]
-            full[i] = v
-        pre_bits = 0
+        full = cones(None)         # cones without any export cut: what a pre-stage computes for an export
+        pre_bits = np.zeros(nb, dtype=np.uint8)
+        per_round = max(1, n_ops // 800)
         while True:
-            c = cones()
+            c = cones(exported)
             groups = partition(c)
-            if len(exported) >= max_exports:
+            n_exp = int(exported.sum())
+            if n_exp >= max_exports:
                 break
-            use = [0] * len(order)
+            use = np.zeros(n_ops, dtype=np.int64)
             for g in groups:
-                bits = g[2]
-                while bits:
-                    low = bits & -bits
-                    use[low.bit_length() - 1] += 1
-                    bits ^= low
-            best, best_gain = None, 0
-            for i, n in enumerate(order):
-                if use[i] < 2 or n.idx in exported or n.idx in out_idx:
-                    continue
-                saved = (use[i] - 1) * wsum(c[i])
-                if saved <= best_gain:
-                    continue
-                gain = saved - wsum(full[i] & ~pre_bits) - EXPORT_LOAD_COST * (use[i] + 1)
-                if gain > best_gain:
-                    best, best_gain = i, gain
-            if best is None or best_gain < min_gain:
+                use += np.unpackbits(g[2])[:n_ops]
+            cand = np.nonzero((use >= 2) & ~exported & ~is_out)[0]
+            if len(cand) == 0:
                 break
-            exported.add(order[best].idx)
-            pre_bits |= full[best]
-        exports = [n for n in order if n.idx in exported]
+            saved = (use[cand] - 1) * wsum_rows(c[cand])
+            cost = wsum_rows(full[cand] & ~pre_bits) + EXPORT_LOAD_COST * (use[cand] + 1)
+            gain = saved - cost
+            best = np.argsort(-gain, kind='stable')
+            taken_cone = np.zeros(nb, dtype=np.uint8)       # union of the cones taken this round
+            taken = []
+            for bi in best:
+                if gain[bi] < min_gain or gain[bi] <= 0 or len(taken) >= per_round or n_exp + len(taken) >= max_exports:
+                    break
+                i = int(cand[bi])
+                if (taken_cone[i // 8] >> (7 - i % 8)) & 1:
+                    continue                                   # inside a cone taken this round
+                if np.any(c[i] & taken_cone):
+                    continue                                   # contains (part of) one
+                taken.append(i)
+                taken_cone |= c[i]
+            if not taken:
+                break
+            for i in taken:
+                exported[i] = True
+                pre_bits |= full[i]
+        exports = [n for i, n in enumerate(order) if exported[i]]
         return exports, [(a, b) for a, b, _ in groups]
 
     def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=CHUNK, first=0,
