@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '--shared', '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-diag-suppress', '177']
+              '--shared', '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-diag-suppress', '177', '--split-compile', '0']
 
 
 def gen_dir(spec_name):

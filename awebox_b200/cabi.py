@@ -36,8 +36,9 @@ class ProblemStruct(C.Structure):
         ('const_val', P_F64), ('const_begin', P_I32),
         ('coeff_coll', P_F64), ('coeff_cont', P_F64),
         ('colind', P_I64), ('row', P_I64),
-        ('n_aff', C.c_int32), ('row_aff', C.c_int32),
-        ('aff_begin', P_I32), ('aff_col', P_I32), ('aff_coef', P_F64), ('aff_const', P_F64),
+        ('n_aff', C.c_int32),
+        ('aff_row', P_I32), ('aff_begin', P_I32), ('aff_col', P_I32), ('aff_coef', P_F64),
+        ('affp_begin', P_I32), ('affp_col', P_I32), ('affp_coef', P_F64), ('aff_const', P_F64),
         ('constraint_scale', C.c_double),
     ]
 
@@ -69,8 +70,9 @@ def make_problem(ocp):
         'const_begin': _i32(ocp.const_begin),
         'coeff_coll': _f64(ocp.coll.coeff_collocation), 'coeff_cont': _f64(ocp.coll.coeff_continuity),
         'colind': _i64(ocp.colind), 'row': _i64(ocp.row),
-        'aff_begin': _i32(ocp.aff_begin), 'aff_col': _i32(ocp.aff_col), 'aff_coef': _f64(ocp.aff_coef),
-        'aff_const': _f64(ocp.aff_const),
+        'aff_row': _i32(ocp.aff_row), 'aff_begin': _i32(ocp.aff_begin), 'aff_col': _i32(ocp.aff_col),
+        'aff_coef': _f64(ocp.aff_coef), 'affp_begin': _i32(ocp.affp_begin), 'affp_col': _i32(ocp.affp_col),
+        'affp_coef': _f64(ocp.affp_coef), 'aff_const': _f64(ocp.aff_const),
     }
     ps = ProblemStruct()
     ps.n_v, ps.n_p, ps.n_g, ps.nnz = ocp.n_v, ocp.n_p, ocp.n_g, ocp.nnz
@@ -83,7 +85,7 @@ def make_problem(ocp):
     ps.n_const, ps.n_periodic = len(ocp.const_slot), len(ocp.periodic_idx)
     ps.row_periodic, ps.x_last = ocp.row_periodic, ocp.v_cx[n_k - 1][d - 1]
     ps.constraint_scale = ocp.constraint_scale
-    ps.n_aff, ps.row_aff = ocp.n_aff, ocp.row_aff
+    ps.n_aff = ocp.n_aff
     for name, arr in arrays.items():
         ctype = dict(ProblemStruct._fields_)[name]
         setattr(ps, name, arr.ctypes.data_as(ctype))

@@ -13,6 +13,8 @@ The emitted body only uses macros (``VIN(i)``, ``PIN(i)``, ``CCIN(r)``, ``OWNIN(
 ``OUT(n, value)``, ``RSQRT``, ``SIGN``), so the same text is compiled into the CUDA kernels
 (``awebox_b200/csrc/awegpu_kernels.cu``) and into the plain-C checker (``oracle/awebox_oracle.c``).
 """
+import struct
+
 import numpy as np
 
 from . import sym as S
@@ -38,11 +40,14 @@ LOOKAHEAD = 8        # statements between a scratch reload and its first use
 LEAF_LOOKAHEAD = 40  # statements between an input load (global memory, L2 latency) and its first use
 HOT_SLOTS = 1 << 20  # no cold tier: the grouped programs need only a few dozen scratch slots
 CHUNK = 16           # outputs staged per flush
+POOL = 0             # per-thread scratch slots shared by spills and the asynchronous input prefetch (0: plain loads; measured slower on B200: the extra shared-memory traffic saturates the MIO queue, profiles/r01_ncu_prefetch_variant.txt)
+PF_AHEAD = 150       # operations between the asynchronous copy of an input and its first use
 GROUP_OPS = 1400     # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
-MAX_EXPORTS = 512    # cap on the intermediate values exported per stage (the gain threshold normally stops earlier)
+MAX_EXPORTS = 64     # intermediate values exported per stage (scaled up for large models, see NodeCode.plan)
 EXPORT_MIN_GAIN = 40
 EXPORT_LOAD_COST = 4
 MAX_STAGES = 3       # main programs + two levels of export pre-stages
+BATCH_MINOR_MAX_OPS = 30000   # largest model (executed FP64 operations per coll + shoot node) that also gets the batch-minor kernels
 
 
 # rough SASS instruction count per operation (program size budget / export heuristic)
@@ -130,6 +135,7 @@ class NodeCode(object):
             outs.append(sc(S._e(e)))
         self.shoot_exprs = outs
         self._kernel_exprs()
+        self._ktab = {}                 # literal constants of the scheduled programs: hex value -> index
         self._names = {}
         for i, v in enumerate(m.vars):
             self._names[v.idx] = 'VIN(%d)' % i
@@ -198,12 +204,15 @@ class NodeCode(object):
 
         -> (export nodes in dependency order, [(first, last+1)] output groups)"""
         limit = GROUP_OPS if limit is None else limit
-        max_exports = MAX_EXPORTS if max_exports is None else max_exports
         min_gain = EXPORT_MIN_GAIN if min_gain is None else min_gain
         order = [n for n in S.topo(exprs) if SCH.is_op(n)]
         n_ops = len(order)
         if n_ops == 0:
             return [], [(0, len(exprs))]
+        if max_exports is None:
+            # measured on B200 (AP2): 64 exports per stage beat both fewer (recomputation) and more (side-buffer
+            # traffic); a model several times larger needs proportionally more to keep the group count down
+            max_exports = max(MAX_EXPORTS, n_ops // 40) if n_ops > 8000 else MAX_EXPORTS
         pos = {n.idx: i for i, n in enumerate(order)}
         wgt = np.array([OP_WEIGHT.get(n.op, 1) for n in order], dtype=np.float32)
         nb = (n_ops + 7) // 8
@@ -255,7 +264,7 @@ class NodeCode(object):
 
         full = cones(None)         # cones without any export cut: what a pre-stage computes for an export
         pre_bits = np.zeros(nb, dtype=np.uint8)
-        per_round = max(1, n_ops // 800)
+        per_round = max(1, n_ops // 800) if n_ops > 8000 else 1
         while True:
             c = cones(exported)
             groups = partition(c)
@@ -302,7 +311,14 @@ class NodeCode(object):
             OVF_ST(slot, reg) OVF_LD(reg, slot)                           cold scratch tier
             OUT(n, value) FLUSH(chunk, count) SYNC_HINT()                 staged outputs
         Scratch slots are ranked by access count; the ``hot_slots`` busiest go to the hot tier."""
-        prog = SCH.allocate(exprs, n_regs, lookahead, leaf_lookahead=LEAF_LOOKAHEAD)
+        names_ = leaf_names or self.k_leaf
+        if POOL > 0:
+            # inputs travel global -> scratch slot asynchronously and reach a register as late as a spill reload
+            prog = SCH.allocate(exprs, n_regs, lookahead, leaf_lookahead=None)
+            prog = SCH.prefetch_leaves(prog, POOL, PF_AHEAD, lambda n: '(' in names_[n.idx] and
+                                       names_[n.idx].split('(')[0] not in ('CCIN', 'OWNIN'))
+        else:
+            prog = SCH.allocate(exprs, n_regs, lookahead, leaf_lookahead=LEAF_LOOKAHEAD)
         access = {}
         for it in prog.ins:
             if it[0] == 'ld':
@@ -315,12 +331,25 @@ class NodeCode(object):
             tier[s_] = ('SPILL', rank) if rank < hot_slots else ('OVF', rank - hot_slots)
         n_hot = min(len(ranked), hot_slots)
         n_cold = max(0, len(ranked) - hot_slots)
+        if POOL > 0:
+            # one pool: slot numbers are final (the prefetch pass has placed its copies between the spills)
+            tier = {s_: ('SPILL', s_) for s_ in access}
+            n_hot, n_cold = prog.stats.get('pool', 0), 0
         lines = ['double ' + ', '.join('r%d' % i for i in range(prog.n_regs)) + ';']
         if not export:
-            lines.append('FLUSH_PREP(%d, %d);' % (q0, first))
+            lines.append('GROUP_INIT(%d, %d, %d);' % (q0, (len(exprs) + chunk - 1) // chunk, first))
+
+        ktab = self._ktab
 
         def src(s_):
-            return _fmt(s_.val) if isinstance(s_, S.Expr) else 'r%d' % s_
+            if not isinstance(s_, S.Expr):
+                return 'r%d' % s_
+            v = float(s_.val)
+            if v != v or v in (float('inf'), float('-inf')) or \
+                    (struct.unpack('<Q', struct.pack('<d', v))[0] & 0xffffffff) == 0:
+                return _fmt(v)           # encodable as an immediate operand of an FP64 instruction
+            # everything else comes from the constant bank (one operand, no register, no move instructions)
+            return 'KC(%d)' % ktab.setdefault(v.hex(), len(ktab))
 
         n_stmt = 0
         n_out = len(exprs)
@@ -331,7 +360,12 @@ class NodeCode(object):
             if prev_leaf and k != 'leaf':
                 lines.append('LEAF_FENCE();')      # keeps the loads above from being sunk to their uses
             prev_leaf = k == 'leaf'
-            if k == 'leaf':
+            if k == 'pf':
+                kind, args = names_[it[2].idx][:-1].split('(')
+                lines.append('PF_%s(%d, %s);' % (kind.replace('IN', ''), it[1], args))
+            elif k == 'leafr':
+                lines.append('LDR(r%d, %d, %d);' % (it[1], it[3], it[4]))
+            elif k == 'leaf':
                 name = (leaf_names or self.k_leaf)[it[2].idx]
                 if '(' in name:
                     kind, args = name[:-1].split('(')
@@ -493,11 +527,18 @@ class NodeCode(object):
             for level in range(MAX_STAGES):
                 kdefs += '#define AWE_%s_S%d_GROUPS %d\n' % (up, level, len(sstats[level]))
             kdefs += '#define AWE_%s_NCHUNKS %d\n' % (up, len(chunks0[0]))
+            kdefs += '#define AWE_%s_MAXQ %d\n' % (up, max((b - a + CHUNK - 1) // CHUNK for a, b in stages[0][1]))
             kdefs += 'static const int awe_%s_chunk_first[] = {%s};\n' % (name, ', '.join(map(str, chunks0[0])))
             kdefs += 'static const int awe_%s_chunk_cnt[] = {%s};\n' % (name, ', '.join(map(str, chunks0[1])))
             stats[name]['n_chunks'] = len(chunks0[0])
+        kvals = [float.fromhex(h) for h, _ in sorted(self._ktab.items(), key=lambda kv: kv[1])] or [0.0]
+        kdefs += '#define AWE_N_KCONST %d\n#define AWE_KCONST_INIT {%s}\n' % (len(kvals), ', '.join(_fmt(v) for v in kvals))
+        # the batch-minor output layout doubles the output-stage kernels: compiled for small models only
+        total_ops = stats['k_coll']['ops_total'] + stats['k_shoot']['ops_total']
+        kdefs += '#define AWE_BATCH_MINOR %d\n' % (1 if total_ops <= BATCH_MINOR_MAX_OPS else 0)
         kdefs += '#define AWE_MAX_STAGES %d\n' % MAX_STAGES
         kdefs += '#define AWE_CHUNK %d\n' % CHUNK
+        kdefs += '#define AWE_POOL %d\n' % POOL
         files['model_defs.h'] = head + kdefs
         return files, stats
 

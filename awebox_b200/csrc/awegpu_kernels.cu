@@ -75,12 +75,12 @@ struct DevProblem {
     const int *coll_dest, *shoot_dest, *const_slot, *const_begin;
     // interval-cooperative flush of the collocation kernel: for interval k and output chunk q, the
     // N_D * AWE_CHUNK staged values of the interval's nodes sorted by destination
-    const int *coop_dst;      // [n_k][AWE_K_COLL_NCHUNKS][N_D * AWE_CHUNK]  destination code (-1: none, at the end)
-    const int *coop_src;      // same shape: staged value index  j * AWE_CHUNK + o
+    const int2 *coop_tab;     // [n_k][AWE_K_COLL_NCHUNKS][N_D * AWE_CHUNK]  {destination code (-1: none, at the end),
+                              //                                              staged value index  j * AWE_CHUNK + o}
     const double *const_val;
-    int n_aff, row_aff;
-    const int *aff_begin, *aff_col;
-    const double *aff_coef, *aff_const;
+    int n_aff;
+    const int *aff_row, *aff_begin, *aff_col, *affp_begin, *affp_col;
+    const double *aff_coef, *affp_coef, *aff_const;
     double cscale;
 };
 
@@ -93,6 +93,9 @@ struct Scratch {
     double *exs;      // [tiles][n_k][AWE_K_SHOOT_EXPORTS][32]
 };
 
+// literal constants of the generated programs: read as constant-bank operands of the FP64 instructions
+__constant__ double c_kconst[AWE_N_KCONST] = AWE_KCONST_INIT;
+#define KC(i) c_kconst[i]
 __constant__ double c_coeff_coll[(N_D + 1) * (N_D + 1)];
 __constant__ double c_coeff_cont[N_D + 1];
 
@@ -158,7 +161,7 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define LD_U(reg, c) LDG_(reg, w_rec + (OFF_U + (c)) * 32)
 #define LD_Z(reg, c) LDG_(reg, w_z + (c) * 32)
 #define LD_TH(reg, t) LDG_(reg, w_rec + (REC_TH + (t)) * 32)
-#define LD_P(reg, i) LDG_(reg, ((i) < AWE_N_THETA0 ? w_pt + (i) * p_es : w_rec + (REC_PHI + (i) - AWE_N_THETA0) * 32))
+#define LD_P(reg, i) LDG_(reg, ((i) < AWE_N_THETA0 ? w_pt + (i) * 32 : w_rec + (REC_PHI + (i) - AWE_N_THETA0) * 32))
 #define LD_EX(reg, i) LDG_(reg, w_ex + (i) * 32)
 #define EXOUT(i, val) w_ex[(i) * 32] = (val)
 #define LD_CC(reg, r) reg = c_coeff_coll[(r) * (N_D + 1) + j1] * itf_nk
@@ -168,39 +171,64 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define SPILL_LD(reg, slot) LDS_(reg, scr_addr + (slot) * (8 * NODE_THREADS))
 #define OVF_ST(slot, reg) SPILL_ST(slot, reg)
 #define OVF_LD(reg, slot) SPILL_LD(reg, slot)
+// asynchronous input prefetch (awebox_b200/schedule.py: prefetch_leaves): PF_* copies the lane's 8 bytes of
+// an input from global memory into one of the thread's scratch slots without passing through a register
+// (LDGSTS), one commit group per copy; LDR waits until at most n younger copies are pending (copies
+// complete in issue order) and reads the slot
+#define CPA_(slot, ptr)                                                                      \
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n\tcp.async.commit_group;" ::    \
+                 "r"(scr_addr + (slot) * (8 * NODE_THREADS)), "l"(ptr) : "memory")
+#define LDR(reg, slot, n)                                                        \
+    asm volatile("cp.async.wait_group %2;\n\tld.shared.f64 %0, [%1];"            \
+                 : "=d"(reg) : "r"(scr_addr + (slot) * (8 * NODE_THREADS)), "n"(n) : "memory")
+#define PF_XO(slot, m) CPA_(slot, w_own + (m) * 32)
+#define PF_XD(slot, m) CPA_(slot, w_xd + (m) * 32)
+#define PF_U(slot, c) CPA_(slot, w_rec + (OFF_U + (c)) * 32)
+#define PF_Z(slot, c) CPA_(slot, w_z + (c) * 32)
+#define PF_TH(slot, t) CPA_(slot, w_rec + (REC_TH + (t)) * 32)
+#define PF_P(slot, i) CPA_(slot, ((i) < AWE_N_THETA0 ? w_pt + (i) * 32 : w_rec + (REC_PHI + (i) - AWE_N_THETA0) * 32))
+#define PF_EX(slot, i) CPA_(slot, w_ex + (i) * 32)
 
 // staged output: OUT parks value number n of the current chunk for this lane's instance, FLUSH writes
 // chunk q (outputs first .. first+cnt-1 of the node) for the 32 instances of the tile and prefetches
 // the destination table of the next chunk
-#define COOP_E ((N_D * AWE_CHUNK + 31) / 32)
+#define COOP_PER (N_D * AWE_CHUNK)
+#define COOP_E ((COOP_PER + 31) / 32)
 #ifndef AWE_EXP_NO_FLUSH
 #define AWE_EXP_NO_FLUSH 0
 #endif
 #define OUT(n, val) stg[(n) * STG_STRIDE + lane] = (val)
-#define FLUSH_PREP(q, first)                                                                         \
+// start of a stage-0 program: q0 = first output chunk of the group, nq = number of chunks.  The
+// cooperative flush reads its destination tables from shared memory; they are fetched here with
+// asynchronous copies that are older than every input copy, hence complete before the first flush.
+#define GROUP_INIT(q0, nq, first)                                                                    \
+    const int q0_ = (q0);                                                                            \
+    (void)q0_;                                                                                       \
     do {                                                                                             \
         if (COOP) {                                                                                  \
-            _Pragma("unroll") for (int e_ = 0; e_ < COOP_E; ++e_)                                    \
-            {                                                                                        \
-                LDGI_(fl_code[e_], coop_dst + (q) * (N_D * AWE_CHUNK) + e_ * 32 + lane);             \
-                LDGI_(fl_src[e_], coop_src + (q) * (N_D * AWE_CHUNK) + e_ * 32 + lane);              \
-            }                                                                                        \
-            LEAF_FENCE();                                                                            \
-        } else if (!BATCH_MINOR)                                                                     \
-        {                                                                                            \
-            LDGI_(fl_code[0], dest + (first) + lane % AWE_CHUNK);                                    \
+            for (int e_ = tid; e_ < (nq) * COOP_PER; e_ += NODE_THREADS)                             \
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::                           \
+                             "r"(tab_addr + e_ * 8), "l"(coop_tab + (q0) * COOP_PER + e_) : "memory"); \
+            asm volatile("cp.async.commit_group;" ::: "memory");                                     \
+            if (AWE_POOL == 0) asm volatile("cp.async.wait_all;" ::: "memory");                      \
+        } else                                                                                       \
+            FLUSH_PREP(q0, first);                                                                   \
+    } while (0)
+#define FLUSH_PREP(q, first)                                                                         \
+    do {                                                                                             \
+        if (!COOP && !BATCH_MINOR) {                                                                 \
+            LDGI_(fl_code, dest + (first) + lane % AWE_CHUNK);                                       \
             LEAF_FENCE();                                                                            \
         }                                                                                            \
     } while (0)
 #define FLUSH(q, first, cnt, q_next, first_next)                                                     \
     do {                                                                                             \
         if (COOP) {                                                                                  \
-            if (!AWE_EXP_NO_FLUSH) flush_coop(smem + (size_t)HOT * NODE_THREADS, fl_code, fl_src, lane, wid, n_valid, g_tile, j_tile, n_g, nnz); \
-            if ((q_next) >= 0) FLUSH_PREP(q_next, first_next);                                       \
+            if (!AWE_EXP_NO_FLUSH) flush_coop(smem + (size_t)HOT * NODE_THREADS, tab_smem + ((q) - q0_) * COOP_PER, lane, wid, n_valid, g_tile, j_tile, n_g, nnz); \
         } else if (BATCH_MINOR)                                                                      \
             flush_chunk_bm(stg, dest + (first), cnt, lane, valid, G, Jv, (size_t)B, (size_t)b);      \
         else {                                                                                       \
-            flush_chunk(stg, fl_code[0], cnt, lane, n_valid, g_tile, j_tile, n_g, nnz);              \
+            flush_chunk(stg, fl_code, cnt, lane, n_valid, g_tile, j_tile, n_g, nnz);                 \
             if ((q_next) >= 0) FLUSH_PREP(q_next, first_next);                                       \
         }                                                                                            \
     } while (0)
@@ -209,27 +237,40 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 // the same 32 instances.  Their staged chunks together cover a (nearly) contiguous range of the CCS
 // value array; lane = position in that range (destination-sorted table), warp w writes instances
 // w, w + N_D, ...: every store instruction writes 32 neighbouring entries of one instance.
-__device__ __forceinline__ void flush_coop(const double *stg_cta, const int (&code)[COOP_E], const int (&src)[COOP_E],
-                                           const int lane, const int wid, const int n_valid, double *__restrict__ g_tile,
-                                           double *__restrict__ j_tile, const int n_g, const int nnz)
+__device__ __forceinline__ void flush_coop(const double *stg_cta, const int2 *tab, const int lane, const int wid,
+                                           const int n_valid, double *__restrict__ g_tile, double *__restrict__ j_tile,
+                                           const int n_g, const int nnz)
 {
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < COOP_E; ++e) {
         // one base pointer, 32-bit element offsets (a tile spans < 2^31 elements of g / jac values)
-        const bool is_j = code[e] >= 0;
+        const int2 t = tab[e * 32 + lane];
+        const int code = t.x;
+        const bool is_j = code >= 0;
         double *base = is_j ? j_tile : g_tile;
-        const int step = (is_j ? nnz : n_g) * N_D;
-        int off = (is_j ? code[e] : -2 - code[e]) + wid * (is_j ? nnz : n_g);
-        const double *s = stg_cta + src[e] * STG_STRIDE + wid;
-        if (code[e] != -1 && base != nullptr) {
+        const int ld = is_j ? nnz : n_g;
+        const int step = ld * N_D;
+        int off = (is_j ? code : -2 - code) + wid * ld;
+        const double *s = stg_cta + t.y * STG_STRIDE + wid;
+        if (code != -1 && base != nullptr) {
+            if (n_valid == TILE) {
+                // full tile: TILE / N_D instances per warp, reads batched ahead of the stores
+#pragma unroll
+                for (int h = 0; h < TILE / N_D; h += 4) {
+                    double v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = s[(h + i) * N_D];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) __stcs(base + (off + (h + i) * step), v[i]);
+                }
+            } else {
 #pragma unroll 1
-            for (int i = wid; i < n_valid; i += N_D) {
-#ifndef AWE_EXP_NO_STORE
-                __stcs(base + off, *s);
-#endif
-                off += step;
-                s += N_D;
+                for (int i = wid; i < n_valid; i += N_D) {
+                    __stcs(base + off, *s);
+                    off += step;
+                    s += N_D;
+                }
             }
         }
     }
@@ -331,8 +372,9 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
             }
         }
     }
-    // ---- theta0, lane-contiguous (one copy per tile)
-    if (k == 0 && ldp != 0) {
+    // ---- theta0, lane-contiguous (one copy per tile; a shared vector is replicated, so that the node
+    //      programs address every parameter with an immediate offset)
+    if (k == 0) {
         double *pt = sc.pt + (size_t)tile * pr.n_theta0 * 32;
         const double *pl = P + (size_t)bl * ldp + p_off;
         for (int e = tid; e < pr.n_theta0 * 32; e += GATHER_THREADS) pt[e] = __ldg(pl + (e >> 5));
@@ -388,18 +430,23 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
                     G[(size_t)(b0 + u) * pr.n_g + pr.row_periodic + n] = v;
             }
         }
-        // ---- affine rows: t_f bounds of single_reelout (awebox/ocp/constraints.py:147-168), thread = (instance, row)
+        // ---- affine rows: t_f bounds of single_reelout (awebox/ocp/constraints.py:147-168), initial conditions
+        //      of an mpc trial (awebox/ocp/operation.py:303-326); thread = (instance, row)
         for (int e = tid; e < n_valid * pr.n_aff; e += GATHER_THREADS) {
             const int u = e / pr.n_aff, n = e - u * pr.n_aff;
             const double *w = W + (size_t)(b0 + u) * pr.n_v;
+            const double *pf = P + (size_t)(b0 + u) * ldp;       // full parameter vector (checked by the host)
             double a = 0.0;
             for (int i = __ldg(pr.aff_begin + n); i < __ldg(pr.aff_begin + n + 1); ++i)
                 a += __ldg(pr.aff_coef + i) * __ldg(w + __ldg(pr.aff_col + i));
+            for (int i = __ldg(pr.affp_begin + n); i < __ldg(pr.affp_begin + n + 1); ++i)
+                a += __ldg(pr.affp_coef + i) * __ldg(pf + __ldg(pr.affp_col + i));
             const double v = pr.cscale * (a + __ldg(pr.aff_const + n));
+            const int row = __ldg(pr.aff_row + n);
             if (BATCH_MINOR)
-                G[(size_t)(pr.row_aff + n) * B + b0 + u] = v;
+                G[(size_t)row * B + b0 + u] = v;
             else
-                G[(size_t)(b0 + u) * pr.n_g + pr.row_aff + n] = v;
+                G[(size_t)(b0 + u) * pr.n_g + row] = v;
         }
     }
 }
@@ -460,10 +507,9 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
     const double *w_z = SHOOT ? w_rec + OFF_Z * 32 : w_own + N_X * 32;
     const double *w_xd = SHOOT ? w_rec + OFF_XDOT * 32
                                : sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
-    // theta0: one vector shared by all instances (read in place, same address in every lane), or the
-    // lane-contiguous copy the gather kernel made of the per-instance vectors
-    const double *w_pt = p_shared ? p_shared : sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
-    const int p_es = p_shared ? 1 : 32;
+    // theta0: the lane-contiguous copy the gather kernel made (per-instance vectors, or the shared one replicated)
+    const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
+    (void)p_shared;
     double *w_ex = (SHOOT ? sc.exs : sc.exc) + (size_t)item * (NEX > 0 ? NEX : 1) * 32 + lane;
     const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
     const double itf_nk = itf * (double)pr.n_k;
@@ -472,10 +518,11 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
                             : pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
     double *g_tile = G + (size_t)b0 * n_g;
     double *j_tile = Jv ? Jv + (size_t)b0 * (size_t)nnz : nullptr;
-    const int *coop_dst = pr.coop_dst + (size_t)k * AWE_K_COLL_NCHUNKS * (N_D * AWE_CHUNK);
-    const int *coop_src = pr.coop_src + (size_t)k * AWE_K_COLL_NCHUNKS * (N_D * AWE_CHUNK);
-    int fl_code[COOP_E], fl_src[COOP_E];
-    (void)dest, (void)g_tile, (void)j_tile, (void)coop_dst, (void)coop_src, (void)fl_code, (void)fl_src;
+    const int2 *coop_tab = pr.coop_tab + (size_t)k * AWE_K_COLL_NCHUNKS * COOP_PER;
+    const int2 *tab_smem = reinterpret_cast<const int2 *>(smem + (size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES);
+    const unsigned tab_addr = (unsigned)__cvta_generic_to_shared(tab_smem);
+    int fl_code = -1;
+    (void)dest, (void)g_tile, (void)j_tile, (void)coop_tab, (void)tab_smem, (void)tab_addr, (void)fl_code;
 #define RUN(FILE_)           \
     switch (group) {         \
         FILE_                \
@@ -543,7 +590,8 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
 template <bool SHOOT, bool FULL>
 static constexpr size_t node_smem_bytes()
 {
-    return sizeof(double) * ((size_t)HOT_OF(SHOOT, FULL) * NODE_THREADS + NODE_WARPS * STG_DOUBLES);
+    return sizeof(double) * ((size_t)HOT_OF(SHOOT, FULL) * NODE_THREADS + NODE_WARPS * STG_DOUBLES) +
+           ((!SHOOT && FULL) ? sizeof(int2) * AWE_K_COLL_MAXQ * COOP_PER : 0);
 }
 template <bool SHOOT, bool FULL, int STAGE>
 static constexpr int node_groups()
@@ -578,6 +626,7 @@ struct awegpu_handle {
     // node-input records of one chunk of instances (see awegpu_gather_kernel)
     Scratch sc{};
     int chunk_tiles = 0, scratch_tiles = 0;
+    int n_affp = 0;          // parameter terms of the affine rows (> 0: the full parameter vector is required)
     int interleave = 1;      // tiles per block of the group-interleaved stage-0 order (0: group-major)
     // casadi sparsity buffers
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
@@ -691,7 +740,8 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     d.n_coll_out = p->n_coll_out, d.n_shoot_out = p->n_shoot_out, d.n_shoot_eq = p->n_shoot_eq, d.n_ineq = p->n_ineq;
     d.n_periodic = p->n_periodic, d.row_periodic = p->row_periodic, d.x_last = p->x_last, d.x_first = p->x_base[0];
     d.cscale = p->constraint_scale;
-    d.n_aff = p->n_aff, d.row_aff = p->row_aff;
+    d.n_aff = p->n_aff;
+    h->n_affp = p->n_aff ? p->affp_begin[p->n_aff] : 0;
     const int nk = p->n_k, dd = p->d;
     // destination codes of the node-local outputs: >= 0 slot of the CCS value array, -1 none,
     // <= -2 row (-2 - code) of g
@@ -708,7 +758,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
                                                 : p->shoot_slot[(size_t)k * p->n_shoot_out + n];
     // interval-cooperative flush tables (collocation kernel, stage 0)
     const int per = N_D * AWE_CHUNK;
-    std::vector<int> coop_dst((size_t)nk * AWE_K_COLL_NCHUNKS * per, -1), coop_src((size_t)nk * AWE_K_COLL_NCHUNKS * per, 0);
+    std::vector<int2> coop_tab((size_t)nk * AWE_K_COLL_NCHUNKS * per, make_int2(-1, 0));
     for (int k = 0; k < nk; ++k)
         for (int q = 0; q < AWE_K_COLL_NCHUNKS; ++q) {
             std::vector<std::pair<long long, int>> ent;
@@ -723,13 +773,12 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
             std::sort(ent.begin(), ent.end());
             for (size_t e = 0; e < ent.size(); ++e) {
                 const long long key = ent[e].first;
-                coop_dst[((size_t)k * AWE_K_COLL_NCHUNKS + q) * per + e] = key >= (1ll << 40) ? (int)(key - (1ll << 40)) : -2 - (int)key;
-                coop_src[((size_t)k * AWE_K_COLL_NCHUNKS + q) * per + e] = ent[e].second;
+                coop_tab[((size_t)k * AWE_K_COLL_NCHUNKS + q) * per + e] =
+                    make_int2(key >= (1ll << 40) ? (int)(key - (1ll << 40)) : -2 - (int)key, ent[e].second);
             }
         }
     int rc = 0;
-    rc |= to_device(h, coop_dst.data(), coop_dst.size(), &d.coop_dst);
-    rc |= to_device(h, coop_src.data(), coop_src.size(), &d.coop_src);
+    rc |= to_device(h, coop_tab.data(), coop_tab.size(), &d.coop_tab);
     rc |= to_device(h, p->x_base, (size_t)nk * (dd + 1), &d.x_base);
     rc |= to_device(h, p->theta_idx, (size_t)nk * p->n_theta, &d.theta_idx);
     rc |= to_device(h, p->tf_idx, (size_t)nk, &d.tf_idx);
@@ -740,7 +789,11 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     rc |= to_device(h, p->const_slot, (size_t)p->n_const, &d.const_slot);
     rc |= to_device(h, p->const_begin, (size_t)nk + 1, &d.const_begin);
     rc |= to_device(h, p->const_val, (size_t)p->n_const, &d.const_val);
+    rc |= to_device(h, p->aff_row, (size_t)p->n_aff, &d.aff_row);
     rc |= to_device(h, p->aff_begin, (size_t)p->n_aff + 1, &d.aff_begin);
+    rc |= to_device(h, p->affp_begin, (size_t)p->n_aff + 1, &d.affp_begin);
+    rc |= to_device(h, p->affp_col, (size_t)(p->n_aff ? p->affp_begin[p->n_aff] : 0), &d.affp_col);
+    rc |= to_device(h, p->affp_coef, (size_t)(p->n_aff ? p->affp_begin[p->n_aff] : 0), &d.affp_coef);
     rc |= to_device(h, p->aff_col, (size_t)(p->n_aff ? p->aff_begin[p->n_aff] : 0), &d.aff_col);
     rc |= to_device(h, p->aff_coef, (size_t)(p->n_aff ? p->aff_begin[p->n_aff] : 0), &d.aff_coef);
     rc |= to_device(h, p->aff_const, (size_t)p->n_aff, &d.aff_const);
@@ -757,7 +810,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
 #define SET_SMEM(kern, bytes) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
 #define SET_NODE1(S_, F_, T_)                                                             \
     SET_SMEM((awegpu_node_kernel<S_, F_, T_, false>), (node_smem_bytes<S_, F_>()));       \
-    SET_SMEM((awegpu_node_kernel<S_, F_, T_, true>), (node_smem_bytes<S_, F_>()))
+    SET_SMEM((awegpu_node_kernel<S_, F_, T_, ((T_) == 0) && AWE_BATCH_MINOR>), (node_smem_bytes<S_, F_>()))
 #define SET_NODE(S_, F_) \
     SET_NODE1(S_, F_, 0);  \
     SET_NODE1(S_, F_, 1);  \
@@ -767,7 +820,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     SET_NODE(true, true);
     SET_NODE(true, false);
     SET_SMEM(awegpu_gather_kernel<false>, gather_smem_bytes());
-    SET_SMEM(awegpu_gather_kernel<true>, gather_smem_bytes());
+    SET_SMEM(awegpu_gather_kernel<AWE_BATCH_MINOR != 0>, gather_smem_bytes());
 #undef SET_NODE
 #undef SET_NODE1
 #undef SET_SMEM
@@ -850,6 +903,10 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
     long long ldp;
     int p_off;
     if (flags & AWEGPU_P_THETA0) {
+        if (h->n_affp > 0) {
+            set_err(h, "this problem has rows that read p.ref (mpc initial conditions): pass full parameter vectors, not AWEGPU_P_THETA0");
+            return 1;
+        }
         ldp = (flags & AWEGPU_P_SHARED) ? 0 : h->dp.n_theta0;
         p_off = 0;
     } else {
@@ -858,6 +915,10 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
     }
     double *jv = (flags & AWEGPU_SKIP_JAC) ? nullptr : Jv;
     const bool full = jv != nullptr, bm = (flags & AWEGPU_JAC_BATCH_MINOR) != 0;
+    if (bm && !AWE_BATCH_MINOR) {
+        set_err(h, "the batch-minor output layout is not compiled into the library of this (large) model");
+        return 1;
+    }
     const int tiles = (B + TILE - 1) / TILE;
     const DevProblem &dp = h->dp;
     {
@@ -869,7 +930,8 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
 #define LAUNCH_STAGE(S_, F, T_, M, n_, st_)                                                                       \
     do {                                                                                                          \
         if (node_groups<S_, F, T_>() > 0) {                                                                       \
-            awegpu_node_kernel<S_, F, T_, M><<<dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>()), \
+            /* the output layout only matters to the output stage: pre-stages have one instantiation */       \
+            awegpu_node_kernel<S_, F, T_, ((T_) == 0) && (M) && AWE_BATCH_MINOR><<<dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>()), \
                                                NODE_THREADS, node_smem_bytes<S_, F>(), st_>>>(dp, h->sc, B, b_base, n_, p_sh,          \
                                                                                              (T_) == 0 ? h->interleave * (((S_) ? dp.n_k : dp.n_k * N_D) + NODE_WARPS - 1) / NODE_WARPS : 0, G, jv); \
             h->launches += 1;                                                                                     \
@@ -893,7 +955,7 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
         const int ct = (tiles - t0 < h->chunk_tiles) ? (tiles - t0) : h->chunk_tiles;
         const int b_base = t0 * TILE;
         if (bm)
-            awegpu_gather_kernel<true><<<dim3(ct, dp.n_k), GATHER_THREADS, gather_smem_bytes(), st>>>(
+            awegpu_gather_kernel<AWE_BATCH_MINOR != 0><<<dim3(ct, dp.n_k), GATHER_THREADS, gather_smem_bytes(), st>>>(
                 dp, h->sc, B, b_base, W, P, ldp, p_off, G, jv);
         else
             awegpu_gather_kernel<false><<<dim3(ct, dp.n_k), GATHER_THREADS, gather_smem_bytes(), st>>>(

@@ -620,15 +620,56 @@ class NodeModel(object):
         self.aero[kite] = {'vec_u': vec_u, 'dcm': R, 'alpha': alpha, 'beta': beta}
         return f_earth, m_body
 
+    # ---- 3-DOF (point-mass) kite aerodynamics (three_dof_kite.py:47-64, 100-137, 171-218;
+    #      kite_dir/tools.py:142-177): lift along the roll-rotated normal of the (tether, apparent wind)
+    #      plane, drag along the apparent wind, CL and roll angle psi are the states coeff[0], coeff[1]
     def three_dof_aero(self, kite):
-        raise NotImplementedError('3-DOF kite aerodynamics: see awebox_b200/mdl/three_dof.py')
+        spec, arch, lab = self.spec, self.arch, self.arch.node_label(kite)
+        if spec.opt('aero.aero_coeff_ref_velocity', 'eff') != 'eff':
+            raise NotImplementedError("aero_coeff_ref_velocity must be 'eff' without induction")
+        q, dq = self.si('x', 'q' + lab), self.si('x', 'dq' + lab)
+        coeff = self.si('x', 'coeff' + lab)
+        vec_u = self.wind_velocity(q[2]) - dq
+        parent = arch.parent_map[kite]
+        vec_t = q - (S.zeros(3) if parent == 0 else self.si('x', 'q' + arch.node_label(parent)))
+        vec_v = S.cross(vec_t, vec_u)
+        vec_w = S.cross(vec_u, vec_v)
+        uhat = vec_u / self.smooth_norm(vec_u)
+        vhat = vec_v / self.smooth_norm(vec_v)
+        what = vec_w / self.smooth_norm(vec_w)
+        psi = coeff[1]
+        cpsi, spsi = S.cos(psi), S.sin(psi)
+        e1 = uhat
+        e2 = cpsi * vhat + spsi * what
+        e3 = cpsi * what - spsi * vhat
+        dcm = S.zeros(3, 3)
+        for i in range(3):
+            dcm[i, 0], dcm[i, 1], dcm[i, 2] = e1[i], e2[i], e3[i]
+        rho = self.density(q[2])
+        cl = coeff[0]
+        cd0 = S.ZERO
+        for label in ('CX', 'CA', 'CD'):
+            key = ('theta0', 'aero', label, '0')
+            if key in self._pidx:
+                cd0 = self.smooth_abs(self.params[self._pidx[key][0]], 0.)
+        cd = cd0 + S.power(cl, 2.) / (np.pi * self.par('geometry', 'ar'))
+        s_ref = self.par('geometry', 's_ref')
+        lift_mag = cl * 1. / 2. * rho * S.dot(vec_u, vec_u) * s_ref
+        drag_mag = cd * 1. / 2. * rho * self.norm(vec_u) * s_ref
+        f_earth = S.vec([lift_mag * e3[i] + drag_mag * vec_u[i] for i in range(3)])
+        self.aero[kite] = {'vec_u': vec_u, 'dcm': dcm}
+        return f_earth
 
     # ---- path inequalities (awebox/mdl/dynamics.py:457-484, 627-821, 1022-1117)
     def _build_inequalities(self):
         spec, arch = self.spec, self.arch
         nn = arch.number_of_nodes
-        includes_force = [int(n) for n in (spec.opt('model_bounds.tether.tether_constraint_includes.force') or [])]
-        includes_stress = [int(n) for n in (spec.opt('model_bounds.tether.tether_constraint_includes.stress') or [])]
+        def node_list(v):
+            # a one-element list comes out of the spec file as a bare number
+            return [int(n) for n in (v if isinstance(v, (list, tuple)) else ([] if v is None else [v]))]
+
+        includes_force = node_list(spec.opt('model_bounds.tether.tether_constraint_includes.force'))
+        includes_stress = node_list(spec.opt('model_bounds.tether.tether_constraint_includes.stress'))
         tightness = float(spec.opt('model_bounds.tether_stress.scaling', 1.0))
         for node in range(1, nn):
             lab = arch.node_label(node)

@@ -35,6 +35,14 @@ class OcpProblem(object):
         self.coll = Collocation(self.n_k, self.d, nlp.get('collocation.scheme', 'radau'))
         self.phase_fix = nlp.get('phase_fix', 'simple')
         self.single_reelout = (self.phase_fix == 'single_reelout')
+        # operation conditions (awebox/ocp/operation.py:52-84, tools/performance_operations.py:63-69)
+        self.traj_type = nlp.get('trajectory.type', 'power_cycle')
+        if self.traj_type not in ('power_cycle', 'mpc'):
+            raise NotImplementedError('trajectory type %r is not supported' % self.traj_type)
+        self.periodic = self.traj_type == 'power_cycle'
+        self.initial_conditions = self.traj_type == 'mpc'
+        if self.traj_type == 'mpc' and nlp.get('mpc.terminal_point_constr', False):
+            raise NotImplementedError('mpc terminal point constraint')
         self.constraint_scale = float(nlp.get('constraint_scale', 1.0))
         self.n_x, self.n_u, self.n_z, self.n_theta = m.n_x, m.n_u, m.n_z, m.n_theta
         self.n_var, self.n_phi, self.n_theta0 = m.n_var, len(spec.phi_names), m.n_theta0
@@ -134,6 +142,23 @@ class OcpProblem(object):
         n_k, d = self.n_k, self.d
         self.n_shoot_eq = len(self.shoot_eq_rows)
         r = 0
+        # initial conditions  x(0) - x_ref(0)  come first (constraints.py:60-65, operation.py:303-326).  The
+        # reference iterates over a Python *set* of state names there, so its row order inside this block
+        # depends on the interpreter's string hash seed; ``nlp['initial_order']`` states the order to
+        # reproduce (default: model order).
+        m = self.model
+        self.row_initial = 0
+        self.initial_idx = []
+        if self.initial_conditions:
+            order = self.spec.nlp.get('initial_order') or m.names('x')
+            if sorted(order) != sorted(m.names('x')):
+                raise ValueError('initial_order must be a permutation of the state names')
+            for nm in order:
+                if nm.rstrip('0123456789') == 'r':
+                    raise NotImplementedError('initial conditions on a rotation matrix state (6-DOF mpc)')
+                o, sz = m.offset[('x', nm)]
+                self.initial_idx += list(range(o, o + sz))
+            r += len(self.initial_idx)
         self.row_shoot, self.row_path, self.row_coll, self.row_cont = [], [], [], []
         for k in range(n_k):
             self.row_shoot.append(r)
@@ -147,9 +172,8 @@ class OcpProblem(object):
             self.row_cont.append(r)
             r += self.n_x
         # periodicity: every non-integral state, names sorted (operation.py:245-267)
-        m = self.model
         self.periodic_idx = []
-        for nm in m.sorted_names('x'):
+        for nm in (m.sorted_names('x') if self.periodic else []):
             if nm in ('e',):
                 continue
             o, sz = m.offset[('x', nm)]
@@ -280,12 +304,26 @@ class OcpProblem(object):
             row = self.row_periodic + n
             const_r.append(row), const_c.append(self.v_x[0] + mm), const_v.append(1.0)
             const_r.append(row), const_c.append(last + mm), const_v.append(-1.0)
-        # ---- affine rows  g[row_aff + n] = scale * (sum_i aff_coef[i] * w[aff_col[i]] + aff_const[n]):
-        #      the t_f bound rows of phase_fix='single_reelout' (constraints.py:147-168 with
-        #      ocp_outputs.py:118-141): period = t_f[0] * n_ro / n_k + t_f[1] * (n_k - n_ro) / n_k,
-        #      rows (period - ub) / s and (lb - period) / s,  s = phase_fix_reelout
-        aff_begin, aff_col, aff_coef, aff_const = [0], [], [], []
-        self.row_aff = self.row_tf_bounds if self.single_reelout else self.n_g
+        # ---- affine rows  g[aff_row[n]] = scale * (sum_i aff_coef[i] * w[aff_col[i]] + sum_i affp_coef[i] * p[affp_col[i]]
+        #                                         + aff_const[n])
+        aff_row, aff_begin, aff_col, aff_coef, aff_const = [], [0], [], [], []
+        affp_begin, affp_col, affp_coef = [0], [], []
+
+        def affine(row, w_terms, p_terms, const):
+            aff_row.append(row)
+            for c, a in w_terms:
+                aff_col.append(c), aff_coef.append(a)
+            for c, a in p_terms:
+                affp_col.append(c), affp_coef.append(a)
+            aff_begin.append(len(aff_col)), affp_begin.append(len(affp_col)), aff_const.append(const)
+
+        # initial conditions of an mpc trial: x_0 - p.ref[x_0]  (operation.py:303-326; P['p','ref'] is a V-shaped
+        # block at the start of P, discretization.py:157-179)
+        for n, mm in enumerate(self.initial_idx):
+            affine(self.row_initial + n, [(self.v_x[0] + mm, 1.0)], [(self.v_x[0] + mm, -1.0)], 0.0)
+        # t_f bound rows of phase_fix='single_reelout' (constraints.py:147-168 with ocp_outputs.py:118-141):
+        # period = t_f[0] * n_ro / n_k + t_f[1] * (n_k - n_ro) / n_k, rows (period - ub) / s and (lb - period) / s,
+        # s = phase_fix_reelout
         if self.single_reelout:
             s_ro = float(self.spec.nlp.get('phase_fix_reelout', 0.7))
             n_ro = int(round(n_k * s_ro))
@@ -294,19 +332,21 @@ class OcpProblem(object):
             sc_tf = float(self.model.scale('theta', 't_f')[0])
             lb, ub = [float(b) / sc_tf for b in self.spec.opt('system_bounds.theta.t_f')]
             w0, w1 = float(n_ro) / n_k, float(n_k - n_ro) / n_k
-            for sign, bound in ((1.0, -ub), (-1.0, lb)):
-                aff_col += [o_tf, o_tf + 1]
-                aff_coef += [sign * w0 / s_ro, sign * w1 / s_ro]
-                aff_const.append(bound / s_ro)
-                aff_begin.append(len(aff_col))
-            for n in range(2):
-                for i in range(aff_begin[n], aff_begin[n + 1]):
-                    const_r.append(self.row_aff + n), const_c.append(aff_col[i]), const_v.append(aff_coef[i])
+            for n, (sign, bound) in enumerate(((1.0, -ub), (-1.0, lb))):
+                affine(self.row_tf_bounds + n, [(o_tf, sign * w0 / s_ro), (o_tf + 1, sign * w1 / s_ro)], [], bound / s_ro)
+        for n in range(len(aff_row)):
+            for i in range(aff_begin[n], aff_begin[n + 1]):
+                const_r.append(aff_row[n]), const_c.append(aff_col[i]), const_v.append(aff_coef[i])
+        self.aff_row = np.array(aff_row, dtype=np.int32)
         self.aff_begin = np.array(aff_begin, dtype=np.int32)
         self.aff_col = np.array(aff_col, dtype=np.int32)
         self.aff_coef = np.array(aff_coef, dtype=float)
         self.aff_const = np.array(aff_const, dtype=float)
-        self.n_aff = len(aff_const)
+        self.affp_begin = np.array(affp_begin, dtype=np.int32)
+        self.affp_col = np.array(affp_col, dtype=np.int32)
+        self.affp_coef = np.array(affp_coef, dtype=float)
+        self.n_aff = len(aff_row)
+        self.needs_full_p = len(affp_col) > 0
         const_begin.append(len(const_r))       # periodicity / affine-row entries belong to the last interval
         self.const_begin = np.array(const_begin, dtype=np.int32)
         for r_, c_ in zip(const_r, const_c):

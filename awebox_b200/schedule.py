@@ -303,3 +303,77 @@ def interpret(prog, leaf_value, n_out):
             else: raise NotImplementedError(op)
             regs[it[1]] = r
     return out
+
+
+def prefetch_leaves(prog, pool, ahead, prefetchable, step=4):
+    """Software prefetch of the input loads through the per-thread scratch slots the spills leave free.
+
+    Every ('leaf', reg, node) whose node satisfies ``prefetchable`` becomes
+        ('pf', slot, node)                issued ~``ahead`` operations earlier (asynchronous copy of the
+                                          input into scratch slot ``slot``; copies complete in issue order)
+        ('leafr', reg, node, slot, n)     at the old place: wait until at most ``n`` younger copies are
+                                          pending, then read the slot into the register
+    so that the in-flight storage of an input is a scratch slot instead of a register and the look-ahead
+    can be several L2 latencies long.  Slots come from one pool of ``pool`` slots shared with the spill
+    slots of the allocator: a copy may use any slot that holds no spilled value and no other pending
+    input between its issue and its read."""
+    import numpy as np
+    ins = prog.ins
+    n_ins = len(ins)
+    pool = max(pool, prog.n_slots)
+    occ = np.zeros((pool, n_ins + 1), dtype=bool)
+    start = {}
+    for i, it in enumerate(ins):
+        if it[0] == 'st':
+            start[it[1]] = i
+            occ[it[1], i] = True
+        elif it[0] == 'ld':
+            occ[it[2], start[it[2]]:i + 1] = True
+    opcount, c = [], 0
+    for it in ins:
+        opcount.append(c)
+        if it[0] == 'op':
+            c += 1
+    first_at = {}
+    for i, oc in enumerate(opcount):
+        first_at.setdefault(oc, i)
+    leaves = [i for i, it in enumerate(ins) if it[0] == 'leaf' and prefetchable(it[2])]
+    place, info = {}, {}
+    last_p, exposed, dist = 0, 0, 0
+    for n, t in enumerate(leaves):
+        p = max(first_at.get(max(0, opcount[t] - ahead), 0), last_p)
+        slot = None
+        while True:
+            free = np.nonzero(~occ[:, p:t + 1].any(axis=1))[0]
+            if len(free):
+                slot = int(free[-1])         # high slot numbers first: the spill allocator fills from 0
+                break
+            if p >= t:
+                break
+            p = min(t, p + step)
+        if slot is None:
+            # no slot is free even at the use: keep the plain load
+            continue
+        if p >= t:
+            exposed += 1
+        occ[slot, p:t + 1] = True
+        place.setdefault(p, []).append(('pf', slot, ins[t][2]))
+        info[t] = (slot, len(info))
+        last_p = p
+        dist += opcount[t] - opcount[p]
+    out, issued = [], 0
+    for i, it in enumerate(ins):
+        for pf in place.get(i, []):
+            out.append(pf)
+            issued += 1
+        if i in info:
+            slot, n = info[i]
+            out.append(('leafr', it[1], it[2], slot, issued - (n + 1)))
+        else:
+            out.append(it)
+    prog.ins = out
+    prog.n_slots = pool
+    used = np.nonzero(occ.any(axis=1))[0]
+    prog.stats = dict(prog.stats, pool=int(used.max()) + 1 if len(used) else 0, pf=len(info), pf_exposed=exposed,
+                      pf_mean_ahead=(dist / max(1, len(info))))
+    return prog

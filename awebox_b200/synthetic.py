@@ -119,3 +119,18 @@ def batch(ocp, B, seed, w0=None, rel=1e-2):
     w0 = base_point(ocp) if w0 is None else w0
     rng = np.random.default_rng(seed)
     return w0[None, :] * (1.0 + rel * rng.uniform(-1.0, 1.0, (B, ocp.n_v)))
+
+
+def scenario_params(ocp, W, seed, rel=1e-2):
+    """per-instance parameter vectors of an MPC scenario batch (BASELINE.json configs[4]): the tracking
+    reference ``p.ref`` (a V-shaped block at the start of P, awebox/ocp/discretization.py:157-179) is the
+    instance's own primal point perturbed by +-rel, so that the initial-condition rows x_0 - p.ref[x_0] differ
+    per instance, and the reference wind speed is perturbed by +-rel."""
+    rng = np.random.default_rng(seed)
+    B = W.shape[0]
+    P = np.tile(ocp.default_p(), (B, 1))
+    P[:, :ocp.n_v] = W * (1.0 + rel * rng.uniform(-1.0, 1.0, W.shape))
+    if '[theta0,wind,u_ref,0]' in ocp.spec.theta0_labels:
+        iu = ocp.p_theta0 + ocp.spec.theta0_labels.index('[theta0,wind,u_ref,0]')
+        P[:, iu] *= 1.0 + rel * rng.uniform(-1.0, 1.0, B)
+    return P

@@ -39,34 +39,59 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """samples SM clock and throttle reasons of one GPU while the timed region runs (NVML, every few ms;
+    nvidia-smi as a fallback when the NVML binding is missing)."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: address the GPU torch uses by its PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id
+            dom = torch.cuda.get_device_properties(index).pci_domain_id
+            dev = torch.cuda.get_device_properties(index).pci_device_id
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(('%08x:%02x:%02x.0' % (dom, bus, dev)).encode())
+            self.nvml = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    n = self.nvml
+                    sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+                            n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+                    self.samples.append([sm, self.sm_max] + ['active' if (r & b) else 'not active' for b in bits])
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(',')]
                 if len(parts) >= 6:
                     self.samples.append(parts)
             except Exception:
-                pass
+                if self.nvml is not None:
+                    self.nvml = None        # fall back to nvidia-smi
             time.sleep(0.1)
 
     def summary(self):
         if not self.samples:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
         sm = sorted(float(s[0]) for s in self.samples)
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(str(s[2 + i]).lower().startswith('active') for s in self.samples)]
         return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]), 'reasons': reasons,
-                'samples': len(self.samples)}
+                'samples': len(self.samples), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 def cpu_leg(ocp, n_threads, budget_s, W, p):
@@ -127,7 +152,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH, help='instances per GPU')
@@ -263,7 +288,8 @@ def main():
             'config': {'workload': WORKLOAD, 'n_k': N_K, 'd': ocp.d, 'instances_per_gpu': B, 'n_v': ocp.n_v,
                        'n_g': ocp.n_g, 'nnz': int(ocp.nnz), 'jac_layout': 'instance-major CCS values',
                        'l2': 'inputs+outputs per step (3.2 GB) exceed the 126 MB L2; no flush needed',
-                       'kernels_per_step': 'gather + 3 collocation stages + 2 shooting stages',
+                       'kernels_per_step': 'gather + %d collocation stages + %d shooting stages' % (
+                           sum(1 for g in info['groups_coll'] if g), sum(1 for g in info['groups_shoot'] if g)),
                        'parallelism': 'batch sharded over %d GPU(s), no data-path collective' % world},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': 'node-evals/s',

@@ -63,12 +63,20 @@ typedef struct awegpu_problem {
     const double  *coeff_cont;      /* [d+1]          l_r(1) */
     const int64_t *colind;          /* [n_v+1] */
     const int64_t *row;             /* [nnz] */
-    /* affine rows  g[row_aff+n] = scale * (sum_{i in [aff_begin[n], aff_begin[n+1])} aff_coef[i] * w[aff_col[i]]
-     * + aff_const[n]): the t_f bound rows of phase_fix='single_reelout' (awebox/ocp/constraints.py:147-168) */
-    int32_t n_aff, row_aff;
+    /* affine rows  g[aff_row[n]] = scale * (sum_{i in [aff_begin[n], aff_begin[n+1])} aff_coef[i] * w[aff_col[i]]
+     *                                      + sum_{i in [affp_begin[n], affp_begin[n+1])} affp_coef[i] * p[affp_col[i]]
+     *                                      + aff_const[n]):
+     * the t_f bound rows of phase_fix='single_reelout' (awebox/ocp/constraints.py:147-168) and the initial
+     * conditions x_0 - p.ref[x_0] of an mpc trial (awebox/ocp/operation.py:303-326).  Rows with parameter terms
+     * need the full parameter vector (not AWEGPU_P_THETA0). */
+    int32_t n_aff;
+    const int32_t *aff_row;         /* [n_aff] */
     const int32_t *aff_begin;       /* [n_aff+1] */
-    const int32_t *aff_col;         /* [aff_begin[n_aff]] */
+    const int32_t *aff_col;         /* [aff_begin[n_aff]]  index into V */
     const double  *aff_coef;        /* [aff_begin[n_aff]] */
+    const int32_t *affp_begin;      /* [n_aff+1] */
+    const int32_t *affp_col;        /* [affp_begin[n_aff]] index into P */
+    const double  *affp_coef;       /* [affp_begin[n_aff]] */
     const double  *aff_const;       /* [n_aff] */
     double constraint_scale;
 } awegpu_problem_t;

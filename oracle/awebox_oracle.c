@@ -56,7 +56,8 @@ static void node_shoot(const double *v, const double *p, double *out)
 const char *awebox_oracle_model_name(void) { return AWE_MODEL_NAME; }
 
 /* one instance: w [n_v], theta0 [n_theta0] -> g [n_g], jv [nnz] (jv may be NULL) */
-static void eval_one(const awegpu_problem_t *pr, const double *w, const double *theta0, double *g, double *jv)
+static void eval_one(const awegpu_problem_t *pr, const double *w, const double *theta0, const double *pfull, double *g,
+                     double *jv)
 {
     const int d = pr->d, n_x = pr->n_x;
     double v[AWE_N_VAR], p[AWE_N_PARAM], out_c[AWE_N_COLL_OUT], out_s[AWE_N_SHOOT_OUT];
@@ -115,11 +116,13 @@ static void eval_one(const awegpu_problem_t *pr, const double *w, const double *
     for (n = 0; n < pr->n_periodic; ++n)
         g[pr->row_periodic + n] = pr->constraint_scale *
                                   (w[pr->x_base[0] + pr->periodic_idx[n]] - w[pr->x_last + pr->periodic_idx[n]]);
-    /* ---- affine rows (t_f bounds of single_reelout, awebox/ocp/constraints.py:147-168) */
+    /* ---- affine rows (t_f bounds of single_reelout, awebox/ocp/constraints.py:147-168; initial conditions of an
+     *      mpc trial, awebox/ocp/operation.py:303-326) */
     for (n = 0; n < pr->n_aff; ++n) {
         double a = 0.0;
         for (r = pr->aff_begin[n]; r < pr->aff_begin[n + 1]; ++r) a += pr->aff_coef[r] * w[pr->aff_col[r]];
-        g[pr->row_aff + n] = pr->constraint_scale * (a + pr->aff_const[n]);
+        for (r = pr->affp_begin[n]; r < pr->affp_begin[n + 1]; ++r) a += pr->affp_coef[r] * pfull[pr->affp_col[r]];
+        g[pr->aff_row[n]] = pr->constraint_scale * (a + pr->aff_const[n]);
     }
     if (jv)
         for (n = 0; n < pr->n_const; ++n) jv[pr->const_slot[n]] = pr->const_val[n];
@@ -134,16 +137,18 @@ int awebox_oracle_eval(const awegpu_problem_t *pr, int B, const double *W, const
     if (pr->n_coll_out != AWE_N_COLL_OUT || pr->n_shoot_out != AWE_N_SHOOT_OUT || pr->n_var != AWE_N_VAR ||
         pr->n_theta0 != AWE_N_THETA0 || pr->d != AWE_D)
         return 1;
+    if ((flags & AWEGPU_P_THETA0) && pr->n_aff > 0 && pr->affp_begin[pr->n_aff] > 0) return 2;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static) num_threads(n_threads > 0 ? n_threads : omp_get_max_threads())
 #endif
     for (b = 0; b < B; ++b) {
-        const double *p;
+        const double *p, *pfull = NULL;
         if (flags & AWEGPU_P_SHARED)
             p = (flags & AWEGPU_P_THETA0) ? P : P + pr->p_theta0;
         else
             p = (flags & AWEGPU_P_THETA0) ? P + (size_t)b * pr->n_theta0 : P + (size_t)b * pr->n_p + pr->p_theta0;
-        eval_one(pr, W + (size_t)b * pr->n_v, p, G + (size_t)b * pr->n_g,
+        if (!(flags & AWEGPU_P_THETA0)) pfull = (flags & AWEGPU_P_SHARED) ? P : P + (size_t)b * pr->n_p;
+        eval_one(pr, W + (size_t)b * pr->n_v, p, pfull, G + (size_t)b * pr->n_g,
                  (Jv && !(flags & AWEGPU_SKIP_JAC)) ? Jv + (size_t)b * pr->nnz : NULL);
     }
     return 0;

@@ -35,6 +35,7 @@ JOBS = {
     # config: [(n_k, number of points with Jacobian)]
     'ampyx_ap2': [(4, 3), (40, 2)],
     'dual_kites': [(3, 2), (20, 1)],
+    'mpc_3dof': [(3, 3), (10, 3)],
 }
 
 
@@ -53,17 +54,33 @@ def run(config, n_k, n_pts, write_spec):
     import casadi as cas            # the restatement under oracle/casadi_shim (activated by ref_build)
     theta0 = np.array(T.p_fix_num['theta0'].full()).ravel()
     sp = bspec.from_awebox(config, T.options, T.architecture, T.model, theta0_values=theta0)
+    n_v = T.nlp.V.cat.shape[0]
+    T.nlp.g_fun(cas.DM(T.w0), cas.DM(T.p0))            # the first numeric call records the instruction tape
+    tape = T.nlp.g_fun._tape
+    colind, row = tape.jac_ccs(n_v)
+    g_labels = T.nlp.g.labels()
+    n_init = sum(1 for l in g_labels if l.startswith('[initial,'))
+    if n_init:
+        # the reference builds the initial-condition rows by iterating over a set of state names
+        # (awebox/ocp/operation.py:312-315): record the order this run produced (run with PYTHONHASHSEED=0)
+        v_labels = T.nlp.V.labels()
+        order = []
+        for r_ in range(n_init):
+            cols = [c for c in range(n_v) if r_ in row[colind[c]:colind[c + 1]]]
+            names = [v_labels[c][1:-1].split(',') for c in cols if v_labels[c].startswith('[x,0,')]
+            assert len(names) == 1, (r_, names)
+            if not order or order[-1] != names[0][2]:
+                order.append(names[0][2])
+        sp.d['nlp']['initial_order'] = order
+        sp.nlp = sp.d['nlp']
     if write_spec:
         os.makedirs(bspec.SPEC_DIR, exist_ok=True)
         sp.to_json(os.path.join(bspec.SPEC_DIR, config + '.json'))
-    n_v = T.nlp.V.cat.shape[0]
     W = perturbed_points(T.w0, n_pts, 20261018 + n_k)
     p = T.p0
     G = []
     for w in W:
         G.append(np.array(T.nlp.g_fun(cas.DM(w), cas.DM(p)).full()).ravel())
-    tape = T.nlp.g_fun._tape
-    colind, row = tape.jac_ccs(n_v)
     JV = [tape.jac_values(np.concatenate([w, p]), colind, row) for w in W]
     # node-level vectors
     M = T.model

@@ -50,7 +50,39 @@ def config_dual_kites(n_k=20):
     return options
 
 
-CONFIGS = {'ampyx_ap2': config_ampyx_ap2, 'dual_kites': config_dual_kites}
+def config_mpc_3dof(n_k=10):
+    """examples/mpc_closed_loop.py:19-70 through awebox/pmpc.py:68-84 (BASELINE.json configs[4]): the tracking
+    MPC trial Pmpc builds from the periodic trial's option seed — single 3-DOF kite, trajectory type 'mpc',
+    horizon N = 10, Radau d = 4, zoh controls, theta fixed (t_f = N * ts, ts = 0.1 s).  Pmpc takes the other
+    theta entries from the solved periodic trial; here they are the reference's own initial-guess values
+    (diam_t 5e-3), since IPOPT is not available to solve the periodic trial."""
+    import awebox.opts.kite_data.ampyx_data as ampyx_data
+    options = {}
+    options['user_options.system_model.architecture'] = {1: 0}
+    options['user_options.kite_standard'] = ampyx_data.data_dict()
+    options['user_options.system_model.kite_dof'] = 3
+    options['user_options.trajectory.system_type'] = 'lift_mode'
+    options['user_options.trajectory.lift_mode.windings'] = 1
+    options['model.system_bounds.theta.t_f'] = [5.0, 15.0]
+    options['params.wind.z_ref'] = 10.0
+    options['user_options.wind.model'] = 'log_wind'
+    options['user_options.wind.u_ref'] = 5.
+    options['user_options.trajectory.lift_mode.phase_fix'] = 'simple'
+    options['solver.linear_solver'] = 'ma57'
+    options['solver.mu_hippo'] = 1e-2
+    # awebox/pmpc.py:68-84
+    options['user_options.trajectory.type'] = 'mpc'
+    options['nlp.discretization'] = 'direct_collocation'
+    options['nlp.n_k'] = n_k
+    options['nlp.collocation.d'] = 4
+    options['nlp.collocation.scheme'] = 'radau'
+    options['nlp.collocation.u_param'] = 'zoh'
+    options['formulation.mpc.terminal_point_constr'] = False
+    options['user_options.trajectory.fixed_params'] = {'diam_t': 5e-3, 't_f': n_k * 0.1}
+    return options
+
+
+CONFIGS = {'ampyx_ap2': config_ampyx_ap2, 'dual_kites': config_dual_kites, 'mpc_3dof': config_mpc_3dof}
 
 
 class RefTrial(object):

@@ -16,6 +16,8 @@
 #define SQRTF(x) sqrt(x)
 #define SIGN(x) (((x) > 0.0) - ((x) < 0.0))
 #define N_D AWE_D
+static const double awe_kconst[AWE_N_KCONST] = AWE_KCONST_INIT;
+#define KC(i) awe_kconst[i]
 #define N_X AWE_N_X
 
 #define LD_XO(reg, m) reg = xo[m]
@@ -29,6 +31,18 @@
 #define LD_OWN(reg, r) reg = (own_r == (r)) ? 1.0 : 0.0
 #define LEAF_FENCE()
 #define LD_EX(reg, i) reg = ex_[i]
+/* asynchronous input prefetch ring (awebox_b200/schedule.py: prefetch_leaves): copies complete in issue
+ * order and only when a wait forces them to, so that a wrong wait count reads a stale slot */
+#define PF_(slot, val) do { pf_slot[pf_n % 4096] = (slot); pf_val[pf_n % 4096] = (val); ++pf_n; } while (0)
+#define PF_XO(slot, m) PF_(slot, xo[m])
+#define PF_XD(slot, m) PF_(slot, xd[m])
+#define PF_U(slot, c) PF_(slot, u[c])
+#define PF_Z(slot, c) PF_(slot, z[c])
+#define PF_P(slot, i) PF_(slot, p[i])
+#define PF_TH(slot, t) PF_(slot, th[t])
+#define PF_EX(slot, i) PF_(slot, ex_[i])
+#define LDR(reg, slot, n) do { while (pf_done < pf_n - (n)) { ring[pf_slot[pf_done % 4096]] = pf_val[pf_done % 4096]; ++pf_done; } \
+                               reg = ring[slot]; } while (0)
 #define EXOUT(i, val) ex_[i] = (val)
 #define SPILL_ST(slot, reg) hot[slot] = reg
 #define SPILL_LD(reg, slot) reg = hot[slot]
@@ -37,6 +51,7 @@
 #define SYNC_HINT()
 #define OUT(n, val) stg_[n] = (val)
 #define FLUSH_PREP(q, first)
+#define GROUP_INIT(q0, nq, first)
 #define FLUSH(q, first, cnt, qn, fn) do { int q_; for (q_ = 0; q_ < (cnt); ++q_) out[(first) + q_] = stg_[q_]; } while (0)
 
 /* xo [n_x] state block of the node, xd [n_x] its time derivative, u, z, th, p [n_param], cc [d+1], itf,
@@ -50,7 +65,8 @@
 void sched_coll(const double *xo, const double *xd, const double *u, const double *z, const double *th,
                 const double *p, const double *cc, double itf, int own_r, double *out, int full)
 {
-    double hot[512], cold[512], stg_[64], ex_[1024];
+    double hot[512], cold[512], stg_[64], ex_[1024], ring[256], pf_val[4096];
+    int pf_slot[4096], pf_n = 0, pf_done = 0;
     int group;
     (void)cold;
     if (full) {
@@ -79,7 +95,8 @@ void sched_coll(const double *xo, const double *xd, const double *u, const doubl
 void sched_shoot(const double *xo, const double *xd, const double *u, const double *z, const double *th,
                  const double *p, double *out, int full)
 {
-    double hot[512], cold[512], stg_[64], ex_[1024];
+    double hot[512], cold[512], stg_[64], ex_[1024], ring[256], pf_val[4096];
+    int pf_slot[4096], pf_n = 0, pf_done = 0;
     const double *cc = 0;
     const double itf = 0.0;
     const int own_r = -1;

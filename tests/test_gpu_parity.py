@@ -34,7 +34,10 @@ def test_native_library_is_loaded():
         assert 'libawegpu_ampyx_ap2.so' in f.read()
 
 
-@pytest.mark.parametrize('name,n_k', [('ampyx_ap2', 4), ('ampyx_ap2', 40)])
+CASES = [('ampyx_ap2', 4), ('ampyx_ap2', 40), ('dual_kites', 3), ('dual_kites', 20), ('mpc_3dof', 3), ('mpc_3dof', 10)]
+
+
+@pytest.mark.parametrize('name,n_k', CASES)
 def test_sparsity_bit_exact(name, n_k):
     ev = evaluator(name, n_k)
     colind, row = ev.sparsity()
@@ -43,7 +46,7 @@ def test_sparsity_bit_exact(name, n_k):
     assert np.array_equal(colind, gold['colind']) and np.array_equal(row, gold['row'])
 
 
-@pytest.mark.parametrize('name,n_k', [('ampyx_ap2', 4), ('ampyx_ap2', 40)])
+@pytest.mark.parametrize('name,n_k', CASES)
 def test_against_reference_golden_vectors(name, n_k):
     ev = evaluator(name, n_k)
     gold = np.load(os.path.join(GOLDEN, '%s_nk%d.npz' % (name, n_k)))
@@ -51,7 +54,8 @@ def test_against_reference_golden_vectors(name, n_k):
     assert_parity(ev.ocp, G, Jv, gold['g'], gold['jv'])
 
 
-@pytest.mark.parametrize('name,n_k,B', [('ampyx_ap2', 4, 257), ('ampyx_ap2', 40, 96)])
+@pytest.mark.parametrize('name,n_k,B', [('ampyx_ap2', 4, 257), ('ampyx_ap2', 40, 96), ('dual_kites', 3, 97),
+                                        ('dual_kites', 20, 40), ('mpc_3dof', 10, 130)])
 def test_against_checker_on_seeded_batch(name, n_k, B):
     ev = evaluator(name, n_k)
     ocp = ev.ocp
@@ -71,6 +75,47 @@ def test_ragged_tiles(B):
     G, Jv = ev.eval(W, p)
     assert G.shape == (B, ev.n_g) and Jv.shape == (B, ev.nnz)
     assert_parity(ev.ocp, G, Jv, G0, J0)
+
+
+def test_dual_kite_power_curve_batch():
+    """BASELINE configs[3]: one OCP, per-instance wind speed (theta0 differs per instance), ragged batch."""
+    ev = evaluator('dual_kites', 3)
+    ocp = ev.ocp
+    B = 64 + 5
+    W = synthetic.batch(ocp, B, seed=3)
+    P = np.tile(ocp.default_p(), (B, 1))
+    iu = ocp.p_theta0 + ocp.spec.theta0_labels.index('[theta0,wind,u_ref,0]')
+    P[:, iu] = np.resize(np.linspace(5.0, 8.0, 64), B)
+    G0, J0 = get_oracle('dual_kites', 3).eval(W, P, flags=cabi.AWEGPU_P_FULL)
+    G, Jv = ev.eval(W, P)
+    assert_parity(ocp, G, Jv, G0, J0)
+    # the t_f bound rows (single_reelout) are the last two rows of g and depend on the two t_f entries only
+    o_tf = ocp.v_theta['t_f'][0]
+    assert list(ocp.aff_row) == [ocp.n_g - 2, ocp.n_g - 1]
+    n_ro = round(ocp.n_k * 0.7)
+    period = (W[:, o_tf] * n_ro + W[:, o_tf + 1] * (ocp.n_k - n_ro)) / ocp.n_k
+    lb, ub = ocp.spec.opt('system_bounds.theta.t_f')
+    assert np.allclose(G[:, -2], (period - ub) / 0.7, rtol=1e-13) and np.allclose(G[:, -1], (lb - period) / 0.7, rtol=1e-13)
+
+
+def test_mpc_scenario_batch():
+    """BASELINE configs[4]: tracking-MPC NLP (3-DOF kite, N = 10), a batch of scenarios that differ in the primal
+    point, the tracked reference / initial state (p.ref) and the wind speed: per-instance full parameter vectors."""
+    from awebox_b200.evaluator import AwegpuError
+    ev = evaluator('mpc_3dof', 10)
+    ocp = ev.ocp
+    B = 257
+    W = synthetic.batch(ocp, B, seed=9)
+    P = synthetic.scenario_params(ocp, W, seed=10)
+    G0, J0 = get_oracle('mpc_3dof', 10).eval(W, P, flags=cabi.AWEGPU_P_FULL)
+    G, Jv = ev.eval(W, P)
+    assert_parity(ocp, G, Jv, G0, J0)
+    idx = np.array(ocp.initial_idx)
+    assert np.array_equal(G[:, :len(idx)], W[:, ocp.v_x[0] + idx] - P[:, ocp.v_x[0] + idx])
+    G2, J2 = ev.eval(W, P, batch_minor=True)
+    assert_parity(ocp, np.ascontiguousarray(G2.T), np.ascontiguousarray(J2.T), G0, J0)
+    with pytest.raises(AwegpuError):
+        ev.eval(W, P[:, ocp.p_theta0:])          # the initial rows need p.ref: theta0-only blocks are refused
 
 
 def test_empty_batch_is_a_no_op():

@@ -8,7 +8,7 @@ import pytest
 from conftest import GOLDEN, get_ocp, get_oracle, jac_tolerance
 from awebox_b200 import cabi
 
-CASES = [('ampyx_ap2', 4), ('ampyx_ap2', 40), ('dual_kites', 3), ('dual_kites', 20)]
+CASES = [('ampyx_ap2', 4), ('ampyx_ap2', 40), ('dual_kites', 3), ('dual_kites', 20), ('mpc_3dof', 3), ('mpc_3dof', 10)]
 
 
 def load(name, n_k):
@@ -82,3 +82,20 @@ def test_oracle_parameter_modes():
     G2, J2 = orc.eval(W, Pfull[:, ocp.p_theta0:], flags=cabi.AWEGPU_P_THETA0)
     assert np.array_equal(G0, G1) and np.array_equal(J0, J1)
     assert np.array_equal(G0, G2) and np.array_equal(J0, J2)
+
+
+def test_mpc_initial_rows_read_the_reference_block_of_p():
+    """trajectory type 'mpc': g starts with x_0 - p.ref[x_0] (awebox/ocp/operation.py:303-326) in the order the
+    reference run produced; no periodicity rows; theta0-only parameter blocks are refused."""
+    from awebox_b200 import synthetic
+    ocp = get_ocp('mpc_3dof', 3)
+    assert ocp.initial_conditions and not ocp.periodic and len(ocp.periodic_idx) == 0
+    assert ocp.spec.nlp['initial_order'] == ['dq10', 'l_t', 'dl_t', 'q10', 'ddl_t', 'coeff10']
+    W = synthetic.batch(ocp, 5, seed=2)
+    P = synthetic.scenario_params(ocp, W, seed=3)
+    G, _ = get_oracle('mpc_3dof', 3).eval(W, P, flags=cabi.AWEGPU_P_FULL)
+    idx = np.array(ocp.initial_idx)
+    want = W[:, ocp.v_x[0] + idx] - P[:, ocp.v_x[0] + idx]
+    assert np.array_equal(G[:, :len(idx)], want)
+    with pytest.raises(RuntimeError):
+        get_oracle('mpc_3dof', 3).eval(W, P[:, ocp.p_theta0:], flags=cabi.AWEGPU_P_THETA0)
