@@ -66,8 +66,10 @@ def test_oracle_values_against_reference(name, n_k):
     G, Jv = get_oracle(name, n_k).eval(gold['w'], gold['p'], flags=cabi.AWEGPU_P_SHARED)
     assert np.all(np.abs(G - gold['g']) <= 1e-12 * np.maximum(1.0, np.abs(gold['g'])))
     assert np.all(np.abs(Jv - gold['jv']) <= jac_tolerance(ocp, gold['jv']))
-    # and the strictly relative statement holds for every entry that is not cancellation noise
-    big = np.abs(gold['jv']) > 1e-6
+    # and the strictly relative statement holds for every entry that is not cancellation noise (an entry three
+    # orders of magnitude below the largest entry of its row is the difference of terms of that size)
+    rowmax = jac_tolerance(ocp, gold['jv'], rtol=1.0) / 1.0
+    big = (np.abs(gold['jv']) > 1e-6) & (np.abs(gold['jv']) >= 1e-3 * rowmax)
     assert np.max(np.abs(Jv - gold['jv'])[big] / np.abs(gold['jv'])[big]) < 1e-10
 
 
