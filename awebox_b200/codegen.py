@@ -42,6 +42,7 @@ HOT_SLOTS = 1 << 20  # no cold tier: the grouped programs need only a few dozen 
 CHUNK = 16           # outputs staged per flush
 POOL = 0             # per-thread scratch slots shared by spills and the asynchronous input prefetch (0: plain loads; measured slower on B200: the extra shared-memory traffic saturates the MIO queue, profiles/r01_ncu_prefetch_variant.txt)
 PF_AHEAD = 150       # operations between the asynchronous copy of an input and its first use
+HINT_AHEAD = 0       # > 0: L2 prefetch hint this many operations before the load of a record / export input
 GROUP_OPS = 1400     # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
 MAX_EXPORTS = 64     # intermediate values exported per stage (scaled up for large models, see NodeCode.plan)
 EXPORT_MIN_GAIN = 40
@@ -319,6 +320,9 @@ class NodeCode(object):
                                        names_[n.idx].split('(')[0] not in ('CCIN', 'OWNIN'))
         else:
             prog = SCH.allocate(exprs, n_regs, lookahead, leaf_lookahead=LEAF_LOOKAHEAD)
+            if HINT_AHEAD > 0:
+                prog = SCH.prefetch_hints(prog, HINT_AHEAD, lambda n: names_[n.idx].split('(')[0] in
+                                          ('XO', 'XD', 'UIN', 'ZIN', 'EXIN'))
         access = {}
         for it in prog.ins:
             if it[0] == 'ld':
@@ -360,7 +364,10 @@ class NodeCode(object):
             if prev_leaf and k != 'leaf':
                 lines.append('LEAF_FENCE();')      # keeps the loads above from being sunk to their uses
             prev_leaf = k == 'leaf'
-            if k == 'pf':
+            if k == 'pfh':
+                kind, args = names_[it[1].idx][:-1].split('(')
+                lines.append('PFH_%s(%s);' % (kind.replace('IN', ''), args))
+            elif k == 'pf':
                 kind, args = names_[it[2].idx][:-1].split('(')
                 lines.append('PF_%s(%d, %s);' % (kind.replace('IN', ''), it[1], args))
             elif k == 'leafr':

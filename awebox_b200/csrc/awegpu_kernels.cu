@@ -78,6 +78,9 @@ struct DevProblem {
     const int2 *coop_tab;     // [n_k][AWE_K_COLL_NCHUNKS][N_D * AWE_CHUNK]  {destination code (-1: none, at the end),
                               //                                              staged value index  j * AWE_CHUNK + o}
     const double *const_val;
+    // the same for calls whose collocation kernel flushes cooperatively: only the entries the flush tables do not carry
+    const int *rest_slot, *rest_begin;
+    const double *rest_val;
     int n_aff;
     const int *aff_row, *aff_begin, *aff_col, *affp_begin, *affp_col;
     const double *aff_coef, *affp_coef, *aff_const;
@@ -96,6 +99,8 @@ struct Scratch {
 // literal constants of the generated programs: read as constant-bank operands of the FP64 instructions
 __constant__ double c_kconst[AWE_N_KCONST] = AWE_KCONST_INIT;
 #define KC(i) c_kconst[i]
+#define COOP_NCONST 8
+__constant__ double c_coop_const[COOP_NCONST];      // distinct values of the constant entries flushed cooperatively
 __constant__ double c_coeff_coll[(N_D + 1) * (N_D + 1)];
 __constant__ double c_coeff_cont[N_D + 1];
 
@@ -141,7 +146,10 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 // ---- statement macros of the generated code -------------------------------------------------------
 // asm volatile: the compiler must neither merge the generator's reloads into one long-lived register
 // nor hoist them.  Record entries of the 32 lanes are 256 bytes apart: base register + immediate.
-#ifdef AWE_VOLATILE_LD
+#if defined(AWE_EXP_NO_LOADS)
+/* ablation: inputs are not loaded (results are wrong): what the programs cost without memory latency */
+#define LDG_(reg, ptr) asm volatile("mov.f64 %0, 0d3FF199999999999A;" : "=d"(reg))
+#elif defined(AWE_VOLATILE_LD)
 #define LDG_(reg, ptr) asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(reg) : "l"(ptr))
 #else
 #define LDG_(reg, ptr) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(reg) : "l"(ptr))
@@ -162,8 +170,15 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define LD_Z(reg, c) LDG_(reg, w_z + (c) * 32)
 #define LD_TH(reg, t) LDG_(reg, w_rec + (REC_TH + (t)) * 32)
 #define LD_P(reg, i) LDG_(reg, ((i) < AWE_N_THETA0 ? w_pt + (i) * 32 : w_rec + (REC_PHI + (i) - AWE_N_THETA0) * 32))
-#define LD_EX(reg, i) LDG_(reg, w_ex + (i) * 32)
-#define EXOUT(i, val) w_ex[(i) * 32] = (val)
+// exports are read-only data for the per-stage kernels, but produced by the same thread inside the fused kernel
+#define LD_EX(reg, i)                                                                         \
+    do {                                                                                      \
+        if (EX_RW)                                                                            \
+            asm volatile("ld.global.f64 %0, [%1];" : "=d"(reg) : "l"(w_ex + (i) * 32) : "memory"); \
+        else                                                                                  \
+            LDG_(reg, w_ex + (i) * 32);                                                       \
+    } while (0)
+#define EXOUT(i, val) asm volatile("st.global.f64 [%0], %1;" ::"l"(w_ex + (i) * 32), "d"(val) : "memory")
 #define LD_CC(reg, r) reg = c_coeff_coll[(r) * (N_D + 1) + j1] * itf_nk
 #define LD_ITF(reg) reg = itf
 #define LD_OWN(reg, r) reg = (j1 == (r)) ? 1.0 : 0.0
@@ -181,6 +196,13 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define LDR(reg, slot, n)                                                        \
     asm volatile("cp.async.wait_group %2;\n\tld.shared.f64 %0, [%1];"            \
                  : "=d"(reg) : "r"(scr_addr + (slot) * (8 * NODE_THREADS)), "n"(n) : "memory")
+// L2 prefetch hints (awebox_b200/schedule.py: prefetch_hints)
+#define PFH_(ptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr))
+#define PFH_XO(m) PFH_(w_own + (m) * 32)
+#define PFH_XD(m) PFH_(w_xd + (m) * 32)
+#define PFH_U(c) PFH_(w_rec + (OFF_U + (c)) * 32)
+#define PFH_Z(c) PFH_(w_z + (c) * 32)
+#define PFH_EX(i) PFH_(w_ex + (i) * 32)
 #define PF_XO(slot, m) CPA_(slot, w_own + (m) * 32)
 #define PF_XD(slot, m) CPA_(slot, w_xd + (m) * 32)
 #define PF_U(slot, c) CPA_(slot, w_rec + (OFF_U + (c)) * 32)
@@ -192,7 +214,11 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 // staged output: OUT parks value number n of the current chunk for this lane's instance, FLUSH writes
 // chunk q (outputs first .. first+cnt-1 of the node) for the 32 instances of the tile and prefetches
 // the destination table of the next chunk
-#define COOP_PER (N_D * AWE_CHUNK)
+// table entries per chunk: the N_D * AWE_CHUNK staged values + room for constant Jacobian entries (continuity
+// rows) that lie between them in the CCS value array; COOP_NCONST rows of replicated constants follow the
+// staging rows of the quad
+#define COOP_STAGED (N_D * AWE_CHUNK)
+#define COOP_PER (COOP_STAGED + 32)
 #define COOP_E ((COOP_PER + 31) / 32)
 #ifndef AWE_EXP_NO_FLUSH
 #define AWE_EXP_NO_FLUSH 0
@@ -210,7 +236,8 @@ __device__ __forceinline__ double sqrt_nr(const double x)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::                           \
                              "r"(tab_addr + e_ * 8), "l"(coop_tab + (q0) * COOP_PER + e_) : "memory"); \
             asm volatile("cp.async.commit_group;" ::: "memory");                                     \
-            if (AWE_POOL == 0) asm volatile("cp.async.wait_all;" ::: "memory");                      \
+            for (int e_ = tid; e_ < COOP_NCONST * STG_STRIDE; e_ += NODE_THREADS)                    \
+                smem[(size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES + e_] = c_coop_const[e_ / STG_STRIDE]; \
         } else                                                                                       \
             FLUSH_PREP(q0, first);                                                                   \
     } while (0)
@@ -224,7 +251,7 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define FLUSH(q, first, cnt, q_next, first_next)                                                     \
     do {                                                                                             \
         if (COOP) {                                                                                  \
-            if (!AWE_EXP_NO_FLUSH) flush_coop(smem + (size_t)HOT * NODE_THREADS, tab_smem + ((q) - q0_) * COOP_PER, lane, wid, n_valid, g_tile, j_tile, n_g, nnz); \
+            if (!AWE_EXP_NO_FLUSH) flush_coop(smem + (size_t)HOT * NODE_THREADS, tab_smem + ((q) - q0_) * COOP_PER, lane, wid, n_valid, g_tile, j_tile, n_g, nnz, bar_id); \
         } else if (BATCH_MINOR)                                                                      \
             flush_chunk_bm(stg, dest + (first), cnt, lane, valid, G, Jv, (size_t)B, (size_t)b);      \
         else {                                                                                       \
@@ -237,11 +264,21 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 // the same 32 instances.  Their staged chunks together cover a (nearly) contiguous range of the CCS
 // value array; lane = position in that range (destination-sorted table), warp w writes instances
 // w, w + N_D, ...: every store instruction writes 32 neighbouring entries of one instance.
+// barrier of the NODE_THREADS threads that own one interval (the whole CTA of the per-stage kernels, one quad
+// of the fused kernel)
+__device__ __forceinline__ void quad_sync(const int bar_id)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NODE_THREADS) : "memory");
+}
+
 __device__ __forceinline__ void flush_coop(const double *stg_cta, const int2 *tab, const int lane, const int wid,
                                            const int n_valid, double *__restrict__ g_tile, double *__restrict__ j_tile,
-                                           const int n_g, const int nnz)
+                                           const int n_g, const int nnz, const int bar_id)
 {
-    __syncthreads();
+    // the destination table of the program was requested at its start (GROUP_INIT): own copies complete, then
+    // the barrier makes everybody's visible
+    if (AWE_POOL == 0) asm volatile("cp.async.wait_all;" ::: "memory");
+    quad_sync(bar_id);
 #pragma unroll
     for (int e = 0; e < COOP_E; ++e) {
         // one base pointer, 32-bit element offsets (a tile spans < 2^31 elements of g / jac values)
@@ -262,7 +299,13 @@ __device__ __forceinline__ void flush_coop(const double *stg_cta, const int2 *ta
 #pragma unroll
                     for (int i = 0; i < 4; ++i) v[i] = s[(h + i) * N_D];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) __stcs(base + (off + (h + i) * step), v[i]);
+                    for (int i = 0; i < 4; ++i) {
+#ifdef AWE_EXP_NO_STORE
+                        if (v[i] == 1.2345e301) __stcs(base + (off + (h + i) * step), v[i]);   /* ablation: staging reads kept, stores (almost) never issued */
+#else
+                        __stcs(base + (off + (h + i) * step), v[i]);
+#endif
+                    }
                 }
             } else {
 #pragma unroll 1
@@ -274,7 +317,7 @@ __device__ __forceinline__ void flush_coop(const double *stg_cta, const int2 *ta
             }
         }
     }
-    __syncthreads();
+    quad_sync(bar_id);
 }
 
 // lane = (instance group, output): output o = lane % AWE_CHUNK of the chunk, instances i = lane / AWE_CHUNK,
@@ -404,6 +447,7 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
     }
     // ---- constant Jacobian entries owned by this interval (continuity; periodicity on the last one):
     //      the value does not depend on the instance, thread = entry
+#ifndef AWE_EXP_NO_CONST
     if (Jv) {
         const int e1 = __ldg(pr.const_begin + k + 1);
         for (int e = __ldg(pr.const_begin + k) + tid; e < e1; e += GATHER_THREADS) {
@@ -416,6 +460,7 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
             }
         }
     }
+#endif
     // ---- periodicity rows  x_0 - x_{n_k-1, d-1}           (awebox/ocp/operation.py:245-267)
     if (k == pr.n_k - 1) {
         for (int u = warp; u < n_valid; u += GATHER_THREADS / 32) {
@@ -467,7 +512,11 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
     constexpr int HOT = HOT_OF(SHOOT, FULL);
     constexpr int NEX = EXPORTS_OF(SHOOT, FULL);
     // the cooperative flush needs the CTA to be exactly the N_D nodes of one interval
+#ifdef AWE_EXP_NO_COOP
+    constexpr bool COOP = false;          /* ablation: per-warp flush for the collocation nodes as well */
+#else
     constexpr bool COOP = !SHOOT && FULL && STAGE == 0 && !BATCH_MINOR && N_D == NODE_WARPS;
+#endif
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // CTA order: blocks of `ilv` consecutive CTA-items, all groups of a block before the next block, so
@@ -519,9 +568,12 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
     double *g_tile = G + (size_t)b0 * n_g;
     double *j_tile = Jv ? Jv + (size_t)b0 * (size_t)nnz : nullptr;
     const int2 *coop_tab = pr.coop_tab + (size_t)k * AWE_K_COLL_NCHUNKS * COOP_PER;
-    const int2 *tab_smem = reinterpret_cast<const int2 *>(smem + (size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES);
+    const int2 *tab_smem = reinterpret_cast<const int2 *>(smem + (size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES +
+                                                          COOP_NCONST * STG_STRIDE);
     const unsigned tab_addr = (unsigned)__cvta_generic_to_shared(tab_smem);
     int fl_code = -1;
+    constexpr int bar_id = 0;
+    constexpr bool EX_RW = false;
     (void)dest, (void)g_tile, (void)j_tile, (void)coop_tab, (void)tab_smem, (void)tab_addr, (void)fl_code;
 #define RUN(FILE_)           \
     switch (group) {         \
@@ -588,13 +640,13 @@ awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int
 }
 
 template <bool SHOOT, bool FULL>
-static constexpr size_t node_smem_bytes()
+__host__ __device__ static constexpr size_t node_smem_bytes()
 {
     return sizeof(double) * ((size_t)HOT_OF(SHOOT, FULL) * NODE_THREADS + NODE_WARPS * STG_DOUBLES) +
-           ((!SHOOT && FULL) ? sizeof(int2) * AWE_K_COLL_MAXQ * COOP_PER : 0);
+           ((!SHOOT && FULL) ? sizeof(double) * COOP_NCONST * STG_STRIDE + sizeof(int2) * AWE_K_COLL_MAXQ * COOP_PER : 0);
 }
 template <bool SHOOT, bool FULL, int STAGE>
-static constexpr int node_groups()
+__host__ __device__ static constexpr int node_groups()
 {
     return SHOOT ? (FULL ? (STAGE == 0 ? AWE_K_SHOOT_S0_GROUPS : STAGE == 1 ? AWE_K_SHOOT_S1_GROUPS : AWE_K_SHOOT_S2_GROUPS)
                          : (STAGE == 0 ? AWE_K_SHOOT_RES_S0_GROUPS
@@ -603,6 +655,137 @@ static constexpr int node_groups()
                          : (STAGE == 0 ? AWE_K_COLL_RES_S0_GROUPS
                                        : STAGE == 1 ? AWE_K_COLL_RES_S1_GROUPS : AWE_K_COLL_RES_S2_GROUPS));
 }
+
+#ifdef AWE_WITH_FUSED
+// --------------------------------------------------------------------------- fused persistent kernel
+// EXPERIMENT (compiled with -DAWE_WITH_FUSED, selected with AWEGPU_FUSED=1): measured 1.5x SLOWER than the
+// per-stage kernels on B200 (profiles/r01_ncu_fused_variant_B1024.txt: 36 % of the stall samples are
+// instruction fetch when the quads drift apart, and in lock step all warps wait for their inputs together).
+// One CTA per SM, FUSED_QUADS quads of NODE_WARPS warps.  A quad owns one interval of one tile (its N_D
+// collocation nodes) or NODE_WARPS shooting nodes; the CTA walks over its units and runs, for every unit, ALL
+// programs of the node function back to back: pre-stages (exports) first, then the output groups.  All warps
+// of the SM execute the same program at the same time (one ~27 KB program in the instruction cache), and the
+// exported intermediates live in a per-warp slot that is rewritten for every unit: they stay in L2 and never
+// travel to HBM, input records are read from HBM once.  Full Jacobian, instance-major layout only.
+#define SMEM_PER_SM (227 * 1024)
+template <bool SHOOT>
+__host__ __device__ static constexpr int fused_quads()
+{
+    // quads that fit the shared memory of one SM (at most 3: the register file holds 12 warps of these programs)
+    return (int)(SMEM_PER_SM / node_smem_bytes<SHOOT, true>() >= 3 ? 3 : SMEM_PER_SM / node_smem_bytes<SHOOT, true>());
+}
+
+template <bool SHOOT>
+__global__ void __launch_bounds__(NODE_THREADS * (fused_quads<SHOOT>() > 0 ? fused_quads<SHOOT>() : 1), 1)
+awegpu_fused_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const int n_items,
+                    double *__restrict__ ex_slots, double *__restrict__ G, double *__restrict__ Jv)
+{
+    constexpr bool FULL = true, BATCH_MINOR = false, EX_RW = true;
+    constexpr int HOT = HOT_OF(SHOOT, FULL);
+    constexpr int NEX = EXPORTS_OF(SHOOT, FULL);
+    constexpr bool COOP = !SHOOT && N_D == NODE_WARPS;
+    constexpr int FUSED_QUADS = fused_quads<SHOOT>();
+    constexpr int N2 = node_groups<SHOOT, true, 2>(), N1 = node_groups<SHOOT, true, 1>(), N0 = node_groups<SHOOT, true, 0>();
+    constexpr size_t QUAD_DOUBLES = node_smem_bytes<SHOOT, true>() / sizeof(double);
+    extern __shared__ double smem_all[];
+    const int quad = threadIdx.x / NODE_THREADS;
+    const int tid = threadIdx.x - quad * NODE_THREADS, lane = tid & 31, wid = tid >> 5;
+    const int bar_id = 1 + quad;
+    double *smem = smem_all + (size_t)quad * QUAD_DOUBLES;
+    double *stg = smem + (size_t)HOT * NODE_THREADS + wid * STG_DOUBLES;
+    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
+    const int2 *tab_smem = reinterpret_cast<const int2 *>(smem + (size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES +
+                                                          COOP_NCONST * STG_STRIDE);
+    const unsigned tab_addr = (unsigned)__cvta_generic_to_shared(tab_smem);
+    const int n_g = pr.n_g;
+    const int nnz = (int)pr.nnz;
+    // exports: one slot per resident warp, rewritten for every unit
+    double *w_ex = ex_slots + ((size_t)blockIdx.x * (FUSED_QUADS * NODE_WARPS) + quad * NODE_WARPS + wid) * (NEX > 0 ? NEX : 1) * 32 + lane;
+    constexpr int PER_UNIT = FUSED_QUADS * NODE_WARPS;
+    (void)stg, (void)scr_addr, (void)tab_smem, (void)tab_addr, (void)w_ex, (void)bar_id;
+#pragma unroll 1
+    for (int unit = blockIdx.x; unit * PER_UNIT < n_items; unit += gridDim.x) {
+        const int item_raw = unit * PER_UNIT + quad * NODE_WARPS + wid;
+        const bool active = item_raw < n_items;        // a whole quad is active or not (collocation: N_D == NODE_WARPS)
+        const int item = active ? item_raw : n_items - 1;
+        int tile, k, j;
+        if (SHOOT) {
+            j = -1, k = item % pr.n_k, tile = item / pr.n_k;
+        } else {
+            j = item % N_D, k = (item / N_D) % pr.n_k, tile = item / (N_D * pr.n_k);
+        }
+        const int j1 = j + 1;
+        const int b0 = b_base + tile * TILE;
+        const int b = b0 + lane;
+        const bool valid = b < B;
+        const int n_valid = min(TILE, B - b0);
+        const double *w_rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32 + lane;
+        const double *w_own = SHOOT ? w_rec + OFF_X0 * 32 : w_rec + OFF_CX(j) * 32;
+        const double *w_z = SHOOT ? w_rec + OFF_Z * 32 : w_own + N_X * 32;
+        const double *w_xd = SHOOT ? w_rec + OFF_XDOT * 32
+                                   : sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
+        const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
+        const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
+        const double itf_nk = itf * (double)pr.n_k;
+        const int *dest = SHOOT ? pr.shoot_dest + (size_t)k * pr.n_shoot_out
+                                : pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
+        double *g_tile = G + (size_t)b0 * n_g;
+        double *j_tile = Jv + (size_t)b0 * (size_t)nnz;
+        const int2 *coop_tab = pr.coop_tab + (size_t)k * AWE_K_COLL_NCHUNKS * COOP_PER;
+        int fl_code = -1;
+        (void)itf_nk, (void)valid, (void)n_valid, (void)dest, (void)g_tile, (void)j_tile, (void)coop_tab, (void)fl_code;
+        (void)j1, (void)w_own, (void)w_z, (void)w_xd, (void)w_pt, (void)b;
+#pragma unroll 1
+        for (int prog = 0; prog < N2 + N1 + N0; ++prog) {
+            if (active) {
+                if (prog < N2) {
+                    const int group = prog;
+                    if (SHOOT) {
+                        switch (group) {
+#include "k_shoot_s2.inc"
+                        }
+                    } else {
+                        switch (group) {
+#include "k_coll_s2.inc"
+                        }
+                    }
+                } else if (prog < N2 + N1) {
+                    const int group = prog - N2;
+                    if (SHOOT) {
+                        switch (group) {
+#include "k_shoot_s1.inc"
+                        }
+                    } else {
+                        switch (group) {
+#include "k_coll_s1.inc"
+                        }
+                    }
+                } else {
+                    const int group = prog - N2 - N1;
+                    if (SHOOT) {
+                        switch (group) {
+#include "k_shoot_s0.inc"
+                        }
+                    } else {
+                        switch (group) {
+#include "k_coll_s0.inc"
+                        }
+                    }
+                }
+            }
+#ifdef AWE_FUSED_LOCKSTEP
+            // all warps of the SM move to the next program together (instruction-cache locality).  Measured
+            // slower on B200 than letting the quads drift: in lock step all warps wait for their opening input
+            // loads at the same time.  Nothing else needs this barrier: the staging area, spill slots and export
+            // slot are per warp, the flush table is protected by the quad barriers of the flush itself.
+            __syncthreads();
+#endif
+        }
+    }
+}
+
+#endif  /* AWE_WITH_FUSED */
+
 static constexpr size_t gather_smem_bytes() { return sizeof(double) * TILE * SLAB_STRIDE; }
 
 // =========================================================================== host side / C ABI
@@ -626,6 +809,9 @@ struct awegpu_handle {
     // node-input records of one chunk of instances (see awegpu_gather_kernel)
     Scratch sc{};
     int chunk_tiles = 0, scratch_tiles = 0;
+    double *ex_coll = nullptr, *ex_shoot = nullptr;   // export slots of the fused kernels
+    int n_sm = 0, fused = 1;
+    int n_rest = 0;          // constant Jacobian entries the cooperative flush does not carry
     int n_affp = 0;          // parameter terms of the affine rows (> 0: the full parameter vector is required)
     int interleave = 1;      // tiles per block of the group-interleaved stage-0 order (0: group-major)
     // casadi sparsity buffers
@@ -686,6 +872,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     for (void *p : h->dev_allocs) cudaFree(p);
     cudaFree(h->dW), cudaFree(h->dP), cudaFree(h->dG), cudaFree(h->dJ);
     cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
+    cudaFree(h->ex_coll), cudaFree(h->ex_shoot);
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -756,12 +943,17 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
                 n < p->n_shoot_eq                ? -2 - (p->row_shoot[k] + n)
                 : n < p->n_shoot_eq + p->n_ineq ? -2 - (p->row_path[k] + n - p->n_shoot_eq)
                                                 : p->shoot_slot[(size_t)k * p->n_shoot_out + n];
-    // interval-cooperative flush tables (collocation kernel, stage 0)
-    const int per = N_D * AWE_CHUNK;
+    // interval-cooperative flush tables (collocation kernel, stage 0).  Constant Jacobian entries (continuity
+    // rows) that lie next to the staged entries of a chunk in the CCS value array ride along: their value comes
+    // from a row of replicated constants, and the stores of the chunk become longer contiguous runs.  What does
+    // not fit (periodicity, affine rows, x_{n_k}) stays with the gather kernel ("rest" lists).
+    const int per = COOP_PER;
     std::vector<int2> coop_tab((size_t)nk * AWE_K_COLL_NCHUNKS * per, make_int2(-1, 0));
+    std::vector<std::vector<std::pair<long long, int>>> ents((size_t)nk * AWE_K_COLL_NCHUNKS);
+    std::vector<int> owner((size_t)p->nnz, -1);          // CCS slot -> (k, q) of the chunk that writes it
     for (int k = 0; k < nk; ++k)
         for (int q = 0; q < AWE_K_COLL_NCHUNKS; ++q) {
-            std::vector<std::pair<long long, int>> ent;
+            std::vector<std::pair<long long, int>> &ent = ents[(size_t)k * AWE_K_COLL_NCHUNKS + q];
             for (int j = 0; j < dd; ++j)
                 for (int o = 0; o < awe_k_coll_chunk_cnt[q]; ++o) {
                     const int code = coll_dest[((size_t)k * dd + j) * p->n_coll_out + awe_k_coll_chunk_first[q] + o];
@@ -769,14 +961,47 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
                     // g rows first (ascending row), then CCS slots (ascending)
                     const long long key = code <= -2 ? (long long)(-2 - code) : (1ll << 40) + code;
                     ent.push_back({key, j * AWE_CHUNK + o});
+                    if (code >= 0) owner[code] = k * AWE_K_COLL_NCHUNKS + q;
                 }
-            std::sort(ent.begin(), ent.end());
-            for (size_t e = 0; e < ent.size(); ++e) {
-                const long long key = ent[e].first;
-                coop_tab[((size_t)k * AWE_K_COLL_NCHUNKS + q) * per + e] =
-                    make_int2(key >= (1ll << 40) ? (int)(key - (1ll << 40)) : -2 - (int)key, ent[e].second);
-            }
         }
+    std::vector<double> cvals;
+    std::vector<int> rest_slot, rest_begin;
+    std::vector<double> rest_val;
+    const bool coop_possible = (dd == NODE_WARPS);
+    for (int k = 0; k < nk; ++k) {
+        rest_begin.push_back((int)rest_slot.size());
+        for (int e = p->const_begin[k]; e < p->const_begin[k + 1]; ++e) {
+            const int slot = p->const_slot[e];
+            const double v = p->const_val[e];
+            int target = -1;
+            for (int dist = 1; coop_possible && dist <= 2 && target < 0; ++dist)
+                for (int sgn = -1; sgn <= 1 && target < 0; sgn += 2) {
+                    const long long nb = (long long)slot + sgn * dist;
+                    if (nb >= 0 && nb < p->nnz && owner[nb] >= 0 && ents[owner[nb]].size() < (size_t)per) target = owner[nb];
+                }
+            int cid = -1;
+            if (target >= 0) {
+                for (size_t c = 0; c < cvals.size(); ++c)
+                    if (cvals[c] == v) cid = (int)c;
+                if (cid < 0 && cvals.size() < COOP_NCONST) cvals.push_back(v), cid = (int)cvals.size() - 1;
+            }
+            if (target >= 0 && cid >= 0)
+                ents[target].push_back({(1ll << 40) + slot, COOP_STAGED + cid});
+            else
+                rest_slot.push_back(slot), rest_val.push_back(v);
+        }
+    }
+    rest_begin.push_back((int)rest_slot.size());
+    for (size_t t = 0; t < ents.size(); ++t) {
+        std::sort(ents[t].begin(), ents[t].end());
+        for (size_t e = 0; e < ents[t].size(); ++e) {
+            const long long key = ents[t][e].first;
+            coop_tab[t * per + e] = make_int2(key >= (1ll << 40) ? (int)(key - (1ll << 40)) : -2 - (int)key, ents[t][e].second);
+        }
+    }
+    cvals.resize(COOP_NCONST, 0.0);
+    CK(cudaMemcpyToSymbol(c_coop_const, cvals.data(), sizeof(double) * COOP_NCONST));
+    h->n_rest = (int)rest_slot.size();
     int rc = 0;
     rc |= to_device(h, coop_tab.data(), coop_tab.size(), &d.coop_tab);
     rc |= to_device(h, p->x_base, (size_t)nk * (dd + 1), &d.x_base);
@@ -789,6 +1014,9 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     rc |= to_device(h, p->const_slot, (size_t)p->n_const, &d.const_slot);
     rc |= to_device(h, p->const_begin, (size_t)nk + 1, &d.const_begin);
     rc |= to_device(h, p->const_val, (size_t)p->n_const, &d.const_val);
+    rc |= to_device(h, rest_slot.data(), rest_slot.size(), &d.rest_slot);
+    rc |= to_device(h, rest_begin.data(), rest_begin.size(), &d.rest_begin);
+    rc |= to_device(h, rest_val.data(), rest_val.size(), &d.rest_val);
     rc |= to_device(h, p->aff_row, (size_t)p->n_aff, &d.aff_row);
     rc |= to_device(h, p->aff_begin, (size_t)p->n_aff + 1, &d.aff_begin);
     rc |= to_device(h, p->affp_begin, (size_t)p->n_aff + 1, &d.affp_begin);
@@ -820,6 +1048,26 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     SET_NODE(true, true);
     SET_NODE(true, false);
     SET_SMEM(awegpu_gather_kernel<false>, gather_smem_bytes());
+#ifdef AWE_WITH_FUSED
+    {
+        // fused persistent kernels (full Jacobian, instance-major): one CTA per SM
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        h->n_sm = prop.multiProcessorCount;
+        const char *ef = getenv("AWEGPU_FUSED");
+        h->fused = ef ? atoi(ef) : 0;
+        if (fused_quads<false>() < 1 || fused_quads<true>() < 1) h->fused = 0;
+        if (h->fused) {
+            SET_SMEM(awegpu_fused_kernel<false>, (fused_quads<false>() * node_smem_bytes<false, true>()));
+            SET_SMEM(awegpu_fused_kernel<true>, (fused_quads<true>() * node_smem_bytes<true, true>()));
+            const size_t line = sizeof(double) * 32;
+            CK(cudaMalloc((void **)&h->ex_coll, line * h->n_sm * fused_quads<false>() * NODE_WARPS * (AWE_K_COLL_EXPORTS ? AWE_K_COLL_EXPORTS : 1)));
+            CK(cudaMalloc((void **)&h->ex_shoot, line * h->n_sm * fused_quads<true>() * NODE_WARPS * (AWE_K_SHOOT_EXPORTS ? AWE_K_SHOOT_EXPORTS : 1)));
+        }
+    }
+#else
+    h->fused = 0;
+#endif
     SET_SMEM(awegpu_gather_kernel<AWE_BATCH_MINOR != 0>, gather_smem_bytes());
 #undef SET_NODE
 #undef SET_NODE1
@@ -920,7 +1168,11 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
         return 1;
     }
     const int tiles = (B + TILE - 1) / TILE;
-    const DevProblem &dp = h->dp;
+    DevProblem dp = h->dp;
+    if (full && !bm && N_D == NODE_WARPS) {
+        // the collocation kernel of this call flushes cooperatively and carries most constant entries itself
+        dp.const_slot = dp.rest_slot, dp.const_begin = dp.rest_begin, dp.const_val = dp.rest_val;
+    }
     {
         const int rc_ = ensure_scratch(h, tiles < h->chunk_tiles ? tiles : h->chunk_tiles);
         if (rc_) return rc_;
@@ -960,6 +1212,20 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
         else
             awegpu_gather_kernel<false><<<dim3(ct, dp.n_k), GATHER_THREADS, gather_smem_bytes(), st>>>(
                 dp, h->sc, B, b_base, W, P, ldp, p_off, G, jv);
+#ifdef AWE_WITH_FUSED
+        if (full && !bm && h->fused) {
+            const int nc_ = ct * dp.n_k * N_D, ns_ = ct * dp.n_k;
+            constexpr int uc_ = fused_quads<false>() * NODE_WARPS, us_ = fused_quads<true>() * NODE_WARPS;
+            const int gs_ = std::min(h->n_sm, (ns_ + us_ - 1) / us_), gc_ = std::min(h->n_sm, (nc_ + uc_ - 1) / uc_);
+            awegpu_fused_kernel<true><<<gs_, NODE_THREADS * fused_quads<true>(), fused_quads<true>() * node_smem_bytes<true, true>(), st>>>(
+                dp, h->sc, B, b_base, ns_, h->ex_shoot, G, jv);
+            if (t0 == 0) CK(cudaEventRecord(h->ev_k0, st));
+            awegpu_fused_kernel<false><<<gc_, NODE_THREADS * fused_quads<false>(), fused_quads<false>() * node_smem_bytes<false, true>(), st>>>(
+                dp, h->sc, B, b_base, nc_, h->ex_coll, G, jv);
+            if (t0 == 0) CK(cudaEventRecord(h->ev_k1, st));
+            h->launches += 2;
+        } else
+#endif
         if (full && !bm) LAUNCH_NODES(true, false);
         else if (full && bm) LAUNCH_NODES(true, true);
         else if (!full && !bm) LAUNCH_NODES(false, false);

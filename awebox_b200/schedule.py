@@ -377,3 +377,33 @@ def prefetch_leaves(prog, pool, ahead, prefetchable, step=4):
     prog.stats = dict(prog.stats, pool=int(used.max()) + 1 if len(used) else 0, pf=len(info), pf_exposed=exposed,
                       pf_mean_ahead=(dist / max(1, len(info))))
     return prog
+
+
+def prefetch_hints(prog, ahead, wanted):
+    """Insert ('pfh', node) ``ahead`` operations before every ('leaf', reg, node) with ``wanted(node)``: a
+    cache prefetch of the input (no register, no scratch slot, no scoreboard), so that the load proper, which
+    the allocator issues a few dozen statements before the first use, finds the line in L2 instead of HBM."""
+    ins = prog.ins
+    opcount, c = [], 0
+    for it in ins:
+        opcount.append(c)
+        if it[0] == 'op':
+            c += 1
+    first_at = {}
+    for i, oc in enumerate(opcount):
+        first_at.setdefault(oc, i)
+    place = {}
+    n = 0
+    for t, it in enumerate(ins):
+        if it[0] == 'leaf' and wanted(it[2]):
+            p = first_at.get(max(0, opcount[t] - ahead), 0)
+            if p < t:
+                place.setdefault(p, []).append(('pfh', it[2]))
+                n += 1
+    out = []
+    for i, it in enumerate(ins):
+        out.extend(place.get(i, []))
+        out.append(it)
+    prog.ins = out
+    prog.stats = dict(prog.stats, pf_hints=n)
+    return prog

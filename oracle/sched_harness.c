@@ -33,6 +33,11 @@ static const double awe_kconst[AWE_N_KCONST] = AWE_KCONST_INIT;
 #define LD_EX(reg, i) reg = ex_[i]
 /* asynchronous input prefetch ring (awebox_b200/schedule.py: prefetch_leaves): copies complete in issue
  * order and only when a wait forces them to, so that a wrong wait count reads a stale slot */
+#define PFH_XO(m)
+#define PFH_XD(m)
+#define PFH_U(c)
+#define PFH_Z(c)
+#define PFH_EX(i)
 #define PF_(slot, val) do { pf_slot[pf_n % 4096] = (slot); pf_val[pf_n % 4096] = (val); ++pf_n; } while (0)
 #define PF_XO(slot, m) PF_(slot, xo[m])
 #define PF_XD(slot, m) PF_(slot, xd[m])
