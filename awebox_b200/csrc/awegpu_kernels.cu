@@ -81,6 +81,8 @@ struct DevProblem {
     // the same for calls whose collocation kernel flushes cooperatively: only the entries the flush tables do not carry
     const int *rest_slot, *rest_begin;
     const double *rest_val;
+    const double *coop_const;      // [COOP_NCONST] distinct values of the constant entries flushed cooperatively
+                                   // (per handle: several handles may share this library)
     int n_aff;
     const int *aff_row, *aff_begin, *aff_col, *affp_begin, *affp_col;
     const double *aff_coef, *affp_coef, *aff_const;
@@ -100,7 +102,6 @@ struct Scratch {
 __constant__ double c_kconst[AWE_N_KCONST] = AWE_KCONST_INIT;
 #define KC(i) c_kconst[i]
 #define COOP_NCONST 8
-__constant__ double c_coop_const[COOP_NCONST];      // distinct values of the constant entries flushed cooperatively
 __constant__ double c_coeff_coll[(N_D + 1) * (N_D + 1)];
 __constant__ double c_coeff_cont[N_D + 1];
 
@@ -237,7 +238,7 @@ __device__ __forceinline__ double sqrt_nr(const double x)
                              "r"(tab_addr + e_ * 8), "l"(coop_tab + (q0) * COOP_PER + e_) : "memory"); \
             asm volatile("cp.async.commit_group;" ::: "memory");                                     \
             for (int e_ = tid; e_ < COOP_NCONST * STG_STRIDE; e_ += NODE_THREADS)                    \
-                smem[(size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES + e_] = c_coop_const[e_ / STG_STRIDE]; \
+                smem[(size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES + e_] = __ldg(pr.coop_const + e_ / STG_STRIDE); \
         } else                                                                                       \
             FLUSH_PREP(q0, first);                                                                   \
     } while (0)
@@ -1000,7 +1001,6 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         }
     }
     cvals.resize(COOP_NCONST, 0.0);
-    CK(cudaMemcpyToSymbol(c_coop_const, cvals.data(), sizeof(double) * COOP_NCONST));
     h->n_rest = (int)rest_slot.size();
     int rc = 0;
     rc |= to_device(h, coop_tab.data(), coop_tab.size(), &d.coop_tab);
@@ -1017,6 +1017,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     rc |= to_device(h, rest_slot.data(), rest_slot.size(), &d.rest_slot);
     rc |= to_device(h, rest_begin.data(), rest_begin.size(), &d.rest_begin);
     rc |= to_device(h, rest_val.data(), rest_val.size(), &d.rest_val);
+    rc |= to_device(h, cvals.data(), cvals.size(), &d.coop_const);
     rc |= to_device(h, p->aff_row, (size_t)p->n_aff, &d.aff_row);
     rc |= to_device(h, p->aff_begin, (size_t)p->n_aff + 1, &d.aff_begin);
     rc |= to_device(h, p->affp_begin, (size_t)p->n_aff + 1, &d.affp_begin);
@@ -1026,6 +1027,20 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     rc |= to_device(h, p->aff_coef, (size_t)(p->n_aff ? p->aff_begin[p->n_aff] : 0), &d.aff_coef);
     rc |= to_device(h, p->aff_const, (size_t)p->n_aff, &d.aff_const);
     if (rc) return rc;
+    {
+        // the collocation coefficients are constants of the library (one spec = one scheme and order): handles
+        // that share the library must agree on them
+        static std::mutex mu;
+        static std::vector<double> seen;
+        std::lock_guard<std::mutex> lock(mu);
+        std::vector<double> now(p->coeff_coll, p->coeff_coll + (dd + 1) * (dd + 1));
+        now.insert(now.end(), p->coeff_cont, p->coeff_cont + dd + 1);
+        if (!seen.empty() && seen != now) {
+            set_err(h, "another handle of this library uses different collocation coefficients");
+            return 4;
+        }
+        seen = now;
+    }
     CK(cudaMemcpyToSymbol(c_coeff_coll, p->coeff_coll, sizeof(double) * (dd + 1) * (dd + 1)));
     CK(cudaMemcpyToSymbol(c_coeff_cont, p->coeff_cont, sizeof(double) * (dd + 1)));
     h->colind.assign(p->colind, p->colind + p->n_v + 1);
