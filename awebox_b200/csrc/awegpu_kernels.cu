@@ -303,6 +303,8 @@ __device__ __forceinline__ void flush_coop(const double *stg_cta, const int2 *ta
                     for (int i = 0; i < 4; ++i) {
 #ifdef AWE_EXP_NO_STORE
                         if (v[i] == 1.2345e301) __stcs(base + (off + (h + i) * step), v[i]);   /* ablation: staging reads kept, stores (almost) never issued */
+#elif defined(AWE_EXP_STORE_NEAR)
+                        __stcs(base + ((off + (h + i) * step) & 0xFFFF), v[i]);   /* ablation: every store lands in the first 512 KB of the tile (L2-resident) */
 #else
                         __stcs(base + (off + (h + i) * step), v[i]);
 #endif
@@ -815,6 +817,7 @@ struct awegpu_handle {
     int n_rest = 0;          // constant Jacobian entries the cooperative flush does not carry
     int n_affp = 0;          // parameter terms of the affine rows (> 0: the full parameter vector is required)
     int interleave = 1;      // tiles per block of the group-interleaved stage-0 order (0: group-major)
+    int interleave_pre = 1;  // the same for the pre-stages
     // casadi sparsity buffers
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
     std::vector<double> scratch_g;
@@ -1102,6 +1105,8 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         h->chunk_tiles = ct;
         const char *ei = getenv("AWEGPU_INTERLEAVE");
         h->interleave = ei ? atoi(ei) : 1;
+        const char *ep = getenv("AWEGPU_INTERLEAVE_PRE");
+        h->interleave_pre = ep ? atoi(ep) : 1;
     }
     // host copies of pointers are not kept: null them so nobody dereferences caller memory later
     h->host.x_base = h->host.x_next = h->host.u_base = h->host.xdot_base = h->host.z_base = nullptr;
@@ -1200,7 +1205,7 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
             /* the output layout only matters to the output stage: pre-stages have one instantiation */       \
             awegpu_node_kernel<S_, F, T_, ((T_) == 0) && (M) && AWE_BATCH_MINOR><<<dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>()), \
                                                NODE_THREADS, node_smem_bytes<S_, F>(), st_>>>(dp, h->sc, B, b_base, n_, p_sh,          \
-                                                                                             (T_) == 0 ? h->interleave * (((S_) ? dp.n_k : dp.n_k * N_D) + NODE_WARPS - 1) / NODE_WARPS : 0, G, jv); \
+                                                                                             ((T_) == 0 ? h->interleave : h->interleave_pre) * (((S_) ? dp.n_k : dp.n_k * N_D) + NODE_WARPS - 1) / NODE_WARPS, G, jv); \
             h->launches += 1;                                                                                     \
         }                                                                                                         \
     } while (0)

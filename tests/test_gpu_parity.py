@@ -118,6 +118,44 @@ def test_mpc_scenario_batch():
         ev.eval(W, P[:, ocp.p_theta0:])          # the initial rows need p.ref: theta0-only blocks are refused
 
 
+def test_chunked_batches(monkeypatch):
+    """batches larger than the side buffers are evaluated in chunks of tiles (forced small here)."""
+    from awebox_b200.evaluator import Evaluator
+    monkeypatch.setenv('AWEGPU_CHUNK_TILES', '2')
+    ocp = get_ocp('ampyx_ap2', 4)
+    ev = Evaluator('ampyx_ap2', ocp=ocp)
+    try:
+        B = 257                                            # 9 tiles -> 5 chunks, the last one ragged
+        W = synthetic.batch(ocp, B, seed=21)
+        p = ocp.default_p()
+        G0, J0 = get_oracle('ampyx_ap2', 4).eval(W, p, flags=cabi.AWEGPU_P_SHARED)
+        G, Jv = ev.eval(W, p)
+        assert_parity(ocp, G, Jv, G0, J0)
+        G2, _ = ev.eval(W, p, jac=False)
+        assert np.all(np.abs(G2 - G0) <= 1e-12 * np.maximum(1.0, np.abs(G0)))
+    finally:
+        ev.close()
+
+
+def test_pinned_host_pipeline_matches_staged_entry():
+    """AWEGPU_HOST_PINNED (direct chunked copies on three streams, what bench.py's e2e leg times) against the
+    staged host entry."""
+    import torch
+    ev = evaluator('ampyx_ap2', 4)
+    ocp = ev.ocp
+    B = 1200                                               # three 512-instance copy chunks, the last one ragged
+    W = synthetic.batch(ocp, B, seed=22)
+    p = ocp.default_p()
+    G0, J0 = ev.eval(W, p)
+    hW, hP = torch.from_numpy(W).pin_memory(), torch.from_numpy(p).pin_memory()
+    hG = torch.empty((B, ocp.n_g), dtype=torch.float64).pin_memory()
+    hJ = torch.empty((B, ocp.nnz), dtype=torch.float64).pin_memory()
+    rc = ev.lib.awegpu_eval_batch_host(ev.handle, B, hW.data_ptr(), hP.data_ptr(), hG.data_ptr(), hJ.data_ptr(),
+                                       cabi.AWEGPU_P_SHARED | cabi.AWEGPU_HOST_PINNED)
+    assert rc == 0
+    assert np.array_equal(hG.numpy(), G0) and np.array_equal(hJ.numpy(), J0)
+
+
 def test_empty_batch_is_a_no_op():
     ev = evaluator('ampyx_ap2', 4)
     G, Jv = ev.eval(np.zeros((0, ev.n_v)), ev.ocp.default_p())
