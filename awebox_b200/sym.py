@@ -166,7 +166,9 @@ def add(a, b):
         return sub(a, b.a)
     if a.op == NEG:
         return sub(b, a.a)
-    if a.idx > b.idx:
+    # canonical operand order: a constant first, otherwise by creation index (constants are cached across
+    # models, so their index must not decide: the generated text would depend on what was built before)
+    if b.op == CONST or (a.op != CONST and a.idx > b.idx):
         a, b = b, a
     return _mk(ADD, a, b)
 
