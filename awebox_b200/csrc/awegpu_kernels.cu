@@ -305,6 +305,8 @@ __device__ __forceinline__ void flush_coop(const double *stg_cta, const int2 *ta
                         if (v[i] == 1.2345e301) __stcs(base + (off + (h + i) * step), v[i]);   /* ablation: staging reads kept, stores (almost) never issued */
 #elif defined(AWE_EXP_STORE_NEAR)
                         __stcs(base + ((off + (h + i) * step) & 0xFFFF), v[i]);   /* ablation: every store lands in the first 512 KB of the tile (L2-resident) */
+#elif defined(AWE_EXP_ST_DEFAULT)
+                        base[off + (h + i) * step] = v[i];       /* ablation: default (write-back, evict-normal) stores */
 #else
                         __stcs(base + (off + (h + i) * step), v[i]);
 #endif
