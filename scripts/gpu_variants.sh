@@ -1,5 +1,5 @@
-for ip in 0 1 2; do
-  echo "interleave_pre=$ip"; AWEGPU_INTERLEAVE_PRE=$ip python scripts/variant_check.py 4096 2>&1 | tail -1
+for rep in 1 2 3; do
+for f in awebox_b200/lib/var/*pol0.so awebox_b200/lib/var/*pol1.so; do
+  AWEGPU_LIB=$f timeout 300 python scripts/variant_check.py 4096 2>&1 | tail -1 | cut -c1-40,86-140
 done
-AWEGPU_INTERLEAVE_PRE=1 python scripts/profile_step.py 4096 3 > /dev/null 2>&1 && AWEGPU_INTERLEAVE_PRE=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 18 --csv --log-file gpurun_out/l_cur.csv python scripts/profile_step.py 4096 3 > /dev/null 2>&1
-python scripts/launch_summary.py gpurun_out/l_cur.csv 6
+done
