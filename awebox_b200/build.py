@@ -18,7 +18,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '--shared', '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-diag-suppress', '177', '--split-compile', '0']
+              '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-diag-suppress', '177']
+N_TU = 5        # translation units of awegpu_kernels.cu (-DAWE_TU=0..4), compiled side by side and linked
 
 
 def gen_dir(spec_name):
@@ -57,11 +58,14 @@ def find_nvcc():
     return nvcc
 
 
-def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None):
+def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None, gen=None):
+    """nvcc: one object per translation unit (-DAWE_TU=n, in parallel: the front end is single-threaded and
+    the generated programs are large), then one shared library.  Deterministic: no --split-compile."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIBDIR, exist_ok=True)
-    g = gen_dir(spec_name)
-    srcs = [os.path.join(CSRC, 'awegpu_kernels.cu')]
-    deps = srcs + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
+    g = gen or gen_dir(spec_name)
+    src = os.path.join(CSRC, 'awegpu_kernels.cu')
+    deps = [src] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
         [os.path.join(g, f) for f in sorted(os.listdir(g)) if f.endswith(('.h', '.inc'))] + \
         [os.path.join(ROOT, 'include', 'awegpu.h')]
     out = out or lib_path(spec_name)
@@ -69,14 +73,36 @@ def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None
     digest = _digest(deps) + ''.join(extra_flags)
     if not force and os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == digest:
         return out
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + ['-I', g, '-I', os.path.join(ROOT, 'include'), '-I', CSRC,
-                                                             '-o', out] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    nvcc = find_nvcc()
+    objdir = os.path.join(g, '_obj')
+    os.makedirs(objdir, exist_ok=True)
+    common = NVCC_FLAGS + list(extra_flags) + ['-I', g, '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
+
+    def one(tu):
+        obj = os.path.join(objdir, 'tu%d.o' % tu)
+        cmd = [nvcc] + common + ['-DAWE_TU=%d' % tu, '-c', '-o', obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return tu, obj, cmd, res
+
+    logs, objs = [], []
+    with ThreadPoolExecutor(N_TU) as pool:
+        results = list(pool.map(one, range(N_TU)))
+    for tu, obj, cmd, res in results:
+        logs.append(' '.join(cmd) + '\n' + res.stdout + res.stderr)
+        objs.append(obj)
+    failed = [r for r in results if r[3].returncode != 0]
+    if not failed:
+        cmd = [nvcc, '--shared', '-o', out] + objs
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        logs.append(' '.join(cmd) + '\n' + res.stdout + res.stderr)
+        if res.returncode != 0:
+            failed = [(-1, None, cmd, res)]
+    log = '\n'.join(logs)
     with open(os.path.join(g, 'nvcc.log'), 'w') as f:
-        f.write(' '.join(cmd) + '\n' + log)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + log[-4000:])
+        f.write(log)
+    shutil.rmtree(objdir, ignore_errors=True)
+    if failed:
+        raise RuntimeError('nvcc failed:\n' + (failed[0][3].stdout + failed[0][3].stderr)[-4000:])
     if verbose:
         print(log)
     with open(stamp, 'w') as f:

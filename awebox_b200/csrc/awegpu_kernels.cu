@@ -33,6 +33,17 @@
 #include "awegpu.h"
 #include "model_defs.h"
 
+// Translation units.  The generated programs make this file expensive to compile (minutes of single-threaded
+// front-end time for a large model), so the build compiles it several times side by side, each time with
+// -DAWE_TU=<n>, and links the objects: unit n instantiates one family of node kernels together with the functions
+// that launch them, unit 0 holds the gather kernel, the residual-only kernels and the host code / C ABI.
+// Without -DAWE_TU everything is in one unit.
+#ifndef AWE_TU
+#define AWE_TU -1
+#endif
+#define TU_OWNS(n) (AWE_TU == -1 || AWE_TU == (n))
+#define AWE_N_TU 5      /* 0 host, 1 coll full stage 0, 2 coll full stages 1-2, 3 shoot full stage 0, 4 shoot full stages 1-2 */
+
 #define TILE 32
 #ifndef AWE_NODE_CTAS
 #define AWE_NODE_CTAS 3          /* resident CTAs (of 4 warps) per SM the node kernels are compiled for */
@@ -672,7 +683,114 @@ __host__ __device__ static constexpr int node_groups()
                                        : STAGE == 1 ? AWE_K_COLL_RES_S1_GROUPS : AWE_K_COLL_RES_S2_GROUPS));
 }
 
-#ifdef AWE_WITH_FUSED
+// --------------------------------------------------------------------------- launch plumbing (per translation unit)
+struct NodeLaunch {
+    dim3 grid;
+    cudaStream_t st;
+    DevProblem dp;
+    Scratch sc;
+    int B, b_base, n_items, ilv;
+    const double *p_sh;
+    double *G, *Jv;
+};
+
+template <bool S, bool F, int T>
+static void launch_node_impl(const bool bm, const NodeLaunch &a)
+{
+    // the output layout only matters to the output stage: pre-stages have one instantiation
+    if (bm && T == 0 && AWE_BATCH_MINOR)
+        awegpu_node_kernel<S, F, T, (T == 0) && AWE_BATCH_MINOR><<<a.grid, NODE_THREADS, node_smem_bytes<S, F>(), a.st>>>(
+            a.dp, a.sc, a.B, a.b_base, a.n_items, a.p_sh, a.ilv, a.G, a.Jv);
+    else
+        awegpu_node_kernel<S, F, T, false><<<a.grid, NODE_THREADS, node_smem_bytes<S, F>(), a.st>>>(
+            a.dp, a.sc, a.B, a.b_base, a.n_items, a.p_sh, a.ilv, a.G, a.Jv);
+}
+
+template <bool S, bool F, int T>
+static cudaError_t attr_node_impl()
+{
+    cudaError_t e = cudaFuncSetAttribute(awegpu_node_kernel<S, F, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)node_smem_bytes<S, F>());
+    if (e == cudaSuccess && T == 0 && AWE_BATCH_MINOR)
+        e = cudaFuncSetAttribute(awegpu_node_kernel<S, F, T, (T == 0) && AWE_BATCH_MINOR>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node_smem_bytes<S, F>());
+    return e;
+}
+
+// every unit has its own copy of the __constant__ coefficient tables (no relocatable device code)
+static cudaError_t set_coeff_here(const double *coeff_coll, const double *coeff_cont)
+{
+    cudaError_t e = cudaMemcpyToSymbol(c_coeff_coll, coeff_coll, sizeof(double) * (N_D + 1) * (N_D + 1));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_coeff_cont, coeff_cont, sizeof(double) * (N_D + 1));
+    return e;
+}
+
+#define DECL_TU(n)                                                              \
+    void awe_launch_tu##n(int stage, bool bm, const NodeLaunch &a);             \
+    cudaError_t awe_init_tu##n(const double *coeff_coll, const double *coeff_cont);
+DECL_TU(1)
+DECL_TU(2)
+DECL_TU(3)
+DECL_TU(4)
+#undef DECL_TU
+
+#if TU_OWNS(1)
+void awe_launch_tu1(int, bool bm, const NodeLaunch &a) { launch_node_impl<false, true, 0>(bm, a); }
+cudaError_t awe_init_tu1(const double *cc, const double *cf)
+{
+    cudaError_t e = set_coeff_here(cc, cf);
+    return e != cudaSuccess ? e : attr_node_impl<false, true, 0>();
+}
+#endif
+#if TU_OWNS(2)
+void awe_launch_tu2(int stage, bool bm, const NodeLaunch &a)
+{
+    if (stage == 1) launch_node_impl<false, true, 1>(bm, a);
+    else launch_node_impl<false, true, 2>(bm, a);
+}
+cudaError_t awe_init_tu2(const double *cc, const double *cf)
+{
+    cudaError_t e = set_coeff_here(cc, cf);
+    if (e == cudaSuccess) e = attr_node_impl<false, true, 1>();
+    return e != cudaSuccess ? e : attr_node_impl<false, true, 2>();
+}
+#endif
+#if TU_OWNS(3)
+void awe_launch_tu3(int, bool bm, const NodeLaunch &a) { launch_node_impl<true, true, 0>(bm, a); }
+cudaError_t awe_init_tu3(const double *cc, const double *cf)
+{
+    cudaError_t e = set_coeff_here(cc, cf);
+    return e != cudaSuccess ? e : attr_node_impl<true, true, 0>();
+}
+#endif
+#if TU_OWNS(4)
+void awe_launch_tu4(int stage, bool bm, const NodeLaunch &a)
+{
+    if (stage == 1) launch_node_impl<true, true, 1>(bm, a);
+    else launch_node_impl<true, true, 2>(bm, a);
+}
+cudaError_t awe_init_tu4(const double *cc, const double *cf)
+{
+    cudaError_t e = set_coeff_here(cc, cf);
+    if (e == cudaSuccess) e = attr_node_impl<true, true, 1>();
+    return e != cudaSuccess ? e : attr_node_impl<true, true, 2>();
+}
+#endif
+
+#if TU_OWNS(0)
+// full-Jacobian kernels live in the other units, residual-only ones here
+template <bool S, bool F, int T>
+static void launch_node(const bool bm, const NodeLaunch &a)
+{
+    if (!F) launch_node_impl<S, false, T>(bm, a);
+    else if (!S && T == 0) awe_launch_tu1(T, bm, a);
+    else if (!S) awe_launch_tu2(T, bm, a);
+    else if (T == 0) awe_launch_tu3(T, bm, a);
+    else awe_launch_tu4(T, bm, a);
+}
+#endif
+
+#if defined(AWE_WITH_FUSED) && TU_OWNS(0)
 // --------------------------------------------------------------------------- fused persistent kernel
 // EXPERIMENT (compiled with -DAWE_WITH_FUSED, selected with AWEGPU_FUSED=1): measured 1.5x SLOWER than the
 // per-stage kernels on B200 (profiles/r01_ncu_fused_variant_B1024.txt: 36 % of the stall samples are
@@ -802,6 +920,7 @@ awegpu_fused_kernel(const DevProblem pr, const Scratch sc, const int B, const in
 
 #endif  /* AWE_WITH_FUSED */
 
+#if TU_OWNS(0)
 static constexpr size_t gather_smem_bytes() { return sizeof(double) * TILE * SLAB_STRIDE; }
 
 // =========================================================================== host side / C ABI
@@ -1058,8 +1177,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         }
         seen = now;
     }
-    CK(cudaMemcpyToSymbol(c_coeff_coll, p->coeff_coll, sizeof(double) * (dd + 1) * (dd + 1)));
-    CK(cudaMemcpyToSymbol(c_coeff_cont, p->coeff_cont, sizeof(double) * (dd + 1)));
+    CK(set_coeff_here(p->coeff_coll, p->coeff_cont));         // this unit's copy (gather kernel, residual-only kernels)
     h->colind.assign(p->colind, p->colind + p->n_v + 1);
     h->row.assign(p->row, p->row + p->nnz);
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -1068,17 +1186,16 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     CK(cudaEventCreate(&h->ev_k0));
     CK(cudaEventCreate(&h->ev_k1));
 #define SET_SMEM(kern, bytes) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)))
-#define SET_NODE1(S_, F_, T_)                                                             \
-    SET_SMEM((awegpu_node_kernel<S_, F_, T_, false>), (node_smem_bytes<S_, F_>()));       \
-    SET_SMEM((awegpu_node_kernel<S_, F_, T_, ((T_) == 0) && AWE_BATCH_MINOR>), (node_smem_bytes<S_, F_>()))
-#define SET_NODE(S_, F_) \
-    SET_NODE1(S_, F_, 0);  \
-    SET_NODE1(S_, F_, 1);  \
-    SET_NODE1(S_, F_, 2)
-    SET_NODE(false, true);
-    SET_NODE(false, false);
-    SET_NODE(true, true);
-    SET_NODE(true, false);
+    CK(awe_init_tu1(p->coeff_coll, p->coeff_cont));
+    CK(awe_init_tu2(p->coeff_coll, p->coeff_cont));
+    CK(awe_init_tu3(p->coeff_coll, p->coeff_cont));
+    CK(awe_init_tu4(p->coeff_coll, p->coeff_cont));
+    CK((attr_node_impl<false, false, 0>()));
+    CK((attr_node_impl<false, false, 1>()));
+    CK((attr_node_impl<false, false, 2>()));
+    CK((attr_node_impl<true, false, 0>()));
+    CK((attr_node_impl<true, false, 1>()));
+    CK((attr_node_impl<true, false, 2>()));
     SET_SMEM(awegpu_gather_kernel<false>, gather_smem_bytes());
 #ifdef AWE_WITH_FUSED
     {
@@ -1101,8 +1218,6 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     h->fused = 0;
 #endif
     SET_SMEM(awegpu_gather_kernel<AWE_BATCH_MINOR != 0>, gather_smem_bytes());
-#undef SET_NODE
-#undef SET_NODE1
 #undef SET_SMEM
     {
         // chunk of instances whose node-input records stay L2-resident while the program groups
@@ -1216,10 +1331,12 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
 #define LAUNCH_STAGE(S_, F, T_, M, n_, st_)                                                                       \
     do {                                                                                                          \
         if (node_groups<S_, F, T_>() > 0) {                                                                       \
-            /* the output layout only matters to the output stage: pre-stages have one instantiation */       \
-            awegpu_node_kernel<S_, F, T_, ((T_) == 0) && (M) && AWE_BATCH_MINOR><<<dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>()), \
-                                               NODE_THREADS, node_smem_bytes<S_, F>(), st_>>>(dp, h->sc, B, b_base, n_, p_sh,          \
-                                                                                             ((T_) == 0 ? h->interleave : h->interleave_pre) * (((S_) ? dp.n_k : dp.n_k * N_D) + NODE_WARPS - 1) / NODE_WARPS, G, jv); \
+            NodeLaunch a_;                                                                                        \
+            a_.grid = dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>());                       \
+            a_.st = st_, a_.dp = dp, a_.sc = h->sc, a_.B = B, a_.b_base = b_base, a_.n_items = n_, a_.p_sh = p_sh; \
+            a_.ilv = ((T_) == 0 ? h->interleave : h->interleave_pre) * (((S_) ? dp.n_k : dp.n_k * N_D) + NODE_WARPS - 1) / NODE_WARPS; \
+            a_.G = G, a_.Jv = jv;                                                                                 \
+            launch_node<S_, F, T_>(M, a_);                                                                        \
             h->launches += 1;                                                                                     \
         }                                                                                                         \
     } while (0)
@@ -1492,3 +1609,5 @@ extern "C" int jac_awegpu_g_work(long long *sz_arg, long long *sz_res, long long
     if (sz_w) *sz_w = 0;
     return 0;
 }
+
+#endif  /* TU_OWNS(0) */

@@ -40,19 +40,20 @@ def main(argv):
         stats = CG.NodeCode(ocp).write(g)
         out = os.path.join(pbuild.LIBDIR, 'var', 'libawegpu_%s.%s.so' % (SPEC, name))
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        cmd = [pbuild.find_nvcc()] + pbuild.NVCC_FLAGS + flags + ['-I', g, '-I', os.path.join(ROOT, 'include'), '-I', pbuild.CSRC,
-                                                                   '-o', out, os.path.join(pbuild.CSRC, 'awegpu_kernels.cu')]
-        jobs.append((name, cmd, g, stats))
+        jobs.append((name, flags, g, out))
         print(name, {k: stats[k]['hot_slots'] for k in ('k_coll', 'k_shoot')}, flush=True)
 
     def run(job):
-        name, cmd, g, _ = job
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        open(os.path.join(g, 'nvcc.log'), 'w').write(res.stdout + res.stderr)
-        regs = [l for l in (res.stdout + res.stderr).splitlines() if 'Used' in l]
-        return name, res.returncode, max((int(l.split('Used')[1].split()[0]) for l in regs), default=-1), (res.stderr[-2000:] if res.returncode else '')
+        name, flags, g, out = job
+        try:
+            pbuild.compile_cuda(SPEC, force=True, extra_flags=tuple(flags), out=out, gen=g)
+        except RuntimeError as e:
+            return name, 1, -1, str(e)[-2000:]
+        log = open(os.path.join(g, 'nvcc.log')).read()
+        regs = [l for l in log.splitlines() if 'Used' in l]
+        return name, 0, max((int(l.split('Used')[1].split()[0]) for l in regs), default=-1), ''
 
-    with ThreadPoolExecutor(4) as ex:
+    with ThreadPoolExecutor(2) as ex:
         for name, rc, regs, err in ex.map(run, jobs):
             print('%s: rc=%d max regs %d %s' % (name, rc, regs, err), flush=True)
 
