@@ -303,12 +303,23 @@ __device__ __forceinline__ void flush_coop(const double *stg_cta, const int2 *ta
     if (AWE_POOL == 0) asm volatile("cp.async.wait_all;" ::: "memory");
     quad_sync(bar_id);
     const int n_ent = tab[COOP_PER - 1].y;        // entries of this chunk (the last table slot carries the count)
+#if !defined(AWE_FLUSH_UNROLLED)
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int e = 0; e < COOP_E; ++e) {
         if (e * 32 >= n_ent) break;
         // one base pointer, 32-bit element offsets (a tile spans < 2^31 elements of g / jac values)
         const int2 t = tab[e * 32 + lane];
+#ifdef AWE_EXP_CONTIG_DST
+        /* ablation (wrong results): the 32 entries of a store instruction are made contiguous, to see what
+           perfectly contiguous destination runs would be worth */
+        const int code0 = __shfl_sync(0xffffffffu, t.x, 0);
+        const int code = (t.x >= 0 && code0 >= 0) ? code0 + lane : t.x;
+#else
         const int code = t.x;
+#endif
         const bool is_j = code >= 0;
         double *base = is_j ? j_tile : g_tile;
         const int ld = is_j ? nnz : n_g;
@@ -318,7 +329,11 @@ __device__ __forceinline__ void flush_coop(const double *stg_cta, const int2 *ta
         if (code != -1 && base != nullptr) {
             if (n_valid == TILE) {
                 // full tile: TILE / N_D instances per warp, reads batched ahead of the stores
+#if defined(AWE_FLUSH_COMPACT) && AWE_FLUSH_COMPACT >= 2
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
                 for (int h = 0; h < TILE / N_D; h += 4) {
                     double v[4];
 #pragma unroll
