@@ -1495,7 +1495,10 @@ extern "C" int awegpu_eval_batch_host(awegpu_handle_t *h, int32_t B, const doubl
         if (!h->stream_out) CK(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
         const bool shared = (flags & AWEGPU_P_SHARED) != 0;
         if (shared) CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        const int chunk = 512;
+        // instances per copy chunk (AWEGPU_COPY_CHUNK overrides): large enough for full-rate PCIe transfers, small
+        // enough to keep the fill and drain of the three-stage pipeline short
+        static const int chunk_env = getenv("AWEGPU_COPY_CHUNK") ? atoi(getenv("AWEGPU_COPY_CHUNK")) : 0;
+        const int chunk = chunk_env > 0 ? chunk_env : 512;
         const int n_chunks = (B + chunk - 1) / chunk;
         while ((int)h->ev_pool.size() < 2 * n_chunks) {
             cudaEvent_t e;
