@@ -179,6 +179,9 @@ def main():
         raise SystemExit('bench.py: no CUDA device visible — this benchmark has no CPU fallback')
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', 'TRACE') and not os.environ.get('NCCL_DEBUG_FILE'):
+            os.environ['NCCL_DEBUG_FILE'] = '/tmp/awegpu_bench_nccl.%h.%p.log'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     ev = Evaluator(SPEC, n_k=N_K, device=local_rank)
     ocp = ev.ocp
