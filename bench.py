@@ -113,7 +113,7 @@ def cpu_leg(ocp, n_threads, budget_s, W, p):
     return done * ocp.n_k * ocp.d / dt, dt, done, n_threads
 
 
-def run_reference(args):
+def run_reference(args, json_out):
     """--impl reference: the CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -146,10 +146,20 @@ def run_reference(args):
                                  'not installable on this box'},
         'e2e': {'value': value, 'unit': 'node-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: keep a private handle for it and send everything else that libraries
+    write to file descriptor 1 (NCCL's version banner, for instance) to stderr."""
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    return out
 
 
 def main():
+    json_out = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
@@ -164,7 +174,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
-        return run_reference(args)
+        return run_reference(args, json_out)
 
     import numpy as np
     import torch
@@ -179,9 +189,6 @@ def main():
         raise SystemExit('bench.py: no CUDA device visible — this benchmark has no CPU fallback')
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # rank 0 prints exactly one line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'INFO', 'TRACE') and not os.environ.get('NCCL_DEBUG_FILE'):
-            os.environ['NCCL_DEBUG_FILE'] = '/tmp/awegpu_bench_nccl.%h.%p.log'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     ev = Evaluator(SPEC, n_k=N_K, device=local_rank)
     ocp = ev.ocp
@@ -319,7 +326,7 @@ def main():
                              'sample': '256-instance blocks of the same workload repeated for %.1f s (%d instances)'
                                        % (cpu_dt, cpu_n)},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
