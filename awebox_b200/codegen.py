@@ -45,9 +45,11 @@ PF_AHEAD = 150       # operations between the asynchronous copy of an input and 
 HINT_AHEAD = 0       # > 0: L2 prefetch hint this many operations before the load of a record / export input
 GROUP_OPS = 1400     # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
 MAX_EXPORTS = 64     # intermediate values exported per stage (scaled up for large models, see NodeCode.plan)
+MAX_EXPORTS_SHOOT = 0 # > 0: the same for the shooting-node function (0: as MAX_EXPORTS)
 EXPORT_MIN_GAIN = 40
 EXPORT_LOAD_COST = 4
-MAX_STAGES = 3       # main programs + two levels of export pre-stages
+MAX_STAGES = 3       # main programs + two levels of export pre-stages (at most N_STAGE_FILES)
+N_STAGE_FILES = 3    # stage files the kernels include (k_*_s0..s2.inc); unused stages are empty
 BATCH_MINOR_MAX_OPS = 30000   # largest model (executed FP64 operations per coll + shoot node) that also gets the batch-minor kernels
 
 
@@ -478,7 +480,10 @@ class NodeCode(object):
             stages, ex_index, ex_nodes = [], {}, []
             cur = list(exprs)
             for level in range(MAX_STAGES):
-                exports, groups = self.plan(cur, max_exports=0 if level == MAX_STAGES - 1 else None)
+                cap = None
+                if name.startswith('k_shoot') and MAX_EXPORTS_SHOOT > 0 and len(cur) and len([n for n in S.topo(cur) if SCH.is_op(n)]) <= 8000:
+                    cap = MAX_EXPORTS_SHOOT
+                exports, groups = self.plan(cur, max_exports=0 if level == MAX_STAGES - 1 else cap)
                 new = [n for n in exports if n.idx not in ex_index]
                 for n in new:
                     ex_index[n.idx] = len(ex_nodes)
@@ -493,7 +498,7 @@ class NodeCode(object):
                 leaf_names[v.idx] = v.name
             sstats = []
             first_export = 0
-            for level in range(MAX_STAGES):
+            for level in range(N_STAGE_FILES):
                 text, gstats = '', []
                 if level < len(stages):
                     outs, groups = stages[level]
@@ -531,7 +536,7 @@ class NodeCode(object):
             up = name.upper()
             kdefs += '#define AWE_%s_EXPORTS %d\n#define AWE_%s_HOT %d\n#define AWE_%s_OPS %d\n' % (
                 up, len(ex_nodes), up, hot, up, stats[name]['ops_total'])
-            for level in range(MAX_STAGES):
+            for level in range(N_STAGE_FILES):
                 kdefs += '#define AWE_%s_S%d_GROUPS %d\n' % (up, level, len(sstats[level]))
             kdefs += '#define AWE_%s_NCHUNKS %d\n' % (up, len(chunks0[0]))
             kdefs += '#define AWE_%s_MAXQ %d\n' % (up, max((b - a + CHUNK - 1) // CHUNK for a, b in stages[0][1]))
