@@ -3,23 +3,25 @@
 // scheduled and register-allocated k_*.inc files (awebox_b200/codegen.py, awebox_b200/schedule.py);
 // everything else here is hand-written.
 //
-// Pipeline per chunk of OCP instances, all on one stream:
+// Pipeline per call, all on one stream:
 //   1. awegpu_gather_kernel   grid (tiles, n_k): stages the interval slab of 32 instances in shared
 //        memory and writes the node-input records lane-contiguously (record entry i of the 32
 //        instances of a tile = one 256-byte line), contracts the collocation polynomial
-//        xdot_kj = (sum_r C[r,j] X_r) / (h t_f), writes the continuity / periodicity rows of g and the
-//        constant Jacobian entries.
-//   2. awegpu_node_kernel<coll>   grid (ceil(tiles*n_k*d / 4), groups): warp = one collocation node of a
-//        tile, lane = instance, blockIdx.y = program group.
-//   3. awegpu_node_kernel<shoot>  the same for the shooting nodes (equality subset + path inequalities).
+//        xdot_kj = (sum_r C[r,j] X_r) / (h t_f), writes the continuity / periodicity / affine rows of g and
+//        the constant Jacobian entries the cooperative flush does not carry.
+//   2. awegpu_node_kernel<coll | shoot, stage 2, 1>   pre-stages: exported intermediates of every node.
+//   3. awegpu_node_kernel<shoot, stage 0>, awegpu_node_kernel<coll, stage 0>   the node outputs.
+//      grid (ceil(items / 4), groups): warp = one node of a tile, lane = instance, blockIdx.y = program group
+//      (CTAs are re-ordered so that the groups of one tile run close in time).
 // A program group is a straight-line FP64 program of <= ~1400 operations that produces a consecutive
 // range of the node's outputs and recomputes what it shares with the other groups.  That keeps every
-// program below the 32 KB instruction cache of the SM (the monolithic ~9000-operation program was
-// instruction-fetch bound: one 256-byte fetch from L2 per 16 instructions, ~280 cycles each, see
-// profiles/) and its working set at ~50 registers + a few dozen scratch slots, so that 12-16 warps are
-// resident per SM.  Results are staged AWE_CHUNK outputs x 32 instances at a time in shared memory and
-// written instance-major with lane = output, so that neighbours in the CCS value array leave the SM in
-// one store instruction.
+// program near the 32 KB instruction cache of the SM (the monolithic ~9000-operation program was
+// instruction-fetch bound) and its working set at 48 FP64 registers + a few dozen shared-memory spill slots:
+// 168 registers, ~70 KB of shared memory per 4-warp CTA, three CTAs per SM.  Results are staged AWE_CHUNK
+// outputs x 32 instances per warp in shared memory; the four warps of a collocation CTA are the four nodes of
+// one interval and flush their chunks together, destination-sorted (flush_coop), so that neighbours in the CCS
+// value array leave the SM in one store instruction.  Measured cost structure and the experiments that did not
+// pay: DESIGN.md section 10.
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
