@@ -238,3 +238,33 @@ def test_full_size_properties():
     r0 = ocp.row_cont[k]
     want = dW[:, ocp.v_x[k + 1]:ocp.v_x[k + 1] + ocp.n_x] - dW[:, ocp.v_cx[k][ocp.d - 1]:ocp.v_cx[k][ocp.d - 1] + ocp.n_x]
     assert float((dG[:, r0:r0 + ocp.n_x] - want).abs().max()) < 1e-14
+
+
+@pytest.mark.parametrize('name,n_k,B', [('dual_kites', 20, 4096), ('mpc_3dof', 10, 8192)])
+def test_other_baseline_configs_at_full_batch(name, n_k, B):
+    """BASELINE configs[2] (dual kites, batch 4096) and configs[4] (8192 MPC scenarios): every output slot is
+    written, a sample of instances agrees with the checker, and instances do not influence one another."""
+    import torch
+    ev = evaluator(name, n_k)
+    ocp = ev.ocp
+    W = synthetic.batch(ocp, B, seed=31)
+    if ocp.needs_full_p:
+        P = synthetic.scenario_params(ocp, W, seed=32)
+        flags = cabi.AWEGPU_P_FULL
+    else:
+        P = ocp.default_p()
+        flags = cabi.AWEGPU_P_SHARED
+    dW, dP = torch.from_numpy(W).cuda(), torch.from_numpy(P).cuda()
+    dG = torch.full((B, ocp.n_g), float('nan'), dtype=torch.float64, device='cuda')
+    dJ = torch.full((B, ocp.nnz), float('nan'), dtype=torch.float64, device='cuda')
+    ev.eval_device(dW, dP, dG, dJ)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(dG).all()) and bool(torch.isfinite(dJ).all())
+    idx = np.arange(0, B, 509)
+    G0, J0 = get_oracle(name, n_k).eval(W[idx], P if P.ndim == 1 else P[idx], flags=flags)
+    assert_parity(ocp, dG[idx].cpu().numpy(), dJ[idx].cpu().numpy(), G0, J0)
+    perm = torch.randperm(B, device='cuda', generator=torch.Generator(device='cuda').manual_seed(1))
+    dG2, dJ2 = torch.empty_like(dG), torch.empty_like(dJ)
+    ev.eval_device(dW[perm].contiguous(), dP if dP.ndim == 1 else dP[perm].contiguous(), dG2, dJ2)
+    torch.cuda.synchronize()
+    assert torch.equal(dG2, dG[perm]) and torch.equal(dJ2, dJ[perm])
