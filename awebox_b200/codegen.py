@@ -542,6 +542,11 @@ class NodeCode(object):
             kdefs += '#define AWE_%s_MAXQ %d\n' % (up, max((b - a + CHUNK - 1) // CHUNK for a, b in stages[0][1]))
             kdefs += 'static const int awe_%s_chunk_first[] = {%s};\n' % (name, ', '.join(map(str, chunks0[0])))
             kdefs += 'static const int awe_%s_chunk_cnt[] = {%s};\n' % (name, ', '.join(map(str, chunks0[1])))
+            gq, acc = [0], 0
+            for a_, b_ in stages[0][1]:
+                acc += (b_ - a_ + CHUNK - 1) // CHUNK
+                gq.append(acc)
+            kdefs += '#define AWE_%s_GROUP_Q0 {%s}\n' % (up, ', '.join(map(str, gq)))
             stats[name]['n_chunks'] = len(chunks0[0])
         kvals = [float.fromhex(h) for h, _ in sorted(self._ktab.items(), key=lambda kv: kv[1])] or [0.0]
         kdefs += '#define AWE_N_KCONST %d\n#define AWE_KCONST_INIT {%s}\n' % (len(kvals), ', '.join(_fmt(v) for v in kvals))

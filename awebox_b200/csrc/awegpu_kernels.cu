@@ -44,6 +44,10 @@
 #define AWE_TU -1
 #endif
 #define TU_OWNS(n) (AWE_TU == -1 || AWE_TU == (n))
+// warp-specialised output stage of the collocation nodes (awegpu_coll_ws_kernel): on unless -DAWE_NO_WS
+#if !defined(AWE_NO_WS) && !defined(AWE_WS)
+#define AWE_WS 1
+#endif
 #define AWE_N_TU 5      /* 0 host, 1 coll full stage 0, 2 coll full stages 1-2, 3 shoot full stage 0, 4 shoot full stages 1-2 */
 
 #define TILE 32
@@ -700,6 +704,140 @@ __host__ __device__ static constexpr int node_groups()
                                        : STAGE == 1 ? AWE_K_COLL_RES_S1_GROUPS : AWE_K_COLL_RES_S2_GROUPS));
 }
 
+#if defined(AWE_WS) && TU_OWNS(1)
+// --------------------------------------------------------------------------- warp-specialised output stage
+// Collocation nodes, full Jacobian, instance-major layout (AWEGPU_WS=0 falls back to awegpu_node_kernel<coll, 0>).
+// Measured on B200 (AP2, B=4096): 1.38 ms against 1.44 ms for the kernel whose computing warps flush themselves.
+// CTA = 8 warps: warps 0-3 run the node programs of the four collocation nodes of one interval and only STAGE their
+// results; warps 4-7 drain the staging area to global memory (the cooperative flush).  Two staging buffers, named
+// barriers full[b] / empty[b] (256 participants: 128 arrive, 128 wait), register file split with setmaxnreg:
+// the store warps hand their registers to the computing ones.
+__device__ const int awe_k_coll_group_q0[] = AWE_K_COLL_GROUP_Q0;
+#define WS_THREADS (2 * NODE_THREADS)
+#define WS_REGS_COMPUTE 208
+#define WS_REGS_STORE 48
+#define WS_BAR_FULL(b) (1 + (b))
+#define WS_BAR_EMPTY(b) (3 + (b))
+#define WS_BAR_STORE 5
+__host__ __device__ static constexpr size_t ws_smem_bytes()
+{
+    return sizeof(double) * ((size_t)AWE_K_COLL_HOT * NODE_THREADS + 2 * NODE_WARPS * STG_DOUBLES + COOP_NCONST * STG_STRIDE) +
+           sizeof(int2) * AWE_K_COLL_MAXQ * COOP_PER;
+}
+
+__device__ __forceinline__ void ws_bar_sync(const int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(WS_THREADS) : "memory"); }
+__device__ __forceinline__ void ws_bar_arrive(const int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(WS_THREADS) : "memory"); }
+
+#undef GROUP_INIT
+#undef FLUSH
+#define GROUP_INIT(q0, nq, first) (void)0
+// a chunk is staged: hand the buffer to the store warps, continue in the other one once it has been drained
+#define FLUSH(q, first, cnt, q_next, first_next)                                              \
+    do {                                                                                      \
+        ws_bar_arrive(WS_BAR_FULL(buf));                                                      \
+        buf ^= 1;                                                                             \
+        stg = stg_base + buf * (NODE_WARPS * STG_DOUBLES);                                    \
+        if ((q_next) >= 0 && ++n_staged >= 2) ws_bar_sync(WS_BAR_EMPTY(buf));                 \
+    } while (0)
+
+__global__ void __launch_bounds__(WS_THREADS, 2)
+awegpu_coll_ws_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const int n_items, const int ilv,
+                      double *__restrict__ G, double *__restrict__ Jv)
+{
+    constexpr bool SHOOT = false, FULL = true, BATCH_MINOR = false, COOP = true, EX_RW = false;
+    constexpr int HOT = AWE_K_COLL_HOT;
+    constexpr int NEX = AWE_K_COLL_EXPORTS;
+    extern __shared__ double smem[];
+    const int role = threadIdx.x / NODE_THREADS;                 // 0: compute, 1: store
+    const int tid = threadIdx.x - role * NODE_THREADS, lane = tid & 31, wid = tid >> 5;
+    int cta_item, group;
+    {
+        const int n_groups = gridDim.y, n_cta_items = gridDim.x;
+        const int lin = blockIdx.y * n_cta_items + blockIdx.x;
+        if (ilv > 0) {
+            const int per_block = ilv * n_groups;
+            const int blk = lin / per_block, rem = lin - blk * per_block;
+            const int blk_items = min(ilv, n_cta_items - blk * ilv);
+            group = rem / blk_items, cta_item = blk * ilv + rem % blk_items;
+        } else
+            group = blockIdx.y, cta_item = blockIdx.x;
+    }
+    const int item = cta_item * NODE_WARPS + wid;                // collocation: whole CTAs are valid or not
+    if (cta_item * NODE_WARPS >= n_items) return;
+    const int j = item % N_D, k = (item / N_D) % pr.n_k, tile = item / (N_D * pr.n_k);
+    const int j1 = j + 1;
+    const int b0 = b_base + tile * TILE;
+    const int n_valid = min(TILE, B - b0);
+    const int n_g = pr.n_g;
+    const int nnz = (int)pr.nnz;
+    double *stg_cta = smem + (size_t)HOT * NODE_THREADS;          // two buffers of NODE_WARPS * STG_DOUBLES
+    double *cst_rows = stg_cta + 2 * NODE_WARPS * STG_DOUBLES;
+    int2 *tab_smem = reinterpret_cast<int2 *>(cst_rows + COOP_NCONST * STG_STRIDE);
+    double *g_tile = G + (size_t)b0 * n_g;
+    double *j_tile = Jv + (size_t)b0 * (size_t)nnz;
+    const int q0 = awe_k_coll_group_q0[group], nq = awe_k_coll_group_q0[group + 1] - q0;
+    if (role == 1) {
+        // ------------------------------------------------------------------ store warps
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_STORE));
+        const int2 *coop_tab = pr.coop_tab + ((size_t)k * AWE_K_COLL_NCHUNKS + q0) * COOP_PER;
+        for (int e = tid; e < nq * COOP_PER; e += NODE_THREADS) tab_smem[e] = __ldg(coop_tab + e);
+        for (int e = tid; e < COOP_NCONST * STG_STRIDE; e += NODE_THREADS) cst_rows[e] = __ldg(pr.coop_const + e / STG_STRIDE);
+        asm volatile("bar.sync %0, %1;" ::"n"(WS_BAR_STORE), "n"(NODE_THREADS) : "memory");
+        int buf = 0;
+#pragma unroll 1
+        for (int q = 0; q < nq; ++q) {
+            ws_bar_sync(WS_BAR_FULL(buf));
+            const int2 *tab = tab_smem + q * COOP_PER;
+            // staged rows of this buffer, then the constant rows: row index COOP_STAGED + c -> cst_rows + c
+            const double *rows = stg_cta + buf * (NODE_WARPS * STG_DOUBLES);
+            const int n_ent = tab[COOP_PER - 1].y;
+#pragma unroll 1
+            for (int e = 0; e * 32 < n_ent; ++e) {
+                const int2 t = tab[e * 32 + lane];
+                const int code = t.x;
+                const bool is_j = code >= 0;
+                double *base = is_j ? j_tile : g_tile;
+                const int ld = is_j ? nnz : n_g;
+                const int step = ld * N_D;
+                int off = (is_j ? code : -2 - code) + wid * ld;
+                const double *s = (t.y < COOP_STAGED ? rows + t.y * STG_STRIDE : cst_rows + (t.y - COOP_STAGED) * STG_STRIDE) + wid;
+                if (code != -1) {
+#pragma unroll 1
+                    for (int i = wid; i < n_valid; i += N_D) {
+                        ST_OUT(base + off, *s);
+                        off += step;
+                        s += N_D;
+                    }
+                }
+            }
+            if (q + 2 < nq) ws_bar_arrive(WS_BAR_EMPTY(buf));       // somebody will wait for this buffer again
+            buf ^= 1;
+        }
+        return;
+    }
+    // ---------------------------------------------------------------------- computing warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_COMPUTE));
+    const int b = b0 + lane;
+    const bool valid = b < B;
+    double *stg_base = stg_cta + wid * STG_DOUBLES;
+    double *stg = stg_base;
+    int buf = 0, n_staged = 0;
+    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
+    const double *w_rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32 + lane;
+    const double *w_own = w_rec + OFF_CX(j) * 32;
+    const double *w_z = w_own + N_X * 32;
+    const double *w_xd = sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
+    const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
+    double *w_ex = sc.exc + (size_t)item * (NEX > 0 ? NEX : 1) * 32 + lane;
+    const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
+    const double itf_nk = itf * (double)pr.n_k;
+    (void)itf_nk, (void)w_ex, (void)valid, (void)scr_addr, (void)w_z, (void)w_pt, (void)j1, (void)n_staged;
+    switch (group) {
+#include "k_coll_s0.inc"
+    }
+}
+#endif  /* AWE_WS */
+
 // --------------------------------------------------------------------------- launch plumbing (per translation unit)
 struct NodeLaunch {
     dim3 grid;
@@ -752,10 +890,26 @@ DECL_TU(4)
 #undef DECL_TU
 
 #if TU_OWNS(1)
-void awe_launch_tu1(int, bool bm, const NodeLaunch &a) { launch_node_impl<false, true, 0>(bm, a); }
+void awe_launch_tu1(int, bool bm, const NodeLaunch &a)
+{
+#ifdef AWE_WS
+    // pays for the large node functions (measured: AP2 -2.4 %, dual kites -1.7 % per step); the small 3-DOF model
+    // is faster with three self-flushing CTAs per SM (+4.6 % with this kernel)
+    static const int use_ws = getenv("AWEGPU_WS") ? atoi(getenv("AWEGPU_WS")) : (AWE_K_COLL_OPS > 8000);
+    if (use_ws && !bm && a.Jv != nullptr && N_D == NODE_WARPS) {
+        awegpu_coll_ws_kernel<<<a.grid, WS_THREADS, ws_smem_bytes(), a.st>>>(a.dp, a.sc, a.B, a.b_base, a.n_items, a.ilv, a.G, a.Jv);
+        return;
+    }
+#endif
+    launch_node_impl<false, true, 0>(bm, a);
+}
 cudaError_t awe_init_tu1(const double *cc, const double *cf)
 {
     cudaError_t e = set_coeff_here(cc, cf);
+#ifdef AWE_WS
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(awegpu_coll_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem_bytes());
+#endif
     return e != cudaSuccess ? e : attr_node_impl<false, true, 0>();
 }
 #endif
