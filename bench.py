@@ -270,8 +270,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        # dominant kernel: the output stage of the collocation-node programs (awegpu_node_kernel<coll, full,
-        # stage 0>), one launch per step.  Algorithmic bytes of that launch: every collocation node reads
+        # dominant kernel: the output stage of the collocation-node programs (awegpu_coll_ws_kernel), one launch
+        # per step.  Algorithmic bytes of that launch: every collocation node reads
         # its input column once ([x; xdot; z] per node, [u; theta; phi] per interval) and writes its
         # residual rows and Jacobian entries once.
         k_ms = float(np.median(kernel_ms))
@@ -309,7 +309,7 @@ def main():
             'gpu_launches': int(gpu_launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
-                         'kernel': 'awegpu_node_kernel<coll, full, stage 0> (output stage of the collocation-node programs)',
+                         'kernel': 'awegpu_coll_ws_kernel (output stage of the collocation-node programs: computing warps + store warps)',
                          'kernel_ms': k_ms, 'kernel_share_of_step': k_ms / s_ms,
                          'algorithmic_bytes_per_launch': int(alg_bytes),
                          'algorithmic_bytes_per_node': per_inst / (ocp.n_k * ocp.d),

@@ -1,8 +1,3 @@
-timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1
-timeout 120 python scripts/variant_check.py 4096 ampyx_ap2 40 2>&1 | tail -1
-AWEGPU_WS=0 timeout 120 python scripts/variant_check.py 4096 ampyx_ap2 40 2>&1 | tail -1
-timeout 120 python scripts/variant_check.py 4096 dual_kites 20 2>&1 | tail -1
-AWEGPU_WS=0 timeout 120 python scripts/variant_check.py 4096 dual_kites 20 2>&1 | tail -1
-timeout 120 python scripts/variant_check.py 8192 mpc_3dof 10 2>&1 | tail -1
-AWEGPU_WS=0 timeout 120 python scripts/variant_check.py 8192 mpc_3dof 10 2>&1 | tail -1
+python scripts/profile_step.py 4096 3 > gpurun_out/plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:awegpu_coll_ws_kernel -s 2 -c 1 -o gpurun_out/prof_r1_s0_B4096 python scripts/profile_step.py 4096 3 > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
