@@ -149,6 +149,31 @@ def run_reference(args, json_out):
     print(json.dumps(line), file=json_out, flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """run this rank (and first-touch its pinned host buffers) on the NUMA node its GPU is attached to: with one
+    rank per GPU the host<->device copies of the e2e leg otherwise share one socket's memory controllers.
+    Returns (previous affinity, node) or (None, None) when the topology cannot be read."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bdf).read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        before = os.sched_getaffinity(0)
+        cpus &= before
+        if not cpus:
+            return None, None
+        os.sched_setaffinity(0, cpus)
+        return before, node
+    except Exception:
+        return None, None
+
+
 def claim_stdout():
     """stdout carries exactly one JSON line: keep a private handle for it and send everything else that libraries
     write to file descriptor 1 (NCCL's version banner, for instance) to stderr."""
@@ -188,6 +213,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device visible — this benchmark has no CPU fallback')
     torch.cuda.set_device(local_rank)
+    affinity_before, numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else (None, None)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     ev = Evaluator(SPEC, n_k=N_K, device=local_rank)
@@ -290,6 +316,8 @@ def main():
             with open(tpath) as f:
                 traffic = json.load(f).get('dram_bytes_per_launch')
         step_bytes = B * ocp.algorithmic_bytes()
+        if affinity_before is not None:
+            os.sched_setaffinity(0, affinity_before)          # the CPU leg uses every host core again
         cpu_v, cpu_dt, cpu_n, cpu_thr = cpu_leg(ocp, os.cpu_count(), args.cpu_seconds, W, p)
         line = {
             'metric': 'collocation-node g+Jacobian evals/s', 'value': value, 'unit': 'node-evals/s',
@@ -305,7 +333,8 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'node-evals/s',
                     'h2d_bytes_per_step': int(8 * (W.size + p.size)) * world,
                     'd2h_bytes_per_step': int(8 * B * (ocp.n_g + ocp.nnz)) * world,
-                    'api': 'awegpu_eval_batch_host (pinned host buffers)'},
+                    'api': 'awegpu_eval_batch_host (pinned host buffers)', 'timing': 'wall clock around the synchronous calls, max over ranks',
+                    'numa_node_of_rank0': numa_node},
             'gpu_launches': int(gpu_launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
