@@ -11,19 +11,29 @@ import torch.multiprocessing as mp
 from conftest import ROOT
 
 
-def _worker(rank, world, port, B, out):
+def _inputs(spec, n_k, B):
+    """-> (ocp, W [B, n_v], P, flags): shared parameter vector for the periodic OCP, per-instance scenario
+    parameters (p.ref, wind speed) for the MPC trial."""
+    from awebox_b200 import synthetic, cabi
+    from conftest import get_ocp
+    ocp = get_ocp(spec, n_k)
+    W = synthetic.batch(ocp, B, seed=9)
+    if ocp.needs_full_p:
+        return ocp, W, synthetic.scenario_params(ocp, W, seed=10), cabi.AWEGPU_P_FULL
+    return ocp, W, ocp.default_p(), cabi.AWEGPU_P_SHARED
+
+
+def _worker(rank, world, port, B, out, spec='ampyx_ap2', n_k=4):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from awebox_b200.parallel import shard_range, gather_results, checksum
-    from awebox_b200 import synthetic, cabi
-    from conftest import get_ocp, get_oracle
-    ocp = get_ocp('ampyx_ap2', 4)
-    W = synthetic.batch(ocp, B, seed=9)
+    from conftest import get_oracle
+    ocp, W, P, flags = _inputs(spec, n_k, B)
     lo, hi = shard_range(B, rank, world)
-    G, Jv = get_oracle('ampyx_ap2', 4).eval(W[lo:hi], ocp.default_p(), flags=cabi.AWEGPU_P_SHARED)
+    G, Jv = get_oracle(spec, n_k).eval(W[lo:hi], P if P.ndim == 1 else P[lo:hi], flags=flags)
     Gall = gather_results(torch.from_numpy(G), B)
     Jall = gather_results(torch.from_numpy(Jv), B)
     cs = checksum(torch.from_numpy(G))
@@ -33,15 +43,13 @@ def _worker(rank, world, port, B, out):
     dist.destroy_process_group()
 
 
-def _run(B, tmp_path):
-    out = str(tmp_path / ('gather_%d.npz' % B))
+def _run(B, tmp_path, spec='ampyx_ap2', n_k=4):
+    out = str(tmp_path / ('gather_%s_%d.npz' % (spec, B)))
     port = 29500 + (os.getpid() + B) % 2000
-    mp.spawn(_worker, args=(2, port, B, out), nprocs=2, join=True)
-    from awebox_b200 import synthetic, cabi
-    from conftest import get_ocp, get_oracle
-    ocp = get_ocp('ampyx_ap2', 4)
-    W = synthetic.batch(ocp, B, seed=9)
-    G0, J0 = get_oracle('ampyx_ap2', 4).eval(W, ocp.default_p(), flags=cabi.AWEGPU_P_SHARED)
+    mp.spawn(_worker, args=(2, port, B, out, spec, n_k), nprocs=2, join=True)
+    from conftest import get_oracle
+    ocp, W, P, flags = _inputs(spec, n_k, B)
+    G0, J0 = get_oracle(spec, n_k).eval(W, P, flags=flags)
     r = np.load(out)
     assert np.array_equal(r['G'], G0) and np.array_equal(r['J'], J0)
     assert abs(float(r['cs']) - G0.sum()) <= 1e-9 * np.abs(G0).sum()
@@ -53,3 +61,8 @@ def test_two_ranks_even_split(tmp_path):
 
 def test_two_ranks_ragged_split(tmp_path):
     _run(7, tmp_path)
+
+
+def test_two_ranks_mpc_scenarios(tmp_path):
+    """BASELINE configs[4]: scenario batch with per-instance parameter vectors, both W and P sharded."""
+    _run(9, tmp_path, spec='mpc_3dof', n_k=3)
