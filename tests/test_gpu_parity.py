@@ -268,3 +268,54 @@ def test_other_baseline_configs_at_full_batch(name, n_k, B):
     ev.eval_device(dW[perm].contiguous(), dP if dP.ndim == 1 else dP[perm].contiguous(), dG2, dJ2)
     torch.cuda.synchronize()
     assert torch.equal(dG2, dG[perm]) and torch.equal(dJ2, dJ[perm])
+
+
+def test_casadi_external_abi():
+    """The symbols casadi.external('awegpu_g', lib) binds (casadi/core/external.cpp conventions): g(V, P) and the
+    Jacobian function jac_awegpu_g(V, P, out_g) -> (jac_g_V [CCS], jac_g_P [empty]), called the way CasADi calls a
+    generated function: arrays of input / output pointers, compact CCS sparsity descriptors."""
+    import ctypes as C
+    ev = evaluator('ampyx_ap2', 4)
+    lib, ocp = ev.lib, ev.ocp
+    gold = np.load(os.path.join(GOLDEN, 'ampyx_ap2_nk4.npz'))
+    assert lib.awegpu_casadi_bind(ev.handle) == 0
+    PD, PLL = C.POINTER(C.c_double), C.POINTER(C.c_longlong)
+    for f in (lib.awegpu_g_n_in, lib.awegpu_g_n_out, lib.jac_awegpu_g_n_in, lib.jac_awegpu_g_n_out):
+        f.restype = C.c_longlong
+    assert (lib.awegpu_g_n_in(), lib.awegpu_g_n_out()) == (2, 1)
+    assert (lib.jac_awegpu_g_n_in(), lib.jac_awegpu_g_n_out()) == (3, 2)
+    for f in (lib.awegpu_g_name_in, lib.awegpu_g_name_out, lib.jac_awegpu_g_name_out):
+        f.restype, f.argtypes = C.c_char_p, [C.c_longlong]
+    assert (lib.awegpu_g_name_in(0), lib.awegpu_g_name_in(1), lib.awegpu_g_name_out(0)) == (b'V', b'P', b'g')
+    assert (lib.jac_awegpu_g_name_out(0), lib.jac_awegpu_g_name_out(1)) == (b'jac_g_V', b'jac_g_P')
+    for f in (lib.awegpu_g_sparsity_in, lib.awegpu_g_sparsity_out, lib.jac_awegpu_g_sparsity_out):
+        f.restype, f.argtypes = PLL, [C.c_longlong]
+    sp = lib.awegpu_g_sparsity_in(0)
+    assert (sp[0], sp[1], sp[2]) == (ocp.n_v, 1, 1)                      # dense column: [nrow, ncol, 1]
+    sp = lib.awegpu_g_sparsity_out(0)
+    assert (sp[0], sp[1], sp[2]) == (ocp.n_g, 1, 1)
+    sp = lib.jac_awegpu_g_sparsity_out(0)                                # [nrow, ncol, colind[ncol+1], row[nnz]]
+    assert (sp[0], sp[1]) == (ocp.n_g, ocp.n_v)
+    colind = np.ctypeslib.as_array(sp, shape=(2 + ocp.n_v + 1 + ocp.nnz,))
+    assert np.array_equal(colind[2:2 + ocp.n_v + 1], gold['colind'])
+    assert np.array_equal(colind[2 + ocp.n_v + 1:], gold['row'])
+    sp = lib.jac_awegpu_g_sparsity_out(1)
+    assert (sp[0], sp[1]) == (ocp.n_g, ocp.n_p) and sp[2 + ocp.n_p] == 0   # structurally empty
+    # numeric calls: int f(const double** arg, double** res, casadi_int* iw, double* w, int mem)
+    w = np.ascontiguousarray(gold['w'][1])
+    p = np.ascontiguousarray(gold['p'])
+    g = np.empty(ocp.n_g)
+    arg = (PD * 3)(w.ctypes.data_as(PD), p.ctypes.data_as(PD), g.ctypes.data_as(PD))
+    res = (PD * 2)(g.ctypes.data_as(PD), None)
+    lib.awegpu_g.argtypes = [C.POINTER(PD), C.POINTER(PD), PLL, PD, C.c_int]
+    lib.jac_awegpu_g.argtypes = lib.awegpu_g.argtypes
+    assert lib.awegpu_g(arg, res, None, None, 0) == 0
+    assert np.all(np.abs(g - gold['g'][1]) <= 1e-12 * np.maximum(1.0, np.abs(gold['g'][1])))
+    jv = np.empty(ocp.nnz)
+    res = (PD * 2)(jv.ctypes.data_as(PD), None)                          # jac_g_P not requested
+    assert lib.jac_awegpu_g(arg, res, None, None, 0) == 0
+    assert np.all(np.abs(jv - gold['jv'][1]) <= jac_tolerance(ocp, gold['jv'][1])[0])
+    # CasADi passes NULL for an all-zero input: refused (g is undefined at t_f = 0), reported as an evaluation error
+    arg0 = (PD * 3)(None, p.ctypes.data_as(PD), None)
+    res = (PD * 2)(g.ctypes.data_as(PD), None)
+    assert lib.awegpu_g(arg0, res, None, None, 0) != 0
