@@ -85,7 +85,9 @@ typedef struct awegpu_handle awegpu_handle_t;
 
 /* flags of awegpu_eval_batch */
 #define AWEGPU_JAC_INSTANCE_MAJOR 0   /* Jv[b*nnz + slot]   (what CasADi consumes per instance) */
-#define AWEGPU_JAC_BATCH_MINOR    1   /* Jv[slot*B + b]     (for batched on-device consumers)   */
+#define AWEGPU_JAC_BATCH_MINOR    1   /* Jv[slot*B + b]     (for batched on-device consumers;   */
+                                      /* not compiled into the libraries of very large models:  */
+                                      /* the call then fails with a message)                    */
 #define AWEGPU_P_FULL             0   /* P holds full parameter vectors, leading dimension n_p  */
 #define AWEGPU_P_THETA0           4   /* P holds theta0 only, leading dimension n_theta0        */
 #define AWEGPU_P_SHARED           8   /* one parameter vector shared by all instances           */
