@@ -1121,6 +1121,7 @@ struct awegpu_handle {
     int n_affp = 0;          // parameter terms of the affine rows (> 0: the full parameter vector is required)
     int interleave = 1;      // tiles per block of the group-interleaved stage-0 order (0: group-major)
     int interleave_pre = 1;  // the same for the pre-stages
+    int ilv_items = 0;       // > 0: block length in CTA-items instead of tiles (AWEGPU_ILV_ITEMS, experiments)
     // casadi sparsity buffers
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
     std::vector<double> scratch_g;
@@ -1407,6 +1408,8 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         h->interleave = ei ? atoi(ei) : 1;
         const char *ep = getenv("AWEGPU_INTERLEAVE_PRE");
         h->interleave_pre = ep ? atoi(ep) : 1;
+        const char *eq = getenv("AWEGPU_ILV_ITEMS");
+        h->ilv_items = eq ? atoi(eq) : 0;
     }
     // host copies of pointers are not kept: null them so nobody dereferences caller memory later
     h->host.x_base = h->host.x_next = h->host.u_base = h->host.xdot_base = h->host.z_base = nullptr;
@@ -1506,6 +1509,7 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
             a_.grid = dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>());                       \
             a_.st = st_, a_.dp = dp, a_.sc = h->sc, a_.B = B, a_.b_base = b_base, a_.n_items = n_, a_.p_sh = p_sh; \
             a_.ilv = ((T_) == 0 ? h->interleave : h->interleave_pre) * (((S_) ? dp.n_k : dp.n_k * N_D) + NODE_WARPS - 1) / NODE_WARPS; \
+            if (h->ilv_items > 0) a_.ilv = h->ilv_items;                                                          \
             a_.G = G, a_.Jv = jv;                                                                                 \
             launch_node<S_, F, T_>(M, a_);                                                                        \
             h->launches += 1;                                                                                     \

@@ -1,5 +1,3 @@
-for f in awebox_b200/lib/var/*.so; do
-  AWEGPU_LIB=$f timeout 90 python scripts/variant_check.py 4096 2>&1 | tail -2 | cut -c1-150
-  echo "rc=$?"
+for n in 5 10 20 40 80; do
+  echo "ilv_items=$n"; AWEGPU_ILV_ITEMS=$n timeout 120 python scripts/variant_check.py 4096 2>&1 | tail -1 | cut -c41-150
 done
-nvidia-smi --query-gpu=name,utilization.gpu --format=csv,noheader
