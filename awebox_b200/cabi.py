@@ -40,6 +40,7 @@ class ProblemStruct(C.Structure):
         ('aff_row', P_I32), ('aff_begin', P_I32), ('aff_col', P_I32), ('aff_coef', P_F64),
         ('affp_begin', P_I32), ('affp_col', P_I32), ('affp_coef', P_F64), ('aff_const', P_F64),
         ('constraint_scale', C.c_double),
+        ('n_kcoll_out', C.c_int32), ('n_kcoll_head', C.c_int32), ('kcoll_slot', P_I32),
     ]
 
 
@@ -73,6 +74,7 @@ def make_problem(ocp):
         'aff_row': _i32(ocp.aff_row), 'aff_begin': _i32(ocp.aff_begin), 'aff_col': _i32(ocp.aff_col),
         'aff_coef': _f64(ocp.aff_coef), 'affp_begin': _i32(ocp.affp_begin), 'affp_col': _i32(ocp.affp_col),
         'affp_coef': _f64(ocp.affp_coef), 'aff_const': _f64(ocp.aff_const),
+        'kcoll_slot': _i32(ocp.kcoll_slot),
     }
     ps = ProblemStruct()
     ps.n_v, ps.n_p, ps.n_g, ps.nnz = ocp.n_v, ocp.n_p, ocp.n_g, ocp.nnz
@@ -86,6 +88,7 @@ def make_problem(ocp):
     ps.row_periodic, ps.x_last = ocp.row_periodic, ocp.v_cx[n_k - 1][d - 1]
     ps.constraint_scale = ocp.constraint_scale
     ps.n_aff = ocp.n_aff
+    ps.n_kcoll_out, ps.n_kcoll_head = len(ocp.kcoll_out), ocp.n_kcoll_head
     for name, arr in arrays.items():
         ctype = dict(ProblemStruct._fields_)[name]
         setattr(ps, name, arr.ctypes.data_as(ctype))

@@ -38,12 +38,14 @@ def _fmt(v):
 N_REGS = 48          # FP64 values the allocator keeps in registers (-> ~128 registers per thread)
 LOOKAHEAD = 8        # statements between a scratch reload and its first use
 LEAF_LOOKAHEAD = 40  # statements between an input load (global memory, L2 latency) and its first use
+LEAF_BURST = 40       # > 0: input loads are issued in generations of this many statements (schedule.allocate)
 HOT_SLOTS = 1 << 20  # no cold tier: the grouped programs need only a few dozen scratch slots
 CHUNK = 16           # outputs staged per flush
+OWN_CAP = 24         # entries staged per flush of a node's own CCS range (whole columns; raised to the largest column)
 POOL = 0             # per-thread scratch slots shared by spills and the asynchronous input prefetch (0: plain loads; measured slower on B200: the extra shared-memory traffic saturates the MIO queue, profiles/r01_ncu_prefetch_variant.txt)
 PF_AHEAD = 150       # operations between the asynchronous copy of an input and its first use
 HINT_AHEAD = 0       # > 0: L2 prefetch hint this many operations before the load of a record / export input
-GROUP_OPS = 1400     # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
+GROUP_OPS = 900      # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
 MAX_EXPORTS = 64     # intermediate values exported per stage (scaled up for large models, see NodeCode.plan)
 MAX_EXPORTS_SHOOT = 0 # > 0: the same for the shooting-node function (0: as MAX_EXPORTS)
 EXPORT_MIN_GAIN = 40
@@ -137,6 +139,48 @@ class NodeCode(object):
                 e = (j_eq[i] if kind == 'eq' else j_ineq[i]).get(c, S.ZERO)
             outs.append(sc(S._e(e)))
         self.shoot_exprs = outs
+
+        # ---- collocation node, output list of the CUDA kernels (ocp.kcoll_out: head + own CCS range)
+        self.cco = S.sym('cco')                     # C[j+1, j+1] / (h t_f)
+        self.ccs = S.symvec('ccs', d)               # ccs[dl] = C[j+1, sib+1] / (h t_f), sib = (j + dl) mod d
+        self.sib_x = {dl: S.symvec('sibx%d_' % dl, ocp.n_x) for dl in range(1, d)}
+        self.sib_xd = {dl: S.symvec('sibxd%d_' % dl, ocp.n_x) for dl in range(1, d)}
+        self.sib_z = {dl: S.symvec('sibz%d_' % dl, ocp.n_z) for dl in range(1, d)}
+        b_of = {}
+        for i in range(len(eq)):
+            for mm in ocp.eq_split[i]['xdot']:
+                b_of[(i, mm)] = j_eq[i].get(rng['xdot'][0] + mm, S.ZERO)
+        b_keys = sorted(b_of)
+        b_sib = {}
+        for dl in range(1, d):
+            mp = {}
+            for i_ in range(ocp.n_x):
+                mp[m.vars[rng['x'][0] + i_]] = self.sib_x[dl][i_]
+                mp[m.vars[rng['xdot'][0] + i_]] = self.sib_xd[dl][i_]
+            for c_ in range(ocp.n_z):
+                mp[m.vars[rng['z'][0] + c_]] = self.sib_z[dl][c_]
+            sub = S.substitute([S._e(b_of[key]) for key in b_keys], mp)
+            for key, e in zip(b_keys, sub):
+                b_sib[(dl,) + key] = e
+        by_old = {item: e for item, e in zip(ocp.coll_out, self.coll_exprs)}
+        outs = []
+        for item in ocp.kcoll_out:
+            kind = item[0]
+            if kind in ('res', 'u', 'theta', 'phi', 'z') or (kind == 'Xc'):
+                outs.append(by_old[item])            # same expression as in the plain emission (scaled already)
+                continue
+            if kind == 'O':
+                _, i, mm = item
+                e = S.ZERO
+                if mm in ocp.eq_split[i]['x']:
+                    e = e + j_eq[i].get(rng['x'][0] + mm, S.ZERO)
+                if mm in ocp.eq_split[i]['xdot']:
+                    e = e + b_of[(i, mm)] * self.cco
+            else:
+                _, dl, i, mm = item
+                e = b_sib[(dl, i, mm)] * self.ccs[dl]
+            outs.append(sc(S._e(e)))
+        self.kcoll_exprs = outs
         self._kernel_exprs()
         self._ktab = {}                 # literal constants of the scheduled programs: hex value -> index
         self._names = {}
@@ -185,11 +229,19 @@ class NodeCode(object):
             base[m.vars[rng['theta'][0] + i]] = th[i]
         for i in range(m.n_param):
             base[m.params[i]] = pi[i]
-        self.k_coll = S.substitute(self.coll_exprs, base)
+        leaf[self.cco.idx] = 'CCO'
+        for dl in range(1, d):
+            leaf[self.ccs[dl].idx] = 'CCS(%d)' % dl
+            for i in range(ocp.n_x):
+                leaf[self.sib_x[dl][i].idx] = 'XS(%d, %d)' % (dl, i)
+                leaf[self.sib_xd[dl][i].idx] = 'XDS(%d, %d)' % (dl, i)
+            for c in range(ocp.n_z):
+                leaf[self.sib_z[dl][c].idx] = 'ZS(%d, %d)' % (dl, c)
+        self.k_coll = S.substitute(self.kcoll_exprs, base)
         self.k_shoot = S.substitute(self.shoot_exprs, base)
 
     @staticmethod
-    def plan(exprs, limit=None, max_exports=None, min_gain=None):
+    def plan(exprs, limit=None, max_exports=None, min_gain=None, cuts=None, forced=()):
         """Split a node function into small programs.
 
         * the outputs are cut into consecutive *groups* whose operation cones weigh at most ``limit``
@@ -204,6 +256,9 @@ class NodeCode(object):
           gains are independent), so that large models are planned in a few dozen rounds.
 
         Cones are rows of a packed bit matrix (numpy), weights are summed by matrix products.
+
+        ``cuts``: output indices at which a new group may start (None: anywhere); ``forced``: indices at which one
+        must start.
 
         -> (export nodes in dependency order, [(first, last+1)] output groups)"""
         limit = GROUP_OPS if limit is None else limit
@@ -257,7 +312,7 @@ class NodeCode(object):
             for i, op in enumerate(out_pos):
                 ce = c[op] if (op >= 0 and not exported[op]) else np.zeros(nb, dtype=np.uint8)
                 u = cur | ce
-                if i > first and wsum(u) > limit:
+                if i > first and (i in forced or (wsum(u) > limit and (cuts is None or i in cuts))):
                     groups.append((first, i, cur))
                     cur, first = ce.copy(), i
                 else:
@@ -305,7 +360,7 @@ class NodeCode(object):
         return exports, [(a, b) for a, b, _ in groups]
 
     def emit_scheduled(self, exprs, n_regs=N_REGS, lookahead=LOOKAHEAD, hot_slots=HOT_SLOTS, chunk=CHUNK, first=0,
-                       export=False, leaf_names=None, q0=0):
+                       export=False, leaf_names=None, q0=0, chunks=None, own_init=None):
         """-> (text, stats): register-allocated straight-line code (awebox_b200/schedule.py) printed
         with statement macros:
             LD_XR(reg, r, m) LD_XO(reg, m) LD_XD(reg, m) LD_U(reg, c) LD_Z(reg, c) LD_TH(reg, t)
@@ -321,7 +376,7 @@ class NodeCode(object):
             prog = SCH.prefetch_leaves(prog, POOL, PF_AHEAD, lambda n: '(' in names_[n.idx] and
                                        names_[n.idx].split('(')[0] not in ('CCIN', 'OWNIN'))
         else:
-            prog = SCH.allocate(exprs, n_regs, lookahead, leaf_lookahead=LEAF_LOOKAHEAD)
+            prog = SCH.allocate(exprs, n_regs, lookahead, leaf_lookahead=LEAF_LOOKAHEAD, leaf_burst=LEAF_BURST)
             if HINT_AHEAD > 0:
                 prog = SCH.prefetch_hints(prog, HINT_AHEAD, lambda n: names_[n.idx].split('(')[0] in
                                           ('XO', 'XD', 'UIN', 'ZIN', 'EXIN'))
@@ -342,8 +397,19 @@ class NodeCode(object):
             tier = {s_: ('SPILL', s_) for s_ in access}
             n_hot, n_cold = prog.stats.get('pool', 0), 0
         lines = ['double ' + ', '.join('r%d' % i for i in range(prog.n_regs)) + ';']
+        if not export and chunks is None:
+            # staged outputs in chunks of ``chunk``, cooperative / per-warp flush
+            chunks = [('head', c0, min(chunk, len(exprs) - c0), q0 + c0 // chunk) for c0 in range(0, len(exprs), chunk)]
         if not export:
-            lines.append('GROUP_INIT(%d, %d, %d);' % (q0, (len(exprs) + chunk - 1) // chunk, first))
+            n_headq = sum(1 for c in chunks if c[0] == 'head')
+            if n_headq:
+                lines.append('GROUP_INIT(%d, %d, %d);' % (q0, n_headq, first))
+            if own_init is not None:
+                lines.append('OWN_INIT(%d, %d, %d, %d);' % own_init)
+            chunk_of, own_idx = {}, 0
+            for ci, (kind, c0, cnt, qid) in enumerate(chunks):
+                for n_ in range(c0, c0 + cnt):
+                    chunk_of[n_] = ci
 
         ktab = self._ktab
 
@@ -394,19 +460,28 @@ class NodeCode(object):
                 if export:
                     lines.append('EXOUT(%d, %s);' % (first + n, src(it[2])))
                     continue
-                lines.append('OUT(%d, %s);' % (n % chunk, src(it[2])))
-                if (n + 1) % chunk == 0 or n + 1 == n_out:
-                    last_chunk = n + 1 == n_out
-                    lines.append('FLUSH(%d, %d, %d, %d, %d);' % (
-                        q0 + n // chunk, first + (n // chunk) * chunk, n % chunk + 1,
-                        -1 if last_chunk else q0 + n // chunk + 1, first + (n // chunk + 1) * chunk))
+                ci = chunk_of[n]
+                kind, c0, cnt, qid = chunks[ci]
+                if kind == 'head':
+                    lines.append('OUT(%d, %s);' % (n - c0, src(it[2])))
+                    if n + 1 == c0 + cnt:
+                        nxt = chunks[ci + 1] if ci + 1 < len(chunks) and chunks[ci + 1][0] == 'head' else None
+                        lines.append('FLUSH(%d, %d, %d, %d, %d);' % (
+                            qid, first + c0, cnt, -1 if nxt is None else nxt[3], first + c0 + cnt))
+                else:
+                    # own CCS range: position table index = output number inside the group's own outputs
+                    if n == c0:
+                        lines.append('OWN_BEGIN(%d);' % qid)
+                    lines.append('OUTO(%d, %s);' % (n - own_init[2] + first if own_init else n, src(it[2])))
+                    if n + 1 == c0 + cnt:
+                        lines.append('FLUSH_OWN(%d);' % qid)
             else:
                 r, n, srcs = it[1], it[2], it[3]
                 lines.append('r%d = %s;' % (r, _rhs(n.op, src(srcs[0]), src(srcs[1]) if len(srcs) > 1 else None)))
                 n_stmt += 1
         stats = dict(prog.stats)
         stats.update(S.count_ops(exprs))
-        stats.update(outputs=n_out, chunks=(n_out + chunk - 1) // chunk, hot_slots=n_hot, cold_slots=n_cold,
+        stats.update(outputs=n_out, chunks=len(chunks) if chunks else 0, hot_slots=n_hot, cold_slots=n_cold,
                      cold_accesses=cold_acc)
         return '\n'.join(lines) + '\n', stats
 
@@ -483,7 +558,14 @@ class NodeCode(object):
                 cap = None
                 if name.startswith('k_shoot') and MAX_EXPORTS_SHOOT > 0 and len(cur) and len([n for n in S.topo(cur) if SCH.is_op(n)]) <= 8000:
                     cap = MAX_EXPORTS_SHOOT
-                exports, groups = self.plan(cur, max_exports=0 if level == MAX_STAGES - 1 else cap)
+                cuts = forced = None
+                if name == 'k_coll' and level == 0:
+                    # groups of own outputs consist of whole CCS columns; head and own outputs do not share a group
+                    n_head = ocp.n_kcoll_head
+                    cuts = set(range(n_head + 1)) | set(n_head + f for f, _ in ocp.kcoll_cols)
+                    forced = {n_head}
+                exports, groups = self.plan(cur, max_exports=0 if level == MAX_STAGES - 1 else cap, cuts=cuts,
+                                            forced=forced or ())
                 new = [n for n in exports if n.idx not in ex_index]
                 for n in new:
                     ex_index[n.idx] = len(ex_nodes)
@@ -510,13 +592,43 @@ class NodeCode(object):
                     g_exprs = S.substitute(outs, mapping) if mapping else outs
                     q0 = 0
                     chunk_first, chunk_cnt = [], []
+                    own_q = []           # own chunks: (first own output, count, first local column, columns)
+                    group_own = []       # per group: (first own chunk, chunks, first own output, outputs)
+                    n_head = ocp.n_kcoll_head if name == 'k_coll' else len(outs)
                     for g, (a, b) in enumerate(groups):
-                        if level == 0:
+                        if level == 0 and a >= n_head:
+                            # own CCS range: chunks of whole columns, at most OWN_CAP staged entries (constant
+                            # entries of the columns included: at most 2 per column)
+                            cols = [ci for ci, (f, c) in enumerate(ocp.kcoll_cols) if a <= n_head + f < b and c > 0]
+                            chunks, cur_cols = [], []
+                            cap = max(OWN_CAP, max(c for _, c in ocp.kcoll_cols) + 2)
+
+                            def close():
+                                if cur_cols:
+                                    f0 = ocp.kcoll_cols[cur_cols[0]][0]
+                                    cnt = sum(ocp.kcoll_cols[ci][1] for ci in cur_cols)
+                                    chunks.append(('own', n_head + f0 - a, cnt, len(own_q)))
+                                    own_q.append((f0, cnt, cur_cols[0], cur_cols[-1] - cur_cols[0] + 1))
+                                    del cur_cols[:]
+
+                            oq0 = len(own_q)
+                            for ci in cols:
+                                if cur_cols and (sum(ocp.kcoll_cols[x][1] + 2 for x in cur_cols) + ocp.kcoll_cols[ci][1] + 2 > cap
+                                                 or ci != cur_cols[-1] + 1):
+                                    close()
+                                cur_cols.append(ci)
+                            close()
+                            assert sum(c[2] for c in chunks) == b - a, 'empty columns inside an own group'
+                            group_own.append((oq0, len(own_q) - oq0, a - n_head, b - a))
+                            body, st = self.emit_scheduled(g_exprs[a:b], first=a, leaf_names=leaf_names, q0=q0, chunks=chunks,
+                                                           own_init=(oq0, len(own_q) - oq0, a, b - a))
+                        elif level == 0:
                             body, st = self.emit_scheduled(g_exprs[a:b], first=a, leaf_names=leaf_names, q0=q0)
                             for c0 in range(a, b, CHUNK):
                                 chunk_first.append(c0)
                                 chunk_cnt.append(min(CHUNK, b - c0))
                             q0 += (b - a + CHUNK - 1) // CHUNK
+                            group_own.append((len(own_q), 0, 0, 0))
                         else:
                             body, st = self.emit_scheduled(g_exprs[a:b], first=ex_index[outs[a].idx], export=True,
                                                            leaf_names=leaf_names)
@@ -529,6 +641,7 @@ class NodeCode(object):
                 sstats.append(gstats)
                 if level == 0:
                     chunks0 = (chunk_first, chunk_cnt)
+                    own0 = (own_q, group_own)
             allg = [st for gs in sstats for st in gs]
             hot = max(st['hot_slots'] for st in allg)
             stats[name] = {'stages': sstats, 'n_exports': len(ex_nodes),
@@ -538,14 +651,34 @@ class NodeCode(object):
                 up, len(ex_nodes), up, hot, up, stats[name]['ops_total'])
             for level in range(N_STAGE_FILES):
                 kdefs += '#define AWE_%s_S%d_GROUPS %d\n' % (up, level, len(sstats[level]))
-            kdefs += '#define AWE_%s_NCHUNKS %d\n' % (up, len(chunks0[0]))
-            kdefs += '#define AWE_%s_MAXQ %d\n' % (up, max((b - a + CHUNK - 1) // CHUNK for a, b in stages[0][1]))
+                # relative cost of the groups (share of the SMs a group gets in the persistent node kernels):
+                # operations + input loads + staged outputs
+                wts = [int(st['op'] + 2 * st['leaf'] + 3 * (st['st'] + st['ld']) + (8 if level == 0 else 2) * st['outputs'])
+                       for st in sstats[level]] or [0]
+                kdefs += '#define AWE_%s_S%d_WEIGHTS {%s}\n' % (up, level, ', '.join(map(str, wts)))
+            kdefs += '#define AWE_%s_NCHUNKS %d\n' % (up, max(1, len(chunks0[0])))
+            n_head_ = ocp.n_kcoll_head if name == 'k_coll' else len(stages[0][0])
+            kdefs += '#define AWE_%s_MAXQ %d\n' % (up, max([1] + [(min(b, n_head_) - a + CHUNK - 1) // CHUNK
+                                                                  for a, b in stages[0][1] if a < n_head_]))
             kdefs += 'static const int awe_%s_chunk_first[] = {%s};\n' % (name, ', '.join(map(str, chunks0[0])))
             kdefs += 'static const int awe_%s_chunk_cnt[] = {%s};\n' % (name, ', '.join(map(str, chunks0[1])))
             gq, acc = [0], 0
             for a_, b_ in stages[0][1]:
-                acc += (b_ - a_ + CHUNK - 1) // CHUNK
+                if a_ < n_head_:
+                    acc += (b_ - a_ + CHUNK - 1) // CHUNK
                 gq.append(acc)
+            if name == 'k_coll':
+                own_q, group_own = own0
+                kdefs += '#define AWE_N_KCOLL_OUT %d\n#define AWE_N_KCOLL_HEAD %d\n#define AWE_N_KCOLL_OWN %d\n' % (
+                    len(ocp.kcoll_out), ocp.n_kcoll_head, len(ocp.kcoll_own))
+                kdefs += '#define AWE_K_COLL_NOWNQ %d\n' % max(1, len(own_q))
+                rs = max([c + 2 * nc for _, c, _, nc in own_q] or [2]) + 2
+                kdefs += '#define AWE_OWN_RS %d\n' % (rs + (rs & 1))
+                kdefs += '#define AWE_K_COLL_MAXOWN %d\n' % max([1] + [n for _, _, _, n in group_own])
+                kdefs += '#define AWE_K_COLL_MAXOWNQ %d\n' % max([1] + [n for _, n, _, _ in group_own])
+                for nm_, col in (('first', 0), ('cnt', 1), ('col0', 2), ('ncol', 3)):
+                    kdefs += 'static const int awe_k_coll_own_%s[] = {%s};\n' % (nm_, ', '.join(str(q[col]) for q in own_q) or '0')
+                stats[name]['own_chunks'] = len(own_q)
             kdefs += '#define AWE_%s_GROUP_Q0 {%s}\n' % (up, ', '.join(map(str, gq)))
             stats[name]['n_chunks'] = len(chunks0[0])
         kvals = [float.fromhex(h) for h, _ in sorted(self._ktab.items(), key=lambda kv: kv[1])] or [0.0]

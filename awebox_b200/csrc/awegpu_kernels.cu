@@ -44,10 +44,6 @@
 #define AWE_TU -1
 #endif
 #define TU_OWNS(n) (AWE_TU == -1 || AWE_TU == (n))
-// warp-specialised output stage of the collocation nodes (awegpu_coll_ws_kernel): on unless -DAWE_NO_WS
-#if !defined(AWE_NO_WS) && !defined(AWE_WS)
-#define AWE_WS 1
-#endif
 #define AWE_N_TU 5      /* 0 host, 1 coll full stage 0, 2 coll full stages 1-2, 3 shoot full stage 0, 4 shoot full stages 1-2 */
 
 #define TILE 32
@@ -100,6 +96,13 @@ struct DevProblem {
     const double *rest_val;
     const double *coop_const;      // [COOP_NCONST] distinct values of the constant entries flushed cooperatively
                                    // (per handle: several handles may share this library)
+    // own CCS range of every collocation node (k, j): the columns of X_{k,j+1} and z_{k,j}, written by the thread
+    // that evaluates the node, chunk by chunk (whole columns; awebox_b200/ocp/nlp.py: kcoll_own)
+    const int4 *own_desc;          // [n_k * d][AWE_K_COLL_NOWNQ] {first CCS slot, entries, first constant, constants}
+    const unsigned char *own_pos;  // [n_k * d][AWE_N_KCOLL_OWN]  position of every own output inside its chunk
+                                   //                             (OWN_DUMP: not a structural entry)
+    const uchar2 *own_cst;         // constant entries inside the own ranges {position in the chunk, value id}
+    const double *own_cval;        // [OWN_NCVAL] their distinct values
     int n_aff;
     const int *aff_row, *aff_begin, *aff_col, *affp_begin, *affp_col;
     const double *aff_coef, *affp_coef, *aff_const;
@@ -198,6 +201,13 @@ __device__ __forceinline__ double sqrt_nr(const double x)
     } while (0)
 #define EXOUT(i, val) asm volatile("st.global.f64 [%0], %1;" ::"l"(w_ex + (i) * 32), "d"(val) : "memory")
 #define LD_CC(reg, r) reg = c_coeff_coll[(r) * (N_D + 1) + j1] * itf_nk
+// inputs of the sibling node (j + dl) mod d of the same interval and the coefficients C[j+1, .] / (h t_f) of the
+// node's own column block (awebox_b200/ocp/nlp.py: kcoll_own)
+#define LD_XS(reg, dl, m) LDG_(reg, w_rec + sib_off[(dl)-1] + (m) * 32)
+#define LD_ZS(reg, dl, c) LDG_(reg, w_rec + sib_off[(dl)-1] + (N_X + (c)) * 32)
+#define LD_XDS(reg, dl, m) LDG_(reg, w_xd + sib_xd[(dl)-1] + (m) * 32)
+#define LD_CCO(reg) reg = c_coeff_coll[j1 * (N_D + 1) + j1] * itf_nk
+#define LD_CCS(reg, dl) reg = c_coeff_coll[j1 * (N_D + 1) + sib_j1[(dl)-1]] * itf_nk
 #define LD_ITF(reg) reg = itf
 #define LD_OWN(reg, r) reg = (j1 == (r)) ? 1.0 : 0.0
 #define SPILL_ST(slot, reg) STS_(scr_addr + (slot) * (8 * NODE_THREADS), reg)
@@ -252,6 +262,30 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #ifndef AWE_EXP_NO_FLUSH
 #define AWE_EXP_NO_FLUSH 0
 #endif
+// own CCS range: per lane one row of the warp's staging area (instance-major: the row IS the run of the CCS value
+// array of the lane's instance; odd row stride: conflict-free for the staging writes, lane = instance, and for the
+// flush reads, lane = entry); OWN_DUMP collects outputs that are not structural entries
+#define OWN_STRIDE (AWE_OWN_RS | 1)
+#define OWN_DUMP (AWE_OWN_RS - 1)
+#define OWN_NCVAL 8
+#define OWN_MAXCST (2 * (N_X + N_Z))
+#define OWN_POS_BYTES (((2 * AWE_K_COLL_MAXOWN + 15) / 16) * 16)
+#define OWN_TAB_BYTES (16 * AWE_K_COLL_MAXOWNQ + OWN_POS_BYTES + ((2 * OWN_MAXCST + 15) / 16) * 16)
+#define OWN_INIT(oq0, noq, ofirst, ocnt)                                                                          \
+    const int oq0_ = (oq0);                                                                                        \
+    (void)oq0_;                                                                                                    \
+    own_init(own_tab, pr, k * N_D + j, (oq0), (noq), (ofirst) - AWE_N_KCOLL_HEAD, (ocnt), lane)
+#define OWN_BEGIN(q) own_d = reinterpret_cast<const int4 *>(own_tab)[(q) - oq0_]
+#define OUTO(idx, val)                                                                                            \
+    do {                                                                                                           \
+        /* byte offset of the output inside the lane's staging row */                                              \
+        const unsigned p_ = reinterpret_cast<const unsigned short *>(own_tab + 16 * AWE_K_COLL_MAXOWNQ)[(idx)];    \
+        if (BATCH_MINOR) {                                                                                         \
+            if (valid && p_ != 8 * OWN_DUMP) ST_OUT(Jv + (size_t)(own_d.x + (p_ >> 3)) * (size_t)B + b, (val));    \
+        } else                                                                                                     \
+            STS_(own_lane + p_, (val));                                                                            \
+    } while (0)
+#define FLUSH_OWN(q) flush_own<BATCH_MINOR>(own_warp, own_lane, own_d, own_tab, own_cval_s, valid, n_valid, lane, Jv, b0, b, B, nnz)
 #define OUT(n, val) stg[(n) * STG_STRIDE + lane] = (val)
 // start of a stage-0 program: q0 = first output chunk of the group, nq = number of chunks.  The
 // cooperative flush reads its destination tables from shared memory; they are fetched here with
@@ -266,7 +300,7 @@ __device__ __forceinline__ double sqrt_nr(const double x)
                              "r"(tab_addr + e_ * 8), "l"(coop_tab + (q0) * COOP_PER + e_) : "memory"); \
             asm volatile("cp.async.commit_group;" ::: "memory");                                     \
             for (int e_ = tid; e_ < COOP_NCONST * STG_STRIDE; e_ += NODE_THREADS)                    \
-                smem[(size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES + e_] = __ldg(pr.coop_const + e_ / STG_STRIDE); \
+                stg_u[NODE_WARPS * STG_DOUBLES + e_] = __ldg(pr.coop_const + e_ / STG_STRIDE); \
         } else                                                                                       \
             FLUSH_PREP(q0, first);                                                                   \
     } while (0)
@@ -280,7 +314,7 @@ __device__ __forceinline__ double sqrt_nr(const double x)
 #define FLUSH(q, first, cnt, q_next, first_next)                                                     \
     do {                                                                                             \
         if (COOP) {                                                                                  \
-            if (!AWE_EXP_NO_FLUSH) flush_coop(smem + (size_t)HOT * NODE_THREADS, tab_smem + ((q) - q0_) * COOP_PER, lane, wid, n_valid, g_tile, j_tile, n_g, nnz, bar_id); \
+            if (!AWE_EXP_NO_FLUSH) flush_coop(stg_u, tab_smem + ((q) - q0_) * COOP_PER, lane, wid, n_valid, g_tile, j_tile, n_g, nnz, bar_id); \
         } else if (BATCH_MINOR)                                                                      \
             flush_chunk_bm(stg, dest + (first), cnt, lane, valid, G, Jv, (size_t)B, (size_t)b);      \
         else {                                                                                       \
@@ -409,6 +443,80 @@ __device__ __forceinline__ void flush_chunk_bm(double *stg, const int *__restric
             if (Jv) ST_OUT(Jv + (size_t)code * B + b, v);
         } else if (code <= -2)
             ST_OUT(G + (size_t)(-2 - code) * B + b, v);
+    }
+    __syncwarp();
+}
+
+// tables of the own chunks oq0 .. oq0 + noq - 1 of node kj -> the warp's table area: [descriptors | positions | constants]
+__device__ __forceinline__ void own_init(unsigned char *tab, const DevProblem &pr, const int kj, const int oq0, const int noq,
+                                         const int ofirst, const int ocnt, const int lane)
+{
+    __syncwarp();
+    int4 *dsc = reinterpret_cast<int4 *>(tab);
+    const int4 *src = pr.own_desc + (size_t)kj * AWE_K_COLL_NOWNQ + oq0;
+    int cst0 = 0, cst1 = 0;
+    if (lane < noq) dsc[lane] = __ldg(src + lane);
+    for (int q = 32 + lane; q < noq; q += 32) dsc[q] = __ldg(src + q);
+    {
+        const int4 a = __ldg(src), z = __ldg(src + noq - 1);
+        cst0 = a.z, cst1 = z.z + z.w;
+    }
+    const unsigned char *ps = pr.own_pos + (size_t)kj * AWE_N_KCOLL_OWN + ofirst;
+    unsigned short *pd = reinterpret_cast<unsigned short *>(tab + 16 * AWE_K_COLL_MAXOWNQ);
+    for (int e = lane; e < ocnt; e += 32) pd[e] = (unsigned short)(8 * __ldg(ps + e));
+    uchar2 *cd = reinterpret_cast<uchar2 *>(tab + 16 * AWE_K_COLL_MAXOWNQ + OWN_POS_BYTES);
+    for (int e = lane; e < cst1 - cst0; e += 32) cd[e] = __ldg(pr.own_cst + cst0 + e);
+    __syncwarp();
+    // descriptors keep absolute constant indices: rebase to the copy
+    if (lane < noq) dsc[lane].z -= cst0;
+    for (int q = 32 + lane; q < noq; q += 32) dsc[q].z -= cst0;
+    __syncwarp();
+}
+
+// one chunk of the own range is staged (lane = instance): constants in, then the warp writes the rows out, lane =
+// entry: every store instruction writes one contiguous run of the CCS value array of one instance
+template <bool BATCH_MINOR>
+__device__ __forceinline__ void flush_own(const double *own_warp, const unsigned own_lane, const int4 d, const unsigned char *tab,
+                                          const double *cval, const bool valid, const int n_valid, const int lane,
+                                          double *__restrict__ Jv, const int b0, const int b, const int B, const int nnz)
+{
+    const uchar2 *cst = reinterpret_cast<const uchar2 *>(tab + 16 * AWE_K_COLL_MAXOWNQ + OWN_POS_BYTES) + d.z;
+    if (BATCH_MINOR) {
+        if (valid)
+            for (int c = 0; c < d.w; ++c) ST_OUT(Jv + (size_t)(d.x + cst[c].x) * (size_t)B + b, cval[cst[c].y]);
+        return;
+    }
+    for (int c = 0; c < d.w; ++c) {
+        const uchar2 pc = cst[c];
+        STS_(own_lane + pc.x * 8, cval[pc.y]);
+    }
+    __syncwarp();
+    const int len = d.y;
+#pragma unroll 1
+    for (int p0 = 0; p0 < len; p0 += 32) {
+        if (p0 + lane < len) {
+            double *dst = Jv + (size_t)b0 * (size_t)nnz + d.x + p0 + lane;
+            const double *src = own_warp + p0 + lane;
+            if (n_valid == TILE) {
+#pragma unroll 1
+                for (int i = 0; i < TILE; i += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = src[u * OWN_STRIDE];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        ST_OUT(dst, v[u]);
+                        dst += nnz;
+                    }
+                    src += 8 * OWN_STRIDE;
+                }
+            } else {
+                for (int i = 0; i < n_valid; ++i) {
+                    ST_OUT(dst, *src);
+                    dst += nnz, src += OWN_STRIDE;
+                }
+            }
+        }
     }
     __syncwarp();
 }
@@ -545,153 +653,65 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
 }
 
 // --------------------------------------------------------------------------- node programs
-// warp = one node of one tile, lane = instance, blockIdx.y = program group of stage STAGE.
-// Stage 0 produces the node's outputs; stages >= 1 produce exported intermediates (run first).
+// Persistent, group-specialised node kernel.  One CTA per SM; a CTA is QUADS quads of NODE_WARPS warps; a quad
+// works on one CTA-item at a time: warp = one node of one tile, lane = instance (collocation: the N_D nodes of one
+// interval, which the cooperative flush relies on; shooting: NODE_WARPS consecutive shooting nodes).  A CTA stays on
+// ONE program group for as long as that group has items left: straight-line code larger than the 32 KB instruction
+// cache is limited by instruction fetch to 0.4-1.3 warp-instructions per clock and SM (profiles/r02_ubench.jsonl),
+// a resident <= 27 KB program is not.  Items of a group are handed out through one atomic counter per group, so the
+// share of the SMs a group gets only has to be roughly proportional to its cost (sched.cta_group, from the
+// generator's weights); a CTA whose group has run dry moves on to the next group.
+// Stage 0 produces the node's outputs; stages >= 1 produce exported intermediates (launched first).
 #define EXPORTS_OF(SHOOT, FULL) \
     ((SHOOT) ? ((FULL) ? AWE_K_SHOOT_EXPORTS : AWE_K_SHOOT_RES_EXPORTS) : ((FULL) ? AWE_K_COLL_EXPORTS : AWE_K_COLL_RES_EXPORTS))
 #define HOT_OF(SHOOT, FULL) \
     ((SHOOT) ? ((FULL) ? AWE_K_SHOOT_HOT : AWE_K_SHOOT_RES_HOT) : ((FULL) ? AWE_K_COLL_HOT : AWE_K_COLL_RES_HOT))
+#define SMEM_PER_SM (227 * 1024)
+#define MAX_GROUPS 64
 
-template <bool SHOOT, bool FULL, int STAGE, bool BATCH_MINOR>
-__global__ void __launch_bounds__(NODE_THREADS, AWE_NODE_CTAS)
-awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const int n_items,
-                   const double *__restrict__ p_shared, const int ilv, double *__restrict__ G, double *__restrict__ Jv)
+#define MAX_CTAS 192
+struct Sched {
+    int *counters;            // [MAX_GROUPS] next CTA-item of every group of this launch (zeroed before the launch)
+    // group a CTA starts with.  By value: a kernel parameter indexed by blockIdx is a uniform value to ptxas, so that
+    // the switch over the program groups is a uniform branch and the warp barriers inside the programs (LEAF_FENCE)
+    // cost nothing; a value loaded from global or shared memory is not, and every LEAF_FENCE becomes a
+    // WARPSYNC.COLLECTIVE that waits for the outstanding loads
+    unsigned char cta_group[MAX_CTAS];
+    int lead;                 // CTA-items a group may run ahead of the slowest one before its CTAs move over
+};
+
+// shared memory of a quad: [spill slots | tables of the own chunks (per warp) | U], where U is either the chunk
+// staging of the cooperative / per-warp flush + replicated constants + destination tables, or the instance-major
+// rows of the own CCS range (a program group uses one of the two layouts)
+template <bool SHOOT, bool FULL>
+__host__ __device__ static constexpr size_t own_tab_doubles()
 {
-    constexpr int HOT = HOT_OF(SHOOT, FULL);
-    constexpr int NEX = EXPORTS_OF(SHOOT, FULL);
-    // the cooperative flush needs the CTA to be exactly the N_D nodes of one interval
-#ifdef AWE_EXP_NO_COOP
-    constexpr bool COOP = false;          /* ablation: per-warp flush for the collocation nodes as well */
-#else
-    constexpr bool COOP = !SHOOT && FULL && STAGE == 0 && !BATCH_MINOR && N_D == NODE_WARPS;
-#endif
-    extern __shared__ double smem[];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // CTA order: blocks of `ilv` consecutive CTA-items, all groups of a block before the next block, so
-    // that the groups that read the same inputs and write into the same sectors run close in time
-    int cta_item, group;
-    {
-        const int n_groups = gridDim.y, n_cta_items = gridDim.x;
-        const int lin = blockIdx.y * n_cta_items + blockIdx.x;          // hardware dispatch order
-        if (ilv > 0) {
-            const int per_block = ilv * n_groups;
-            const int blk = lin / per_block, rem = lin - blk * per_block;
-            const int blk_items = min(ilv, n_cta_items - blk * ilv);   // the last block may be short
-            group = rem / blk_items, cta_item = blk * ilv + rem % blk_items;
-        } else
-            group = blockIdx.y, cta_item = blockIdx.x;
-    }
-    const int item = cta_item * NODE_WARPS + wid;
-    if (item >= n_items) return;
-    int tile, k, j;
-    if (SHOOT) {
-        j = -1, k = item % pr.n_k, tile = item / pr.n_k;
-    } else {
-        j = item % N_D, k = (item / N_D) % pr.n_k, tile = item / (N_D * pr.n_k);
-    }
-    const int j1 = j + 1;
-    const int b0 = b_base + tile * TILE;
-    const int b = b0 + lane;
-    const bool valid = b < B;
-    const int n_valid = min(TILE, B - b0);
-    const int n_g = pr.n_g;
-    const int nnz = (int)pr.nnz;
-    double *stg = smem + (size_t)HOT * NODE_THREADS + wid * STG_DOUBLES;
-    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
-
-    const double *w_rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32 + lane;
-    const double *w_own = SHOOT ? w_rec + OFF_X0 * 32 : w_rec + OFF_CX(j) * 32;
-    const double *w_z = SHOOT ? w_rec + OFF_Z * 32 : w_own + N_X * 32;
-    const double *w_xd = SHOOT ? w_rec + OFF_XDOT * 32
-                               : sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
-    // theta0: the lane-contiguous copy the gather kernel made (per-instance vectors, or the shared one replicated)
-    const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
-    (void)p_shared;
-    double *w_ex = (SHOOT ? sc.exs : sc.exc) + (size_t)item * (NEX > 0 ? NEX : 1) * 32 + lane;
-    const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
-    const double itf_nk = itf * (double)pr.n_k;
-    (void)itf_nk, (void)w_ex, (void)valid, (void)n_valid, (void)stg, (void)scr_addr;
-    const int *dest = SHOOT ? pr.shoot_dest + (size_t)k * pr.n_shoot_out
-                            : pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
-    double *g_tile = G + (size_t)b0 * n_g;
-    double *j_tile = Jv ? Jv + (size_t)b0 * (size_t)nnz : nullptr;
-    const int2 *coop_tab = pr.coop_tab + (size_t)k * AWE_K_COLL_NCHUNKS * COOP_PER;
-    const int2 *tab_smem = reinterpret_cast<const int2 *>(smem + (size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES +
-                                                          COOP_NCONST * STG_STRIDE);
-    const unsigned tab_addr = (unsigned)__cvta_generic_to_shared(tab_smem);
-    int fl_code = -1;
-    constexpr int bar_id = 0;
-    constexpr bool EX_RW = false;
-    (void)dest, (void)g_tile, (void)j_tile, (void)coop_tab, (void)tab_smem, (void)tab_addr, (void)fl_code;
-#define RUN(FILE_)           \
-    switch (group) {         \
-        FILE_                \
-    }
-    if (SHOOT && FULL) {
-        if (STAGE == 0) {
-            switch (group) {
-#include "k_shoot_s0.inc"
-            }
-        } else if (STAGE == 1) {
-            switch (group) {
-#include "k_shoot_s1.inc"
-            }
-        } else {
-            switch (group) {
-#include "k_shoot_s2.inc"
-            }
-        }
-    } else if (SHOOT && !FULL) {
-        if (STAGE == 0) {
-            switch (group) {
-#include "k_shoot_res_s0.inc"
-            }
-        } else if (STAGE == 1) {
-            switch (group) {
-#include "k_shoot_res_s1.inc"
-            }
-        } else {
-            switch (group) {
-#include "k_shoot_res_s2.inc"
-            }
-        }
-    } else if (!SHOOT && FULL) {
-        if (STAGE == 0) {
-            switch (group) {
-#include "k_coll_s0.inc"
-            }
-        } else if (STAGE == 1) {
-            switch (group) {
-#include "k_coll_s1.inc"
-            }
-        } else {
-            switch (group) {
-#include "k_coll_s2.inc"
-            }
-        }
-    } else {
-        if (STAGE == 0) {
-            switch (group) {
-#include "k_coll_res_s0.inc"
-            }
-        } else if (STAGE == 1) {
-            switch (group) {
-#include "k_coll_res_s1.inc"
-            }
-        } else {
-            switch (group) {
-#include "k_coll_res_s2.inc"
-            }
-        }
-    }
-#undef RUN
+    return (!SHOOT && FULL) ? ((size_t)NODE_WARPS * OWN_TAB_BYTES + 7) / 8 : 0;
 }
-
+template <bool SHOOT, bool FULL>
+__host__ __device__ static constexpr size_t union_doubles()
+{
+    const size_t head = (size_t)NODE_WARPS * STG_DOUBLES +
+                        ((!SHOOT && FULL) ? (size_t)COOP_NCONST * STG_STRIDE + (size_t)AWE_K_COLL_MAXQ * COOP_PER : 0);
+    const size_t own = (!SHOOT && FULL) ? (size_t)NODE_THREADS * OWN_STRIDE : 0;
+    return head > own ? head : own;
+}
 template <bool SHOOT, bool FULL>
 __host__ __device__ static constexpr size_t node_smem_bytes()
 {
-    return sizeof(double) * ((size_t)HOT_OF(SHOOT, FULL) * NODE_THREADS + NODE_WARPS * STG_DOUBLES) +
-           ((!SHOOT && FULL) ? sizeof(double) * COOP_NCONST * STG_STRIDE + sizeof(int2) * AWE_K_COLL_MAXQ * COOP_PER : 0);
+    return sizeof(double) * ((size_t)HOT_OF(SHOOT, FULL) * NODE_THREADS + own_tab_doubles<SHOOT, FULL>() + union_doubles<SHOOT, FULL>());
+}
+// quads per CTA: what the shared memory of an SM holds, at most AWE_NODE_QUADS (3 quads = 12 warps leave every
+// thread 168 registers)
+#ifndef AWE_NODE_QUADS
+#define AWE_NODE_QUADS 3
+#endif
+template <bool SHOOT, bool FULL>
+__host__ __device__ static constexpr int node_quads()
+{
+    return (SMEM_PER_SM - 64) / node_smem_bytes<SHOOT, FULL>() >= AWE_NODE_QUADS
+               ? AWE_NODE_QUADS
+               : ((SMEM_PER_SM - 64) / node_smem_bytes<SHOOT, FULL>() >= 1 ? (int)((SMEM_PER_SM - 64) / node_smem_bytes<SHOOT, FULL>()) : 1);
 }
 template <bool SHOOT, bool FULL, int STAGE>
 __host__ __device__ static constexpr int node_groups()
@@ -704,171 +724,243 @@ __host__ __device__ static constexpr int node_groups()
                                        : STAGE == 1 ? AWE_K_COLL_RES_S1_GROUPS : AWE_K_COLL_RES_S2_GROUPS));
 }
 
-#if defined(AWE_WS) && TU_OWNS(1)
-// --------------------------------------------------------------------------- warp-specialised output stage
-// Collocation nodes, full Jacobian, instance-major layout (AWEGPU_WS=0 falls back to awegpu_node_kernel<coll, 0>).
-// Measured on B200 (AP2, B=4096): 1.38 ms against 1.44 ms for the kernel whose computing warps flush themselves.
-// CTA = 8 warps: warps 0-3 run the node programs of the four collocation nodes of one interval and only STAGE their
-// results; warps 4-7 drain the staging area to global memory (the cooperative flush).  Two staging buffers, named
-// barriers full[b] / empty[b] (256 participants: 128 arrive, 128 wait), register file split with setmaxnreg:
-// the store warps hand their registers to the computing ones.
-__device__ const int awe_k_coll_group_q0[] = AWE_K_COLL_GROUP_Q0;
-#define WS_THREADS (2 * NODE_THREADS)
-#define WS_REGS_COMPUTE 208
-#define WS_REGS_STORE 48
-#define WS_BAR_FULL(b) (1 + (b))
-#define WS_BAR_EMPTY(b) (3 + (b))
-#define WS_BAR_STORE 5
-__host__ __device__ static constexpr size_t ws_smem_bytes()
+template <bool SHOOT, bool FULL, int STAGE, bool BATCH_MINOR>
+__global__ void __launch_bounds__(NODE_THREADS * node_quads<SHOOT, FULL>(), 1)
+awegpu_node_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const int n_items,
+                   const double *__restrict__ p_shared, const Sched sched, double *__restrict__ G, double *__restrict__ Jv)
 {
-    return sizeof(double) * ((size_t)AWE_K_COLL_HOT * NODE_THREADS + 2 * NODE_WARPS * STG_DOUBLES + COOP_NCONST * STG_STRIDE) +
-           sizeof(int2) * AWE_K_COLL_MAXQ * COOP_PER;
-}
-
-__device__ __forceinline__ void ws_bar_sync(const int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(WS_THREADS) : "memory"); }
-__device__ __forceinline__ void ws_bar_arrive(const int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(WS_THREADS) : "memory"); }
-
-#undef GROUP_INIT
-#undef FLUSH
-#define GROUP_INIT(q0, nq, first) (void)0
-// a chunk is staged: hand the buffer to the store warps, continue in the other one once it has been drained
-#define FLUSH(q, first, cnt, q_next, first_next)                                              \
-    do {                                                                                      \
-        ws_bar_arrive(WS_BAR_FULL(buf));                                                      \
-        buf ^= 1;                                                                             \
-        stg = stg_base + buf * (NODE_WARPS * STG_DOUBLES);                                    \
-        if ((q_next) >= 0 && ++n_staged >= 2) ws_bar_sync(WS_BAR_EMPTY(buf));                 \
-    } while (0)
-
-__global__ void __launch_bounds__(WS_THREADS, 2)
-awegpu_coll_ws_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const int n_items, const int ilv,
-                      double *__restrict__ G, double *__restrict__ Jv)
-{
-    constexpr bool SHOOT = false, FULL = true, BATCH_MINOR = false, COOP = true, EX_RW = false;
-    constexpr int HOT = AWE_K_COLL_HOT;
-    constexpr int NEX = AWE_K_COLL_EXPORTS;
-    extern __shared__ double smem[];
-    const int role = threadIdx.x / NODE_THREADS;                 // 0: compute, 1: store
-    const int tid = threadIdx.x - role * NODE_THREADS, lane = tid & 31, wid = tid >> 5;
-    int cta_item, group;
-    {
-        const int n_groups = gridDim.y, n_cta_items = gridDim.x;
-        const int lin = blockIdx.y * n_cta_items + blockIdx.x;
-        if (ilv > 0) {
-            const int per_block = ilv * n_groups;
-            const int blk = lin / per_block, rem = lin - blk * per_block;
-            const int blk_items = min(ilv, n_cta_items - blk * ilv);
-            group = rem / blk_items, cta_item = blk * ilv + rem % blk_items;
-        } else
-            group = blockIdx.y, cta_item = blockIdx.x;
+    constexpr int HOT = HOT_OF(SHOOT, FULL);
+    constexpr int NEX = EXPORTS_OF(SHOOT, FULL);
+    constexpr int QUADS = node_quads<SHOOT, FULL>();
+    constexpr int N_GROUPS = node_groups<SHOOT, FULL, STAGE>();
+    constexpr size_t QUAD_DOUBLES = node_smem_bytes<SHOOT, FULL>() / sizeof(double);
+    // the cooperative flush needs the quad to be exactly the N_D nodes of one interval
+#ifdef AWE_EXP_NO_COOP
+    constexpr bool COOP = false;          /* ablation: per-warp flush for the collocation nodes as well */
+#else
+    constexpr bool COOP = !SHOOT && FULL && STAGE == 0 && !BATCH_MINOR && N_D == NODE_WARPS;
+#endif
+    extern __shared__ double smem_all[];
+    __shared__ int s_next[QUADS][2], s_group[QUADS][2];
+    const int quad = threadIdx.x / NODE_THREADS;
+    const int tid = threadIdx.x - quad * NODE_THREADS, lane = tid & 31, wid = tid >> 5;
+    const int bar_id = 1 + quad;
+    double *smem = smem_all + (size_t)quad * QUAD_DOUBLES;
+    double *stg_u = smem + (size_t)HOT * NODE_THREADS + own_tab_doubles<SHOOT, FULL>();
+    double *stg = stg_u + wid * STG_DOUBLES;
+    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
+    const int2 *tab_smem = reinterpret_cast<const int2 *>(stg_u + NODE_WARPS * STG_DOUBLES + COOP_NCONST * STG_STRIDE);
+    const unsigned tab_addr = (unsigned)__cvta_generic_to_shared(tab_smem);
+    // own CCS range (collocation nodes, stage 0): the warp's table area and the lane's staging row
+    unsigned char *own_tab = reinterpret_cast<unsigned char *>(smem + (size_t)HOT * NODE_THREADS) + (size_t)wid * OWN_TAB_BYTES;
+    const double *own_warp = stg_u + (size_t)wid * 32 * OWN_STRIDE;
+    const unsigned own_lane = (unsigned)__cvta_generic_to_shared(stg_u + (size_t)tid * OWN_STRIDE);
+    int4 own_d = make_int4(0, 0, 0, 0);
+    __shared__ double own_cval_s[OWN_NCVAL];
+    if (!SHOOT && FULL && STAGE == 0) {
+        if (threadIdx.x < OWN_NCVAL) own_cval_s[threadIdx.x] = __ldg(pr.own_cval + threadIdx.x);
+        __syncthreads();
     }
-    const int item = cta_item * NODE_WARPS + wid;                // collocation: whole CTAs are valid or not
-    if (cta_item * NODE_WARPS >= n_items) return;
-    const int j = item % N_D, k = (item / N_D) % pr.n_k, tile = item / (N_D * pr.n_k);
-    const int j1 = j + 1;
-    const int b0 = b_base + tile * TILE;
-    const int n_valid = min(TILE, B - b0);
+    (void)own_tab, (void)own_lane, (void)own_warp, (void)own_d;
     const int n_g = pr.n_g;
     const int nnz = (int)pr.nnz;
-    double *stg_cta = smem + (size_t)HOT * NODE_THREADS;          // two buffers of NODE_WARPS * STG_DOUBLES
-    double *cst_rows = stg_cta + 2 * NODE_WARPS * STG_DOUBLES;
-    int2 *tab_smem = reinterpret_cast<int2 *>(cst_rows + COOP_NCONST * STG_STRIDE);
-    double *g_tile = G + (size_t)b0 * n_g;
-    double *j_tile = Jv + (size_t)b0 * (size_t)nnz;
-    const int q0 = awe_k_coll_group_q0[group], nq = awe_k_coll_group_q0[group + 1] - q0;
-    if (role == 1) {
-        // ------------------------------------------------------------------ store warps
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REGS_STORE));
-        const int2 *coop_tab = pr.coop_tab + ((size_t)k * AWE_K_COLL_NCHUNKS + q0) * COOP_PER;
-        for (int e = tid; e < nq * COOP_PER; e += NODE_THREADS) tab_smem[e] = __ldg(coop_tab + e);
-        for (int e = tid; e < COOP_NCONST * STG_STRIDE; e += NODE_THREADS) cst_rows[e] = __ldg(pr.coop_const + e / STG_STRIDE);
-        asm volatile("bar.sync %0, %1;" ::"n"(WS_BAR_STORE), "n"(NODE_THREADS) : "memory");
-        int buf = 0;
+    const int n_cta_items = (n_items + NODE_WARPS - 1) / NODE_WARPS;
+    constexpr bool EX_RW = false;
+    (void)p_shared, (void)stg, (void)scr_addr, (void)tab_smem, (void)tab_addr;
+    int group = sched.cta_group[blockIdx.x];
+    int it = 0;
+    // A CTA leaves its group for the one that lags most when its own group is more than `lead` CTA-items ahead of
+    // it: the groups of one tile then run within a short time of each other, so that the records and exports they
+    // share are read from L2 and the sectors they share in the output are completed in L2 (a static split lets
+    // the groups drift apart by dozens of tiles).  Also the end game: a group that has run dry counts as "ahead".
+    const int lead = sched.lead;
+    // (Choosing the group one item early, to hide the latency of the counter reads and of the atomic, was measured
+    // 5 - 50 % slower: with stale counters the CTAs flock to the same lagging group and the groups drift apart.)
 #pragma unroll 1
-        for (int q = 0; q < nq; ++q) {
-            ws_bar_sync(WS_BAR_FULL(buf));
-            const int2 *tab = tab_smem + q * COOP_PER;
-            // staged rows of this buffer, then the constant rows: row index COOP_STAGED + c -> cst_rows + c
-            const double *rows = stg_cta + buf * (NODE_WARPS * STG_DOUBLES);
-            const int n_ent = tab[COOP_PER - 1].y;
-#pragma unroll 1
-            for (int e = 0; e * 32 < n_ent; ++e) {
-                const int2 t = tab[e * 32 + lane];
-                const int code = t.x;
-                const bool is_j = code >= 0;
-                double *base = is_j ? j_tile : g_tile;
-                const int ld = is_j ? nnz : n_g;
-                const int step = ld * N_D;
-                int off = (is_j ? code : -2 - code) + wid * ld;
-                const double *s = (t.y < COOP_STAGED ? rows + t.y * STG_STRIDE : cst_rows + (t.y - COOP_STAGED) * STG_STRIDE) + wid;
-                if (code != -1) {
-#pragma unroll 1
-                    for (int i = wid; i < n_valid; i += N_D) {
-                        ST_OUT(base + off, *s);
-                        off += step;
-                        s += N_D;
+    while (true) {
+        // next CTA-item: one atomic per quad, handed to the other threads through shared memory (two slots: a
+        // thread may be one iteration ahead of the slowest thread of its quad, never two)
+        if (wid == 0) {
+            int g = group;
+            int mine = 0x7fffffff, best = 0x7fffffff, best_g = 0;
+            for (int g0 = 0; g0 < N_GROUPS; g0 += 32) {
+                const int gg = g0 + lane;
+                const int c = gg < N_GROUPS ? *(volatile const int *)(sched.counters + gg) : 0x7fffffff;
+                const int m = __reduce_min_sync(0xffffffffu, c);
+                if (m < best) best = m, best_g = g0 + __ffs(__ballot_sync(0xffffffffu, c == m)) - 1;
+                const int cm = __shfl_sync(0xffffffffu, c, g & 31);
+                if ((g >> 5) == (g0 >> 5)) mine = cm;
+            }
+            if (mine >= n_cta_items || mine - best > lead) g = best_g;
+            if (lane == 0) {
+                s_next[quad][it & 1] = atomicAdd(sched.counters + g, 1);
+                s_group[quad][it & 1] = g;
+            }
+        }
+        quad_sync(bar_id);
+        const int cta_item = s_next[quad][it & 1];
+        {
+            // votes: warp-uniform values by construction (see Sched)
+            const int g = s_group[quad][it & 1];
+            int gu = 0;
+#pragma unroll
+            for (int bit = 0; bit < 6; ++bit) gu |= __any_sync(0xffffffffu, (g >> bit) & 1) ? (1 << bit) : 0;
+            group = gu;
+        }
+        ++it;
+        if (__all_sync(0xffffffffu, cta_item >= n_cta_items)) break;
+
+        {
+            const int item_raw = cta_item * NODE_WARPS + wid;
+            const bool active = __all_sync(0xffffffffu, item_raw < n_items);   // collocation (N_D == NODE_WARPS): whole quads are active
+            const int item = active ? item_raw : n_items - 1;
+            int tile, k, j;
+            if (SHOOT) {
+                j = -1, k = item % pr.n_k, tile = item / pr.n_k;
+            } else {
+                j = item % N_D, k = (item / N_D) % pr.n_k, tile = item / (N_D * pr.n_k);
+            }
+            const int j1 = j + 1;
+            const int b0 = b_base + tile * TILE;
+            const int b = b0 + lane;
+            const bool valid = b < B;
+            const int n_valid = min(TILE, B - b0);
+            const double *w_rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32 + lane;
+            const double *w_own = SHOOT ? w_rec + OFF_X0 * 32 : w_rec + OFF_CX(j) * 32;
+            const double *w_z = SHOOT ? w_rec + OFF_Z * 32 : w_own + N_X * 32;
+            const double *w_xd = SHOOT ? w_rec + OFF_XDOT * 32
+                                       : sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
+            // theta0: the lane-contiguous copy the gather kernel made (per-instance vectors, or the shared one replicated)
+            const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
+            double *w_ex = (SHOOT ? sc.exs : sc.exc) + (size_t)item * (NEX > 0 ? NEX : 1) * 32 + lane;
+            // siblings of the interval: record offsets of their state blocks, offsets of their contracted derivatives
+            // relative to the node's own, their block indices
+            int sib_off[N_D > 1 ? N_D - 1 : 1], sib_xd[N_D > 1 ? N_D - 1 : 1], sib_j1[N_D > 1 ? N_D - 1 : 1];
+#pragma unroll
+            for (int dl = 1; dl < N_D; ++dl) {
+                const int sj = SHOOT ? 0 : (j + dl) % N_D;
+                sib_off[dl - 1] = OFF_CX(sj) * 32, sib_xd[dl - 1] = (sj - j) * (N_X * 32), sib_j1[dl - 1] = sj + 1;
+            }
+            (void)sib_off, (void)sib_xd, (void)sib_j1;
+            const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
+            const double itf_nk = itf * (double)pr.n_k;
+            const int *dest = SHOOT ? pr.shoot_dest + (size_t)k * pr.n_shoot_out
+                                    : pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
+            double *g_tile = G + (size_t)b0 * n_g;
+            double *j_tile = Jv ? Jv + (size_t)b0 * (size_t)nnz : nullptr;
+            const int2 *coop_tab = pr.coop_tab + (size_t)k * AWE_K_COLL_NCHUNKS * COOP_PER;
+            int fl_code = -1;
+            (void)itf_nk, (void)w_ex, (void)valid, (void)n_valid, (void)w_z, (void)w_pt, (void)w_xd, (void)w_own, (void)j1, (void)b;
+            (void)dest, (void)g_tile, (void)j_tile, (void)coop_tab, (void)fl_code;
+            if (active) {
+                if (SHOOT && FULL) {
+                    if (STAGE == 0) {
+                        switch (group) {
+#include "k_shoot_s0.inc"
+                        }
+                    } else if (STAGE == 1) {
+                        switch (group) {
+#include "k_shoot_s1.inc"
+                        }
+                    } else {
+                        switch (group) {
+#include "k_shoot_s2.inc"
+                        }
+                    }
+                } else if (SHOOT && !FULL) {
+                    if (STAGE == 0) {
+                        switch (group) {
+#include "k_shoot_res_s0.inc"
+                        }
+                    } else if (STAGE == 1) {
+                        switch (group) {
+#include "k_shoot_res_s1.inc"
+                        }
+                    } else {
+                        switch (group) {
+#include "k_shoot_res_s2.inc"
+                        }
+                    }
+                } else if (!SHOOT && FULL) {
+                    if (STAGE == 0) {
+                        switch (group) {
+#include "k_coll_s0.inc"
+                        }
+                    } else if (STAGE == 1) {
+                        switch (group) {
+#include "k_coll_s1.inc"
+                        }
+                    } else {
+                        switch (group) {
+#include "k_coll_s2.inc"
+                        }
+                    }
+                } else {
+                    if (STAGE == 0) {
+                        switch (group) {
+#include "k_coll_res_s0.inc"
+                        }
+                    } else if (STAGE == 1) {
+                        switch (group) {
+#include "k_coll_res_s1.inc"
+                        }
+                    } else {
+                        switch (group) {
+#include "k_coll_res_s2.inc"
+                        }
                     }
                 }
             }
-            if (q + 2 < nq) ws_bar_arrive(WS_BAR_EMPTY(buf));       // somebody will wait for this buffer again
-            buf ^= 1;
         }
-        return;
-    }
-    // ---------------------------------------------------------------------- computing warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REGS_COMPUTE));
-    const int b = b0 + lane;
-    const bool valid = b < B;
-    double *stg_base = stg_cta + wid * STG_DOUBLES;
-    double *stg = stg_base;
-    int buf = 0, n_staged = 0;
-    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
-    const double *w_rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32 + lane;
-    const double *w_own = w_rec + OFF_CX(j) * 32;
-    const double *w_z = w_own + N_X * 32;
-    const double *w_xd = sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
-    const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
-    double *w_ex = sc.exc + (size_t)item * (NEX > 0 ? NEX : 1) * 32 + lane;
-    const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
-    const double itf_nk = itf * (double)pr.n_k;
-    (void)itf_nk, (void)w_ex, (void)valid, (void)scr_addr, (void)w_z, (void)w_pt, (void)j1, (void)n_staged;
-    switch (group) {
-#include "k_coll_s0.inc"
     }
 }
-#endif  /* AWE_WS */
 
 // --------------------------------------------------------------------------- launch plumbing (per translation unit)
 struct NodeLaunch {
-    dim3 grid;
+    int n_ctas;               // SMs of the device
     cudaStream_t st;
     DevProblem dp;
     Scratch sc;
-    int B, b_base, n_items, ilv;
+    int B, b_base, n_items;
     const double *p_sh;
+    int *counters;            // [6][MAX_GROUPS]: one block per (collocation | shooting, stage), zeroed by the caller
+    const unsigned char *cta_group;     // [6][n_ctas] (host)
+    int lead;
     double *G, *Jv;
 };
 
 template <bool S, bool F, int T>
 static void launch_node_impl(const bool bm, const NodeLaunch &a)
 {
+    constexpr int kind = (S ? 3 : 0) + T;
+    constexpr int quads = node_quads<S, F>();
+    const int n_cta_items = (a.n_items + NODE_WARPS - 1) / NODE_WARPS;
+    // no more CTAs than there are quads' worth of work
+    const long long work = (long long)n_cta_items * node_groups<S, F, T>();
+    const int grid = (int)std::min<long long>(a.n_ctas, (work + quads - 1) / quads);
+    Sched sched;
+    sched.counters = a.counters + kind * MAX_GROUPS;
+    sched.lead = a.lead;
+    // a smaller grid samples the table evenly
+    for (int c = 0; c < grid; ++c) sched.cta_group[c] = a.cta_group[(size_t)kind * a.n_ctas + (size_t)c * a.n_ctas / grid];
+    const size_t smem = quads * node_smem_bytes<S, F>();
     // the output layout only matters to the output stage: pre-stages have one instantiation
     if (bm && T == 0 && AWE_BATCH_MINOR)
-        awegpu_node_kernel<S, F, T, (T == 0) && AWE_BATCH_MINOR><<<a.grid, NODE_THREADS, node_smem_bytes<S, F>(), a.st>>>(
-            a.dp, a.sc, a.B, a.b_base, a.n_items, a.p_sh, a.ilv, a.G, a.Jv);
+        awegpu_node_kernel<S, F, T, (T == 0) && AWE_BATCH_MINOR><<<grid, NODE_THREADS * quads, smem, a.st>>>(
+            a.dp, a.sc, a.B, a.b_base, a.n_items, a.p_sh, sched, a.G, a.Jv);
     else
-        awegpu_node_kernel<S, F, T, false><<<a.grid, NODE_THREADS, node_smem_bytes<S, F>(), a.st>>>(
-            a.dp, a.sc, a.B, a.b_base, a.n_items, a.p_sh, a.ilv, a.G, a.Jv);
+        awegpu_node_kernel<S, F, T, false><<<grid, NODE_THREADS * quads, smem, a.st>>>(
+            a.dp, a.sc, a.B, a.b_base, a.n_items, a.p_sh, sched, a.G, a.Jv);
 }
 
 template <bool S, bool F, int T>
 static cudaError_t attr_node_impl()
 {
-    cudaError_t e = cudaFuncSetAttribute(awegpu_node_kernel<S, F, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)node_smem_bytes<S, F>());
+    const int bytes = (int)(node_quads<S, F>() * node_smem_bytes<S, F>());
+    cudaError_t e = cudaFuncSetAttribute(awegpu_node_kernel<S, F, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess && T == 0 && AWE_BATCH_MINOR)
         e = cudaFuncSetAttribute(awegpu_node_kernel<S, F, T, (T == 0) && AWE_BATCH_MINOR>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)node_smem_bytes<S, F>());
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
 
@@ -890,26 +982,10 @@ DECL_TU(4)
 #undef DECL_TU
 
 #if TU_OWNS(1)
-void awe_launch_tu1(int, bool bm, const NodeLaunch &a)
-{
-#ifdef AWE_WS
-    // pays for the large node functions (measured: AP2 -2.4 %, dual kites -1.7 % per step); the small 3-DOF model
-    // is faster with three self-flushing CTAs per SM (+4.6 % with this kernel)
-    static const int use_ws = getenv("AWEGPU_WS") ? atoi(getenv("AWEGPU_WS")) : (AWE_K_COLL_OPS > 8000);
-    if (use_ws && !bm && a.Jv != nullptr && N_D == NODE_WARPS) {
-        awegpu_coll_ws_kernel<<<a.grid, WS_THREADS, ws_smem_bytes(), a.st>>>(a.dp, a.sc, a.B, a.b_base, a.n_items, a.ilv, a.G, a.Jv);
-        return;
-    }
-#endif
-    launch_node_impl<false, true, 0>(bm, a);
-}
+void awe_launch_tu1(int, bool bm, const NodeLaunch &a) { launch_node_impl<false, true, 0>(bm, a); }
 cudaError_t awe_init_tu1(const double *cc, const double *cf)
 {
     cudaError_t e = set_coeff_here(cc, cf);
-#ifdef AWE_WS
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(awegpu_coll_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws_smem_bytes());
-#endif
     return e != cudaSuccess ? e : attr_node_impl<false, true, 0>();
 }
 #endif
@@ -961,135 +1037,7 @@ static void launch_node(const bool bm, const NodeLaunch &a)
 }
 #endif
 
-#if defined(AWE_WITH_FUSED) && TU_OWNS(0)
-// --------------------------------------------------------------------------- fused persistent kernel
-// EXPERIMENT (compiled with -DAWE_WITH_FUSED, selected with AWEGPU_FUSED=1): measured 1.5x SLOWER than the
-// per-stage kernels on B200 (profiles/r01_ncu_fused_variant_B1024.txt: 36 % of the stall samples are
-// instruction fetch when the quads drift apart, and in lock step all warps wait for their inputs together).
-// One CTA per SM, FUSED_QUADS quads of NODE_WARPS warps.  A quad owns one interval of one tile (its N_D
-// collocation nodes) or NODE_WARPS shooting nodes; the CTA walks over its units and runs, for every unit, ALL
-// programs of the node function back to back: pre-stages (exports) first, then the output groups.  All warps
-// of the SM execute the same program at the same time (one ~27 KB program in the instruction cache), and the
-// exported intermediates live in a per-warp slot that is rewritten for every unit: they stay in L2 and never
-// travel to HBM, input records are read from HBM once.  Full Jacobian, instance-major layout only.
-#define SMEM_PER_SM (227 * 1024)
-template <bool SHOOT>
-__host__ __device__ static constexpr int fused_quads()
-{
-    // quads that fit the shared memory of one SM (at most 3: the register file holds 12 warps of these programs)
-    return (int)(SMEM_PER_SM / node_smem_bytes<SHOOT, true>() >= 3 ? 3 : SMEM_PER_SM / node_smem_bytes<SHOOT, true>());
-}
 
-template <bool SHOOT>
-__global__ void __launch_bounds__(NODE_THREADS * (fused_quads<SHOOT>() > 0 ? fused_quads<SHOOT>() : 1), 1)
-awegpu_fused_kernel(const DevProblem pr, const Scratch sc, const int B, const int b_base, const int n_items,
-                    double *__restrict__ ex_slots, double *__restrict__ G, double *__restrict__ Jv)
-{
-    constexpr bool FULL = true, BATCH_MINOR = false, EX_RW = true;
-    constexpr int HOT = HOT_OF(SHOOT, FULL);
-    constexpr int NEX = EXPORTS_OF(SHOOT, FULL);
-    constexpr bool COOP = !SHOOT && N_D == NODE_WARPS;
-    constexpr int FUSED_QUADS = fused_quads<SHOOT>();
-    constexpr int N2 = node_groups<SHOOT, true, 2>(), N1 = node_groups<SHOOT, true, 1>(), N0 = node_groups<SHOOT, true, 0>();
-    constexpr size_t QUAD_DOUBLES = node_smem_bytes<SHOOT, true>() / sizeof(double);
-    extern __shared__ double smem_all[];
-    const int quad = threadIdx.x / NODE_THREADS;
-    const int tid = threadIdx.x - quad * NODE_THREADS, lane = tid & 31, wid = tid >> 5;
-    const int bar_id = 1 + quad;
-    double *smem = smem_all + (size_t)quad * QUAD_DOUBLES;
-    double *stg = smem + (size_t)HOT * NODE_THREADS + wid * STG_DOUBLES;
-    const unsigned scr_addr = (unsigned)__cvta_generic_to_shared(smem + tid);
-    const int2 *tab_smem = reinterpret_cast<const int2 *>(smem + (size_t)HOT * NODE_THREADS + NODE_WARPS * STG_DOUBLES +
-                                                          COOP_NCONST * STG_STRIDE);
-    const unsigned tab_addr = (unsigned)__cvta_generic_to_shared(tab_smem);
-    const int n_g = pr.n_g;
-    const int nnz = (int)pr.nnz;
-    // exports: one slot per resident warp, rewritten for every unit
-    double *w_ex = ex_slots + ((size_t)blockIdx.x * (FUSED_QUADS * NODE_WARPS) + quad * NODE_WARPS + wid) * (NEX > 0 ? NEX : 1) * 32 + lane;
-    constexpr int PER_UNIT = FUSED_QUADS * NODE_WARPS;
-    (void)stg, (void)scr_addr, (void)tab_smem, (void)tab_addr, (void)w_ex, (void)bar_id;
-#pragma unroll 1
-    for (int unit = blockIdx.x; unit * PER_UNIT < n_items; unit += gridDim.x) {
-        const int item_raw = unit * PER_UNIT + quad * NODE_WARPS + wid;
-        const bool active = item_raw < n_items;        // a whole quad is active or not (collocation: N_D == NODE_WARPS)
-        const int item = active ? item_raw : n_items - 1;
-        int tile, k, j;
-        if (SHOOT) {
-            j = -1, k = item % pr.n_k, tile = item / pr.n_k;
-        } else {
-            j = item % N_D, k = (item / N_D) % pr.n_k, tile = item / (N_D * pr.n_k);
-        }
-        const int j1 = j + 1;
-        const int b0 = b_base + tile * TILE;
-        const int b = b0 + lane;
-        const bool valid = b < B;
-        const int n_valid = min(TILE, B - b0);
-        const double *w_rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32 + lane;
-        const double *w_own = SHOOT ? w_rec + OFF_X0 * 32 : w_rec + OFF_CX(j) * 32;
-        const double *w_z = SHOOT ? w_rec + OFF_Z * 32 : w_own + N_X * 32;
-        const double *w_xd = SHOOT ? w_rec + OFF_XDOT * 32
-                                   : sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
-        const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
-        const double itf = 1.0 / __ldg(w_rec + (REC_TH + (AWE_TF_LOCAL - (2 * N_X + N_U + N_Z))) * 32);
-        const double itf_nk = itf * (double)pr.n_k;
-        const int *dest = SHOOT ? pr.shoot_dest + (size_t)k * pr.n_shoot_out
-                                : pr.coll_dest + (size_t)(k * N_D + j) * pr.n_coll_out;
-        double *g_tile = G + (size_t)b0 * n_g;
-        double *j_tile = Jv + (size_t)b0 * (size_t)nnz;
-        const int2 *coop_tab = pr.coop_tab + (size_t)k * AWE_K_COLL_NCHUNKS * COOP_PER;
-        int fl_code = -1;
-        (void)itf_nk, (void)valid, (void)n_valid, (void)dest, (void)g_tile, (void)j_tile, (void)coop_tab, (void)fl_code;
-        (void)j1, (void)w_own, (void)w_z, (void)w_xd, (void)w_pt, (void)b;
-#pragma unroll 1
-        for (int prog = 0; prog < N2 + N1 + N0; ++prog) {
-            if (active) {
-                if (prog < N2) {
-                    const int group = prog;
-                    if (SHOOT) {
-                        switch (group) {
-#include "k_shoot_s2.inc"
-                        }
-                    } else {
-                        switch (group) {
-#include "k_coll_s2.inc"
-                        }
-                    }
-                } else if (prog < N2 + N1) {
-                    const int group = prog - N2;
-                    if (SHOOT) {
-                        switch (group) {
-#include "k_shoot_s1.inc"
-                        }
-                    } else {
-                        switch (group) {
-#include "k_coll_s1.inc"
-                        }
-                    }
-                } else {
-                    const int group = prog - N2 - N1;
-                    if (SHOOT) {
-                        switch (group) {
-#include "k_shoot_s0.inc"
-                        }
-                    } else {
-                        switch (group) {
-#include "k_coll_s0.inc"
-                        }
-                    }
-                }
-            }
-#ifdef AWE_FUSED_LOCKSTEP
-            // all warps of the SM move to the next program together (instruction-cache locality).  Measured
-            // slower on B200 than letting the quads drift: in lock step all warps wait for their opening input
-            // loads at the same time.  Nothing else needs this barrier: the staging area, spill slots and export
-            // slot are per warp, the flush table is protected by the quad barriers of the flush itself.
-            __syncthreads();
-#endif
-        }
-    }
-}
-
-#endif  /* AWE_WITH_FUSED */
 
 #if TU_OWNS(0)
 static constexpr size_t gather_smem_bytes() { return sizeof(double) * TILE * SLAB_STRIDE; }
@@ -1115,13 +1063,12 @@ struct awegpu_handle {
     // node-input records of one chunk of instances (see awegpu_gather_kernel)
     Scratch sc{};
     int chunk_tiles = 0, scratch_tiles = 0;
-    double *ex_coll = nullptr, *ex_shoot = nullptr;   // export slots of the fused kernels
-    int n_sm = 0, fused = 1;
+    int n_sm = 0;
+    int lead_tiles = 2;           // tiles a program group may run ahead of the slowest group (AWEGPU_LEAD)
+    int *counters = nullptr;      // [6][MAX_GROUPS] work counters of the persistent node kernels
+    std::vector<unsigned char> cta_group;     // [2 (full | residual only)][6][n_sm] group every CTA starts with
     int n_rest = 0;          // constant Jacobian entries the cooperative flush does not carry
     int n_affp = 0;          // parameter terms of the affine rows (> 0: the full parameter vector is required)
-    int interleave = 1;      // tiles per block of the group-interleaved stage-0 order (0: group-major)
-    int interleave_pre = 1;  // the same for the pre-stages
-    int ilv_items = 0;       // > 0: block length in CTA-items instead of tiles (AWEGPU_ILV_ITEMS, experiments)
     // casadi sparsity buffers
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
     std::vector<double> scratch_g;
@@ -1180,7 +1127,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     for (void *p : h->dev_allocs) cudaFree(p);
     cudaFree(h->dW), cudaFree(h->dP), cudaFree(h->dG), cudaFree(h->dJ);
     cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
-    cudaFree(h->ex_coll), cudaFree(h->ex_shoot);
+    cudaFree(h->counters);
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1211,7 +1158,8 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     // the compiled node functions must belong to this problem
     if (p->n_var != AWE_N_VAR || p->n_theta0 != AWE_N_THETA0 || p->n_phi != AWE_N_PHI || p->d != AWE_D ||
         p->n_x != N_X || p->n_u != N_U || p->n_z != N_Z || p->n_theta != N_TH ||
-        p->n_coll_out != AWE_N_COLL_OUT || p->n_shoot_out != AWE_N_SHOOT_OUT ||
+        p->n_coll_out != AWE_N_COLL_OUT || p->n_shoot_out != AWE_N_SHOOT_OUT || p->n_kcoll_out != AWE_N_KCOLL_OUT ||
+        p->n_kcoll_head != AWE_N_KCOLL_HEAD || p->kcoll_slot == nullptr ||
         p->n_shoot_eq + p->n_ineq != AWE_N_SHOOT_ROWS) {
         set_err(h, "problem dimensions do not match the compiled model '" AWE_MODEL_NAME "'");
         return 4;
@@ -1232,7 +1180,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     DevProblem &d = h->dp;
     d.n_v = p->n_v, d.n_p = p->n_p, d.n_g = p->n_g, d.n_k = p->n_k, d.n_theta0 = p->n_theta0, d.n_phi = p->n_phi;
     d.v_phi = p->v_phi, d.p_theta0 = p->p_theta0, d.nnz = p->nnz;
-    d.n_coll_out = p->n_coll_out, d.n_shoot_out = p->n_shoot_out, d.n_shoot_eq = p->n_shoot_eq, d.n_ineq = p->n_ineq;
+    d.n_coll_out = p->n_kcoll_out, d.n_shoot_out = p->n_shoot_out, d.n_shoot_eq = p->n_shoot_eq, d.n_ineq = p->n_ineq;
     d.n_periodic = p->n_periodic, d.row_periodic = p->row_periodic, d.x_last = p->x_last, d.x_first = p->x_base[0];
     d.cscale = p->constraint_scale;
     d.n_aff = p->n_aff;
@@ -1240,11 +1188,68 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     const int nk = p->n_k, dd = p->d;
     // destination codes of the node-local outputs: >= 0 slot of the CCS value array, -1 none,
     // <= -2 row (-2 - code) of g
-    std::vector<int> coll_dest((size_t)nk * dd * p->n_coll_out), shoot_dest((size_t)nk * p->n_shoot_out);
+    // (collocation nodes: the kernels' own output order, head outputs first, then the node's own CCS range)
+    const int nco = p->n_kcoll_out;
+    std::vector<int> coll_dest((size_t)nk * dd * nco), shoot_dest((size_t)nk * p->n_shoot_out);
     for (int kj = 0; kj < nk * dd; ++kj)
-        for (int n = 0; n < p->n_coll_out; ++n)
-            coll_dest[(size_t)kj * p->n_coll_out + n] =
-                n < AWE_N_EQ ? -2 - (p->row_coll[kj] + n) : p->coll_slot[(size_t)kj * p->n_coll_out + n];
+        for (int n = 0; n < nco; ++n)
+            coll_dest[(size_t)kj * nco + n] = n < AWE_N_EQ ? -2 - (p->row_coll[kj] + n) : p->kcoll_slot[(size_t)kj * nco + n];
+    // ---- own CCS ranges: chunk descriptors, positions of the outputs inside their chunk, constant entries
+    std::vector<int4> own_desc((size_t)nk * dd * AWE_K_COLL_NOWNQ, make_int4(0, 0, 0, 0));
+    std::vector<unsigned char> own_pos((size_t)nk * dd * (AWE_N_KCOLL_OWN > 0 ? AWE_N_KCOLL_OWN : 1), (unsigned char)OWN_DUMP);
+    std::vector<uchar2> own_cst;
+    std::vector<double> own_cval;
+    std::vector<char> own_handled((size_t)p->nnz, 0);        // CCS slots written by the own-range flush
+    {
+        std::vector<int> const_of((size_t)p->nnz, -1);
+        for (int e = 0; e < p->n_const; ++e) const_of[p->const_slot[e]] = e;
+        std::vector<int> at;
+        for (int kj = 0; kj < nk * dd && AWE_N_KCOLL_OWN > 0; ++kj) {
+            const int k = kj / dd, j = kj % dd;
+            const int vcol = p->x_base[k * (dd + 1) + j + 1];
+            for (int q = 0; q < AWE_K_COLL_NOWNQ; ++q) {
+                const long long s0 = p->colind[vcol + awe_k_coll_own_col0[q]];
+                const long long s1 = p->colind[vcol + awe_k_coll_own_col0[q] + awe_k_coll_own_ncol[q]];
+                const int len = (int)(s1 - s0);
+                if (len > OWN_DUMP || len > 250) {
+                    set_err(h, "own CCS range: a chunk does not fit the staging row");
+                    return 4;
+                }
+                at.assign(len, -1);
+                for (int n = awe_k_coll_own_first[q]; n < awe_k_coll_own_first[q] + awe_k_coll_own_cnt[q]; ++n) {
+                    const int slot = p->kcoll_slot[(size_t)kj * nco + AWE_N_KCOLL_HEAD + n];
+                    if (slot < 0) continue;
+                    if (slot < s0 || slot >= s1 || at[slot - s0] != -1) {
+                        set_err(h, "own CCS range: an output lies outside the columns of its chunk");
+                        return 4;
+                    }
+                    at[slot - s0] = n;
+                    own_pos[(size_t)kj * AWE_N_KCOLL_OWN + n] = (unsigned char)(slot - s0);
+                }
+                const int c0 = (int)own_cst.size();
+                for (int e = 0; e < len; ++e) {
+                    own_handled[s0 + e] = 1;
+                    if (at[e] != -1) continue;
+                    const int ce = const_of[s0 + e];
+                    if (ce < 0) {
+                        set_err(h, "own CCS range: a slot is neither an output nor a constant entry");
+                        return 4;
+                    }
+                    int cid = -1;
+                    for (size_t c = 0; c < own_cval.size(); ++c)
+                        if (own_cval[c] == p->const_val[ce]) cid = (int)c;
+                    if (cid < 0) own_cval.push_back(p->const_val[ce]), cid = (int)own_cval.size() - 1;
+                    if (cid >= OWN_NCVAL || (int)own_cst.size() - c0 >= OWN_MAXCST) {
+                        set_err(h, "own CCS range: too many constant entries");
+                        return 4;
+                    }
+                    own_cst.push_back(make_uchar2((unsigned char)e, (unsigned char)cid));
+                }
+                own_desc[(size_t)kj * AWE_K_COLL_NOWNQ + q] = make_int4((int)s0, len, c0, (int)own_cst.size() - c0);
+            }
+        }
+        own_cval.resize(OWN_NCVAL, 0.0);
+    }
     for (int k = 0; k < nk; ++k)
         for (int n = 0; n < p->n_shoot_out; ++n)
             shoot_dest[(size_t)k * p->n_shoot_out + n] =
@@ -1264,7 +1269,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
             std::vector<std::pair<long long, int>> &ent = ents[(size_t)k * AWE_K_COLL_NCHUNKS + q];
             for (int j = 0; j < dd; ++j)
                 for (int o = 0; o < awe_k_coll_chunk_cnt[q]; ++o) {
-                    const int code = coll_dest[((size_t)k * dd + j) * p->n_coll_out + awe_k_coll_chunk_first[q] + o];
+                    const int code = coll_dest[((size_t)k * dd + j) * nco + awe_k_coll_chunk_first[q] + o];
                     if (code == -1) continue;
                     // g rows first (ascending row), then CCS slots (ascending)
                     const long long key = code <= -2 ? (long long)(-2 - code) : (1ll << 40) + code;
@@ -1281,6 +1286,11 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         for (int e = p->const_begin[k]; e < p->const_begin[k + 1]; ++e) {
             const int slot = p->const_slot[e];
             const double v = p->const_val[e];
+            if (own_handled[slot]) {
+                // inside the own range of a collocation node: written by its flush; the gather kernel keeps it only
+                // for the calls that do not run the full collocation programs
+                continue;
+            }
             int target = -1;
             for (int dist = 1; coop_possible && dist <= 2 && target < 0; ++dist)
                 for (int sgn = -1; sgn <= 1 && target < 0; sgn += 2) {
@@ -1326,6 +1336,10 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     rc |= to_device(h, rest_begin.data(), rest_begin.size(), &d.rest_begin);
     rc |= to_device(h, rest_val.data(), rest_val.size(), &d.rest_val);
     rc |= to_device(h, cvals.data(), cvals.size(), &d.coop_const);
+    rc |= to_device(h, own_desc.data(), own_desc.size(), &d.own_desc);
+    rc |= to_device(h, own_pos.data(), own_pos.size(), &d.own_pos);
+    rc |= to_device(h, own_cst.data(), own_cst.size(), &d.own_cst);
+    rc |= to_device(h, own_cval.data(), own_cval.size(), &d.own_cval);
     rc |= to_device(h, p->aff_row, (size_t)p->n_aff, &d.aff_row);
     rc |= to_device(h, p->aff_begin, (size_t)p->n_aff + 1, &d.aff_begin);
     rc |= to_device(h, p->affp_begin, (size_t)p->n_aff + 1, &d.affp_begin);
@@ -1369,26 +1383,46 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     CK((attr_node_impl<true, false, 1>()));
     CK((attr_node_impl<true, false, 2>()));
     SET_SMEM(awegpu_gather_kernel<false>, gather_smem_bytes());
-#ifdef AWE_WITH_FUSED
     {
-        // fused persistent kernels (full Jacobian, instance-major): one CTA per SM
+        // persistent node kernels: one CTA per SM; the group a CTA starts with, in proportion to the cost the
+        // generator estimated for the groups of every (collocation | shooting, stage) launch
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, device));
         h->n_sm = prop.multiProcessorCount;
-        const char *ef = getenv("AWEGPU_FUSED");
-        h->fused = ef ? atoi(ef) : 0;
-        if (fused_quads<false>() < 1 || fused_quads<true>() < 1) h->fused = 0;
-        if (h->fused) {
-            SET_SMEM(awegpu_fused_kernel<false>, (fused_quads<false>() * node_smem_bytes<false, true>()));
-            SET_SMEM(awegpu_fused_kernel<true>, (fused_quads<true>() * node_smem_bytes<true, true>()));
-            const size_t line = sizeof(double) * 32;
-            CK(cudaMalloc((void **)&h->ex_coll, line * h->n_sm * fused_quads<false>() * NODE_WARPS * (AWE_K_COLL_EXPORTS ? AWE_K_COLL_EXPORTS : 1)));
-            CK(cudaMalloc((void **)&h->ex_shoot, line * h->n_sm * fused_quads<true>() * NODE_WARPS * (AWE_K_SHOOT_EXPORTS ? AWE_K_SHOOT_EXPORTS : 1)));
-        }
+        if (getenv("AWEGPU_LEAD")) h->lead_tiles = atoi(getenv("AWEGPU_LEAD"));
+        const char *en = getenv("AWEGPU_CTAS");
+        if (en && atoi(en) > 0) h->n_sm = atoi(en);
+        static const int w_full[6][MAX_GROUPS] = {AWE_K_COLL_S0_WEIGHTS, AWE_K_COLL_S1_WEIGHTS, AWE_K_COLL_S2_WEIGHTS,
+                                                  AWE_K_SHOOT_S0_WEIGHTS, AWE_K_SHOOT_S1_WEIGHTS, AWE_K_SHOOT_S2_WEIGHTS};
+        static const int w_res[6][MAX_GROUPS] = {AWE_K_COLL_RES_S0_WEIGHTS, AWE_K_COLL_RES_S1_WEIGHTS, AWE_K_COLL_RES_S2_WEIGHTS,
+                                                 AWE_K_SHOOT_RES_S0_WEIGHTS, AWE_K_SHOOT_RES_S1_WEIGHTS, AWE_K_SHOOT_RES_S2_WEIGHTS};
+        const int n_full[6] = {AWE_K_COLL_S0_GROUPS, AWE_K_COLL_S1_GROUPS, AWE_K_COLL_S2_GROUPS,
+                               AWE_K_SHOOT_S0_GROUPS, AWE_K_SHOOT_S1_GROUPS, AWE_K_SHOOT_S2_GROUPS};
+        const int n_res[6] = {AWE_K_COLL_RES_S0_GROUPS, AWE_K_COLL_RES_S1_GROUPS, AWE_K_COLL_RES_S2_GROUPS,
+                              AWE_K_SHOOT_RES_S0_GROUPS, AWE_K_SHOOT_RES_S1_GROUPS, AWE_K_SHOOT_RES_S2_GROUPS};
+        if (h->n_sm > MAX_CTAS) h->n_sm = MAX_CTAS;
+        std::vector<unsigned char> &cg = h->cta_group;
+        cg.assign((size_t)2 * 6 * h->n_sm, 0);
+        for (int f = 0; f < 2; ++f)
+            for (int kind = 0; kind < 6; ++kind) {
+                const int ng = f == 0 ? n_full[kind] : n_res[kind];
+                const int *w = f == 0 ? w_full[kind] : w_res[kind];
+                if (ng > MAX_GROUPS) {
+                    set_err(h, "more program groups than MAX_GROUPS");
+                    return 4;
+                }
+                double tot = 0, acc = 0;
+                for (int g = 0; g < ng; ++g) tot += w[g] > 0 ? w[g] : 1;
+                int g = 0;
+                // CTA c starts with the group whose share of the cumulated weight contains (c + 0.5) / n_sm
+                for (int c = 0; c < h->n_sm && ng > 0; ++c) {
+                    const double x = (c + 0.5) / h->n_sm * tot;
+                    while (g + 1 < ng && acc + (w[g] > 0 ? w[g] : 1) <= x) acc += (w[g] > 0 ? w[g] : 1), ++g;
+                    cg[((size_t)f * 6 + kind) * h->n_sm + c] = (unsigned char)g;
+                }
+            }
+        CK(cudaMalloc((void **)&h->counters, 6 * MAX_GROUPS * sizeof(int)));
     }
-#else
-    h->fused = 0;
-#endif
     SET_SMEM(awegpu_gather_kernel<AWE_BATCH_MINOR != 0>, gather_smem_bytes());
 #undef SET_SMEM
     {
@@ -1404,12 +1438,6 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
             if (ct < 1) ct = 1;
         }
         h->chunk_tiles = ct;
-        const char *ei = getenv("AWEGPU_INTERLEAVE");
-        h->interleave = ei ? atoi(ei) : 1;
-        const char *ep = getenv("AWEGPU_INTERLEAVE_PRE");
-        h->interleave_pre = ep ? atoi(ep) : 1;
-        const char *eq = getenv("AWEGPU_ILV_ITEMS");
-        h->ilv_items = eq ? atoi(eq) : 0;
     }
     // host copies of pointers are not kept: null them so nobody dereferences caller memory later
     h->host.x_base = h->host.x_next = h->host.u_base = h->host.xdot_base = h->host.z_base = nullptr;
@@ -1506,11 +1534,11 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
     do {                                                                                                          \
         if (node_groups<S_, F, T_>() > 0) {                                                                       \
             NodeLaunch a_;                                                                                        \
-            a_.grid = dim3(((n_) + NODE_WARPS - 1) / NODE_WARPS, node_groups<S_, F, T_>());                       \
-            a_.st = st_, a_.dp = dp, a_.sc = h->sc, a_.B = B, a_.b_base = b_base, a_.n_items = n_, a_.p_sh = p_sh; \
-            a_.ilv = ((T_) == 0 ? h->interleave : h->interleave_pre) * (((S_) ? dp.n_k : dp.n_k * N_D) + NODE_WARPS - 1) / NODE_WARPS; \
-            if (h->ilv_items > 0) a_.ilv = h->ilv_items;                                                          \
+            a_.n_ctas = h->n_sm, a_.st = st_, a_.dp = dp, a_.sc = h->sc, a_.B = B, a_.b_base = b_base;            \
+            a_.n_items = n_, a_.p_sh = p_sh, a_.counters = h->counters;                                           \
+            a_.cta_group = h->cta_group.data() + (size_t)((F) ? 0 : 6) * h->n_sm;                                        \
             a_.G = G, a_.Jv = jv;                                                                                 \
+            a_.lead = h->lead_tiles * ((S_) ? dp.n_k : dp.n_k * N_D) / NODE_WARPS;                                \
             launch_node<S_, F, T_>(M, a_);                                                                        \
             h->launches += 1;                                                                                     \
         }                                                                                                         \
@@ -1520,6 +1548,7 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
         const int nc_ = ct * dp.n_k * N_D, ns_ = ct * dp.n_k; \
         /* one stream: running the shooting chain beside the collocation chain was measured and */ \
         /* bought nothing (every kernel fills the SMs on its own)                                */ \
+        CK(cudaMemsetAsync(h->counters, 0, 6 * MAX_GROUPS * sizeof(int), st)); \
         LAUNCH_STAGE(false, F, 2, M, nc_, st);            \
         LAUNCH_STAGE(true, F, 2, M, ns_, st);             \
         LAUNCH_STAGE(false, F, 1, M, nc_, st);            \
@@ -1538,20 +1567,6 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
         else
             awegpu_gather_kernel<false><<<dim3(ct, dp.n_k), GATHER_THREADS, gather_smem_bytes(), st>>>(
                 dp, h->sc, B, b_base, W, P, ldp, p_off, G, jv);
-#ifdef AWE_WITH_FUSED
-        if (full && !bm && h->fused) {
-            const int nc_ = ct * dp.n_k * N_D, ns_ = ct * dp.n_k;
-            constexpr int uc_ = fused_quads<false>() * NODE_WARPS, us_ = fused_quads<true>() * NODE_WARPS;
-            const int gs_ = std::min(h->n_sm, (ns_ + us_ - 1) / us_), gc_ = std::min(h->n_sm, (nc_ + uc_ - 1) / uc_);
-            awegpu_fused_kernel<true><<<gs_, NODE_THREADS * fused_quads<true>(), fused_quads<true>() * node_smem_bytes<true, true>(), st>>>(
-                dp, h->sc, B, b_base, ns_, h->ex_shoot, G, jv);
-            if (t0 == 0) CK(cudaEventRecord(h->ev_k0, st));
-            awegpu_fused_kernel<false><<<gc_, NODE_THREADS * fused_quads<false>(), fused_quads<false>() * node_smem_bytes<false, true>(), st>>>(
-                dp, h->sc, B, b_base, nc_, h->ex_coll, G, jv);
-            if (t0 == 0) CK(cudaEventRecord(h->ev_k1, st));
-            h->launches += 2;
-        } else
-#endif
         if (full && !bm) LAUNCH_NODES(true, false);
         else if (full && bm) LAUNCH_NODES(true, true);
         else if (!full && !bm) LAUNCH_NODES(false, false);

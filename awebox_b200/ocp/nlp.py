@@ -236,6 +236,46 @@ class OcpProblem(object):
                     self.coll_out.append(('phi', i, c))
         self.eq_split = eq_split
 
+        # ---- collocation-node output list of the CUDA kernels (awebox_b200/csrc/awegpu_kernels.cu).  The thread
+        #   that evaluates node (k, j) OWNS the CCS columns of its own state block X_{j+1} and of z_{k,j}: it writes
+        #   every entry of those columns, the rows of the d-1 sibling nodes of the interval included
+        #   (d r_sib / d X_{j+1}[m] = d r/d xdot_m (at the sibling) * C[j+1, sib+1] / (h t_f): the d r/d xdot block is a
+        #   few dozen cheap entries, re-evaluated from the sibling's inputs).  With the constant continuity /
+        #   periodicity entries those columns are one contiguous range of the CCS value array per instance, which
+        #   leaves the SM as whole, aligned runs.  Everything else the node contributes ("head": residual rows, the
+        #   entries in the x_k, u_k, theta and phi columns) goes through the interval-cooperative flush.
+        #     head: ('res', i) | ('Xc', i, m, 0) | ('u', i, c) | ('theta', i, t) | ('phi', i, c)
+        #     own:  ('O', i, m)       row i of the node itself, column X_{j+1}[m]   (direct + through-xdot part)
+        #           ('S', dl, i, m)   row i of sibling (j + dl) mod d, column X_{j+1}[m]
+        #           ('z', i, c)       row i of the node itself, column z_{k,j}[c]
+        #   own outputs are listed column by column; kcoll_cols[c] = (first own output, count) of local column c
+        #   (c < n_x: X_{j+1}[c], then z)
+        self.kcoll_head = [('res', i) for i in range(self.n_eq)]
+        for mm in range(self.n_x):
+            for i in range(self.n_eq):
+                if mm in eq_split[i]['xdot']:
+                    self.kcoll_head.append(('Xc', i, mm, 0))
+        self.kcoll_head += [it for it in self.coll_out if it[0] in ('u', 'theta', 'phi')]
+        self.kcoll_own, self.kcoll_cols = [], []
+        for mm in range(self.n_x):
+            first = len(self.kcoll_own)
+            for i in range(self.n_eq):
+                if mm in eq_split[i]['x'] or mm in eq_split[i]['xdot']:
+                    self.kcoll_own.append(('O', i, mm))
+            for dl in range(1, d):
+                for i in range(self.n_eq):
+                    if mm in eq_split[i]['xdot']:
+                        self.kcoll_own.append(('S', dl, i, mm))
+            self.kcoll_cols.append((first, len(self.kcoll_own) - first))
+        for c in range(self.n_z):
+            first = len(self.kcoll_own)
+            for i in range(self.n_eq):
+                if c in eq_split[i]['z']:
+                    self.kcoll_own.append(('z', i, c))
+            self.kcoll_cols.append((first, len(self.kcoll_own) - first))
+        self.kcoll_out = self.kcoll_head + self.kcoll_own
+        self.n_kcoll_head = len(self.kcoll_head)
+
         # ---- shooting-node local outputs: residual rows then direct entries
         sh_rows = [('eq', i) for i in self.shoot_eq_rows] + [('ineq', i) for i in range(self.n_ineq)]
         self.shoot_rows = sh_rows
@@ -288,6 +328,40 @@ class OcpProblem(object):
                         col = self.x_base(k, r) + mm
                     coll_keys[k, j, n] = (row, col)
                     add(row, col)
+        kcoll_keys = np.full((n_k, d, len(self.kcoll_out), 2), -1, dtype=np.int64)
+        for k in range(n_k):
+            for j in range(d):
+                for n, item in enumerate(self.kcoll_out):
+                    kind = item[0]
+                    if kind == 'res':
+                        continue
+                    if kind == 'S':
+                        _, dl, i, mm = item
+                        sib = (j + dl) % d
+                        if C[j + 1, sib + 1] == 0.0:
+                            continue
+                        kcoll_keys[k, j, n] = (self.row_coll[k][sib] + i, self.x_base(k, j + 1) + mm)
+                        continue
+                    i = item[1]
+                    row = self.row_coll[k][j] + i
+                    if kind == 'O':
+                        mm = item[2]
+                        if not (mm in self.eq_split[i]['x'] or C[j + 1, j + 1] != 0.0):
+                            continue
+                        col = self.x_base(k, j + 1) + mm
+                    elif kind == 'Xc':
+                        if C[0, j + 1] == 0.0:
+                            continue
+                        col = self.x_base(k, 0) + item[2]
+                    elif kind == 'theta':
+                        col = int(self.theta_idx[k, item[2]])
+                    elif kind == 'phi':
+                        col = self.v_phi + item[2]
+                    elif kind == 'u':
+                        col = self.v_u[k] + item[2]
+                    else:
+                        col = self.v_cz[k][j] + item[2]
+                    kcoll_keys[k, j, n] = (row, col)
         # ---- constant entries: continuity, periodicity, t_f bounds
         const_r, const_c, const_v = [], [], []
         const_begin = []
@@ -374,6 +448,11 @@ class OcpProblem(object):
             return out.reshape(keys.shape[:-1])
 
         self.coll_slot = slots(coll_keys)            # [n_k, d, n_coll_out]   (-1: not an entry)
+        self.kcoll_slot = slots(kcoll_keys)          # [n_k, d, n_kcoll_out]  the same entries, kernel output order
+        a_ = np.sort(self.coll_slot[self.coll_slot >= 0])
+        b_ = np.sort(self.kcoll_slot[self.kcoll_slot >= 0])
+        if len(a_) != len(b_) or np.any(a_ != b_):
+            raise AssertionError('kernel output list does not cover the collocation entries exactly once')
         self.shoot_slot = slots(shoot_keys)          # [n_k, n_shoot_out]
         ck = np.stack([np.array(const_r, dtype=np.int64), np.array(const_c, dtype=np.int64)], axis=1)
         self.const_slot = slots(ck)

@@ -79,6 +79,12 @@ typedef struct awegpu_problem {
     const double  *affp_coef;       /* [affp_begin[n_aff]] */
     const double  *aff_const;       /* [n_aff] */
     double constraint_scale;
+    /* output order of the collocation-node programs of the CUDA kernels (awebox_b200/ocp/nlp.py: kcoll_out): the
+     * same structural entries as coll_slot, listed as "head" outputs (residual rows and the entries in the x_k, u_k,
+     * theta and phi columns) followed by the node's own CCS range (the columns of X_{k,j+1} and z_{k,j}, all rows,
+     * sibling nodes of the interval included) */
+    int32_t n_kcoll_out, n_kcoll_head;
+    const int32_t *kcoll_slot;      /* [n_k*d*n_kcoll_out]  CCS slot, -1 = none */
 } awegpu_problem_t;
 
 typedef struct awegpu_handle awegpu_handle_t;

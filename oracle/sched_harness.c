@@ -29,6 +29,13 @@ static const double awe_kconst[AWE_N_KCONST] = AWE_KCONST_INIT;
 #define LD_ITF(reg) reg = itf
 #define LD_TH(reg, t) reg = th[t]
 #define LD_OWN(reg, r) reg = (own_r == (r)) ? 1.0 : 0.0
+/* inputs of the sibling nodes of the interval and the coefficients of the node's own column block
+ * (awebox_b200/ocp/nlp.py: kcoll_own) */
+#define LD_XS(reg, dl, m) reg = xs[((dl) - 1) * AWE_N_X + (m)]
+#define LD_XDS(reg, dl, m) reg = xds[((dl) - 1) * AWE_N_X + (m)]
+#define LD_ZS(reg, dl, c) reg = zs[((dl) - 1) * AWE_N_Z + (c)]
+#define LD_CCO(reg) reg = cco
+#define LD_CCS(reg, dl) reg = ccs[dl]
 #define LEAF_FENCE()
 #define LD_EX(reg, i) reg = ex_[i]
 /* asynchronous input prefetch ring (awebox_b200/schedule.py: prefetch_leaves): copies complete in issue
@@ -58,6 +65,11 @@ static const double awe_kconst[AWE_N_KCONST] = AWE_KCONST_INIT;
 #define FLUSH_PREP(q, first)
 #define GROUP_INIT(q0, nq, first)
 #define FLUSH(q, first, cnt, qn, fn) do { int q_; for (q_ = 0; q_ < (cnt); ++q_) out[(first) + q_] = stg_[q_]; } while (0)
+/* own CCS range: results are returned in kernel output order (ocp.kcoll_out) */
+#define OWN_INIT(oq0, noq, ofirst, ocnt) own_first_ = (ofirst)
+#define OWN_BEGIN(q)
+#define OUTO(idx, val) out[own_first_ + (idx)] = (val)
+#define FLUSH_OWN(q)
 
 /* xo [n_x] state block of the node, xd [n_x] its time derivative, u, z, th, p [n_param], cc [d+1], itf,
  * j1 = own block index in 1..d (collocation) */
@@ -68,12 +80,13 @@ static const double awe_kconst[AWE_N_KCONST] = AWE_KCONST_INIT;
         }
 
 void sched_coll(const double *xo, const double *xd, const double *u, const double *z, const double *th,
-                const double *p, const double *cc, double itf, int own_r, double *out, int full)
+                const double *p, const double *cc, double itf, int own_r, double *out, int full,
+                const double *xs, const double *xds, const double *zs, double cco, const double *ccs)
 {
     double hot[512], cold[512], stg_[64], ex_[1024], ring[256], pf_val[4096];
     int pf_slot[4096], pf_n = 0, pf_done = 0;
-    int group;
-    (void)cold;
+    int group, own_first_ = 0;
+    (void)cold, (void)own_first_;
     if (full) {
         for (group = 0; group < AWE_K_COLL_S2_GROUPS; ++group) switch (group) {
 #include "k_coll_s2.inc"
@@ -102,11 +115,11 @@ void sched_shoot(const double *xo, const double *xd, const double *u, const doub
 {
     double hot[512], cold[512], stg_[64], ex_[1024], ring[256], pf_val[4096];
     int pf_slot[4096], pf_n = 0, pf_done = 0;
-    const double *cc = 0;
-    const double itf = 0.0;
+    const double *cc = 0, *xs = 0, *xds = 0, *zs = 0, *ccs = 0;
+    const double itf = 0.0, cco = 0.0;
     const int own_r = -1;
-    int group;
-    (void)cc, (void)itf, (void)own_r, (void)cold;
+    int group, own_first_ = 0;
+    (void)cc, (void)itf, (void)own_r, (void)cold, (void)xs, (void)xds, (void)zs, (void)ccs, (void)cco, (void)own_first_;
     if (full) {
         for (group = 0; group < AWE_K_SHOOT_S2_GROUPS; ++group) switch (group) {
 #include "k_shoot_s2.inc"

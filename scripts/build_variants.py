@@ -35,7 +35,7 @@ def main(argv):
             else:
                 k, v = kv.split('=')
                 setattr(CG, k, type(defaults[k])(v))
-        CG.NodeCode.emit_scheduled.__defaults__ = (CG.N_REGS, CG.LOOKAHEAD, CG.HOT_SLOTS, CG.CHUNK, 0, False, None, 0)
+        CG.NodeCode.emit_scheduled.__defaults__ = (CG.N_REGS, CG.LOOKAHEAD, CG.HOT_SLOTS, CG.CHUNK, 0, False, None, 0, None, None)
         g = os.path.join(pbuild.CSRC, 'gen', '_var_' + name)
         stats = CG.NodeCode(ocp).write(g)
         out = os.path.join(pbuild.LIBDIR, 'var', 'libawegpu_%s.%s.so' % (SPEC, name))
