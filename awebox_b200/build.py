@@ -65,7 +65,7 @@ def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None
     os.makedirs(LIBDIR, exist_ok=True)
     g = gen or gen_dir(spec_name)
     src = os.path.join(CSRC, 'awegpu_kernels.cu')
-    deps = [src] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
+    deps = [src] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", "_reduce.cu"))] + \
         [os.path.join(g, f) for f in sorted(os.listdir(g)) if f.endswith(('.h', '.inc'))] + \
         [os.path.join(ROOT, 'include', 'awegpu.h')]
     out = out or lib_path(spec_name)
@@ -85,8 +85,15 @@ def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None
         return tu, obj, cmd, res
 
     logs, objs = [], []
-    with ThreadPoolExecutor(N_TU) as pool:
-        results = list(pool.map(one, range(N_TU)))
+    def reduce_unit(_):
+        # model-independent kernels (awegpu_reduce.cu)
+        obj = os.path.join(objdir, 'reduce.o')
+        cmd = [nvcc] + common + ['-c', '-o', obj, os.path.join(CSRC, 'awegpu_reduce.cu')]
+        return 'reduce', obj, cmd, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(N_TU + 1) as pool:
+        futs = [pool.submit(one, tu) for tu in range(N_TU)] + [pool.submit(reduce_unit, 0)]
+        results = [f.result() for f in futs]
     for tu, obj, cmd, res in results:
         logs.append(' '.join(cmd) + '\n' + res.stdout + res.stderr)
         objs.append(obj)

@@ -14,6 +14,8 @@ AWEGPU_P_THETA0 = 4
 AWEGPU_P_SHARED = 8
 AWEGPU_SKIP_JAC = 16
 AWEGPU_HOST_PINNED = 32
+AWEGPU_RED_LAMBDA_SHARED = 1
+AWEGPU_RED_V_SHARED = 2
 
 
 class ProblemStruct(C.Structure):

@@ -35,7 +35,9 @@ def _fmt(v):
 # back-end parameters of the CUDA emission (awebox_b200/schedule.py): FP64 registers handed to the
 # allocator, reload look-ahead (statements), shared-memory scratch slots per thread, statements
 # between two CTA-wide re-convergence points (instruction-cache locality)
-N_REGS = 48          # FP64 values the allocator keeps in registers (-> ~128 registers per thread)
+N_REGS = 48          # FP64 values the allocator keeps in registers (-> 168 registers per thread, three quads per SM)
+N_REGS_FAT = 80      # the same when only two quads fit an SM (255 registers per thread)
+SMEM_PER_SM = 227 * 1024
 LOOKAHEAD = 8        # statements between a scratch reload and its first use
 LEAF_LOOKAHEAD = 40  # statements between an input load (global memory, L2 latency) and its first use
 LEAF_BURST = 40       # > 0: input loads are issued in generations of this many statements (schedule.allocate)
@@ -46,6 +48,7 @@ POOL = 0             # per-thread scratch slots shared by spills and the asynchr
 PF_AHEAD = 150       # operations between the asynchronous copy of an input and its first use
 HINT_AHEAD = 0       # > 0: L2 prefetch hint this many operations before the load of a record / export input
 GROUP_OPS = 900      # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
+_GROUP_OPS_DEFAULT = GROUP_OPS    # (an experiment that changes GROUP_OPS overrides the per-model table below)
 MAX_EXPORTS = 64     # intermediate values exported per stage (scaled up for large models, see NodeCode.plan)
 MAX_EXPORTS_SHOOT = 0 # > 0: the same for the shooting-node function (0: as MAX_EXPORTS)
 EXPORT_MIN_GAIN = 40
@@ -75,9 +78,16 @@ def _rhs(op, a, b):
                         S.ATAN: 'atan', S.EXP: 'exp', S.LOG: 'log', S.FABS: 'fabs'}[op], a)
 
 
+# per-model overrides of the parameters above, chosen by measurement on B200 (the planner's outcome is not monotone in
+# its budget: scripts/build_variants.py + scripts/gpu_variants.sh): mpc_3dof 0.81 ms per 8192-scenario step with the
+# default group budget, 0.66 ms with 1400
+TUNED = {'mpc_3dof': {'GROUP_OPS': 1400}}
+
+
 class NodeCode(object):
     def __init__(self, ocp):
         self.ocp = ocp
+        self.group_ops = TUNED.get(ocp.spec.name, {}).get('GROUP_OPS')
         m = ocp.model
         d = ocp.d
         eq, ineq = m.eq_exprs(), m.ineq_exprs()
@@ -526,7 +536,10 @@ class NodeCode(object):
         stats['outputs'] = len(exprs)
         return '\n'.join(lines) + '\n', stats
 
-    def emit_all(self):
+    def emit_all(self, n_regs_of=None):
+        """``n_regs_of``: {variant name: FP64 registers handed to the allocator} (default N_REGS everywhere)."""
+        n_regs_of = n_regs_of or {}
+        self._ktab = {}
         coll, cs = self.emit(self.coll_exprs)
         shoot, ss = self.emit(self.shoot_exprs)
         ocp = self.ocp
@@ -564,7 +577,8 @@ class NodeCode(object):
                     n_head = ocp.n_kcoll_head
                     cuts = set(range(n_head + 1)) | set(n_head + f for f, _ in ocp.kcoll_cols)
                     forced = {n_head}
-                exports, groups = self.plan(cur, max_exports=0 if level == MAX_STAGES - 1 else cap, cuts=cuts,
+                exports, groups = self.plan(cur, limit=self.group_ops if GROUP_OPS == _GROUP_OPS_DEFAULT else None,
+                                            max_exports=0 if level == MAX_STAGES - 1 else cap, cuts=cuts,
                                             forced=forced or ())
                 new = [n for n in exports if n.idx not in ex_index]
                 for n in new:
@@ -621,9 +635,11 @@ class NodeCode(object):
                             assert sum(c[2] for c in chunks) == b - a, 'empty columns inside an own group'
                             group_own.append((oq0, len(own_q) - oq0, a - n_head, b - a))
                             body, st = self.emit_scheduled(g_exprs[a:b], first=a, leaf_names=leaf_names, q0=q0, chunks=chunks,
-                                                           own_init=(oq0, len(own_q) - oq0, a, b - a))
+                                                           own_init=(oq0, len(own_q) - oq0, a, b - a),
+                                                           n_regs=n_regs_of.get(name, N_REGS))
                         elif level == 0:
-                            body, st = self.emit_scheduled(g_exprs[a:b], first=a, leaf_names=leaf_names, q0=q0)
+                            body, st = self.emit_scheduled(g_exprs[a:b], first=a, leaf_names=leaf_names, q0=q0,
+                                                           n_regs=n_regs_of.get(name, N_REGS))
                             for c0 in range(a, b, CHUNK):
                                 chunk_first.append(c0)
                                 chunk_cnt.append(min(CHUNK, b - c0))
@@ -631,7 +647,7 @@ class NodeCode(object):
                             group_own.append((len(own_q), 0, 0, 0))
                         else:
                             body, st = self.emit_scheduled(g_exprs[a:b], first=ex_index[outs[a].idx], export=True,
-                                                           leaf_names=leaf_names)
+                                                           leaf_names=leaf_names, n_regs=n_regs_of.get(name, N_REGS))
                             assert [ex_index[n.idx] for n in outs[a:b]] == list(range(ex_index[outs[a].idx],
                                                                                       ex_index[outs[a].idx] + b - a))
                         text += 'case %d: {\n%s} break;\n' % (g, body)
@@ -692,10 +708,25 @@ class NodeCode(object):
         files['model_defs.h'] = head + kdefs
         return files, stats
 
+    def emit_fitted(self):
+        """emit_all with the register budget of the full collocation / shooting programs chosen so that the persistent
+        node kernels keep as many warps per SM as possible: three quads of 168-register threads if the spill slots,
+        staging rows and tables of three quads fit the shared memory of an SM, else two quads of 255-register threads
+        (N_REGS_FAT values in registers: far fewer spill slots)."""
+        files, stats = self.emit_all()
+        fat = {}
+        for name in ('k_coll', 'k_shoot'):
+            if quad_smem_bytes(name, stats[name]['hot_slots'], files['model_defs.h']) * 3 > SMEM_PER_SM - 64:
+                fat[name] = N_REGS_FAT
+        if fat:
+            files, stats = self.emit_all(n_regs_of=fat)
+        stats['n_regs'] = {name: fat.get(name, N_REGS) for name in ('k_coll', 'k_shoot')}
+        return files, stats
+
     def write(self, out_dir):
         import os
         os.makedirs(out_dir, exist_ok=True)
-        files, stats = self.emit_all()
+        files, stats = self.emit_fitted()
         for name, text in files.items():
             path = os.path.join(out_dir, name)
             old = open(path).read() if os.path.exists(path) else None
@@ -703,6 +734,24 @@ class NodeCode(object):
                 with open(path, 'w') as f:
                     f.write(text)
         return stats
+
+
+def quad_smem_bytes(name, hot, defs):
+    """shared memory of one quad of the persistent node kernel (mirrors node_smem_bytes in awegpu_kernels.cu)."""
+    import re
+
+    def macro(key, default=0):
+        m_ = re.search(r'#define %s (\d+)' % key, defs)
+        return int(m_.group(1)) if m_ else default
+
+    stg = 4 * CHUNK * 33
+    if name == 'k_shoot':
+        return 8 * (hot * 128 + stg)
+    n_x, n_z = macro('AWE_N_X'), macro('AWE_N_Z')
+    own_tab = 16 * macro('AWE_K_COLL_MAXOWNQ', 1) + ((2 * macro('AWE_K_COLL_MAXOWN', 1) + 15) // 16) * 16 + ((4 * (n_x + n_z) + 15) // 16) * 16
+    head = stg + 8 * 33 + macro('AWE_K_COLL_MAXQ', 1) * (4 * CHUNK + 32)
+    own = 128 * (macro('AWE_OWN_RS', 2) | 1)
+    return 8 * (hot * 128 + (4 * own_tab + 7) // 8 + max(head, own))
 
 
 def flops(stats):

@@ -33,6 +33,7 @@
 #include <utility>
 
 #include "awegpu.h"
+#include "awegpu_reduce.h"
 #include "model_defs.h"
 
 // Translation units.  The generated programs make this file expensive to compile (minutes of single-threaded
@@ -1066,6 +1067,9 @@ struct awegpu_handle {
     int n_sm = 0;
     int lead_tiles = 2;           // tiles a program group may run ahead of the slowest group (AWEGPU_LEAD)
     int *counters = nullptr;      // [6][MAX_GROUPS] work counters of the persistent node kernels
+    const int *colind32 = nullptr, *row32 = nullptr;     // CCS pattern on the device (awegpu_reduce_batch)
+    double *dLam = nullptr, *dVec = nullptr, *dRed = nullptr;     // staging of awegpu_eval_batch_reduce_host
+    size_t capLam = 0, capVec = 0, capRed = 0;
     std::vector<unsigned char> cta_group;     // [2 (full | residual only)][6][n_sm] group every CTA starts with
     int n_rest = 0;          // constant Jacobian entries the cooperative flush does not carry
     int n_affp = 0;          // parameter terms of the affine rows (> 0: the full parameter vector is required)
@@ -1127,7 +1131,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     for (void *p : h->dev_allocs) cudaFree(p);
     cudaFree(h->dW), cudaFree(h->dP), cudaFree(h->dG), cudaFree(h->dJ);
     cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
-    cudaFree(h->counters);
+    cudaFree(h->counters), cudaFree(h->dLam), cudaFree(h->dVec), cudaFree(h->dRed);
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1366,6 +1370,10 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     CK(set_coeff_here(p->coeff_coll, p->coeff_cont));         // this unit's copy (gather kernel, residual-only kernels)
     h->colind.assign(p->colind, p->colind + p->n_v + 1);
     h->row.assign(p->row, p->row + p->nnz);
+    {
+        std::vector<int> c32(h->colind.begin(), h->colind.end()), r32(h->row.begin(), h->row.end());
+        if (to_device(h, c32.data(), c32.size(), &h->colind32) || to_device(h, r32.data(), r32.size(), &h->row32)) return 2;
+    }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
@@ -1717,6 +1725,96 @@ extern "C" int awegpu_eval_batch_host(awegpu_handle_t *h, int32_t B, const doubl
     CK(cudaStreamSynchronize(h->stream));
     memcpy(G, h->hG, nG * sizeof(double));
     if (want_j) memcpy(Jv, h->hJ, nJ * sizeof(double));
+    return 0;
+}
+
+// --------------------------------------------------------------------------- device-resident products (awegpu_reduce.cu)
+extern "C" int awegpu_reduce_batch(awegpu_handle_t *h, int32_t B, const double *G, const double *Jvals, const double *lambda,
+                                   const double *v, int32_t flags, double *JTl, double *Jv, double *cnorm, double *rnorm,
+                                   double *ginf, void *stream)
+{
+    if (!h) return 1;
+    if (B <= 0) return 0;
+    if (!Jvals || (ginf && !G)) {
+        set_err(h, "awegpu_reduce_batch: null Jvals (or ginf without G)");
+        return 1;
+    }
+    CK(cudaSetDevice(h->device));
+    ReduceArgs a;
+    a.B = B, a.n_v = h->dp.n_v, a.n_g = h->dp.n_g, a.nnz = h->dp.nnz;
+    a.colind = h->colind32, a.row = h->row32;
+    a.G = G, a.J = Jvals, a.lambda = lambda, a.v = v;
+    a.ld_lambda = (flags & AWEGPU_RED_LAMBDA_SHARED) ? 0 : h->dp.n_g;
+    a.ld_v = (flags & AWEGPU_RED_V_SHARED) ? 0 : h->dp.n_v;
+    a.JTl = JTl, a.Jv = Jv, a.cnorm = cnorm, a.rnorm = rnorm, a.ginf = ginf;
+    const int rc = awe_reduce_launch(stream ? (cudaStream_t)stream : h->stream, a, h->n_sm);
+    if (rc == -1) {
+        set_err(h, "awegpu_reduce_batch: the row accumulators of this problem do not fit the shared memory of an SM");
+        return 1;
+    }
+    if (rc != 0) {
+        set_err(h, std::string("awegpu_reduce_batch: ") + cudaGetErrorString((cudaError_t)rc));
+        return 2;
+    }
+    h->launches += 1;
+    return 0;
+}
+
+static int grow_dev(awegpu_handle *h, double **dev, size_t *cap, size_t need)
+{
+    if (need > *cap) {
+        if (*dev) cudaFree(*dev);
+        *dev = nullptr, *cap = 0;
+        CK(cudaMalloc((void **)dev, (need ? need : 1) * sizeof(double)));
+        *cap = need;
+    }
+    return 0;
+}
+
+// host entry: g and jac_g are evaluated and kept on the device; only g and the requested products cross PCIe
+extern "C" int awegpu_eval_batch_reduce_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P,
+                                             const double *lambda, const double *v, int32_t flags, int32_t red_flags,
+                                             double *G, double *JTl, double *Jv, double *cnorm, double *rnorm, double *ginf)
+{
+    if (!h) return 1;
+    if (B <= 0) return 0;
+    if (flags & (AWEGPU_JAC_BATCH_MINOR | AWEGPU_SKIP_JAC)) {
+        set_err(h, "awegpu_eval_batch_reduce_host: instance-major layout with Jacobian only");
+        return 1;
+    }
+    CK(cudaSetDevice(h->device));
+    const DevProblem &d = h->dp;
+    const size_t nW = (size_t)B * d.n_v;
+    const size_t p_len = (flags & AWEGPU_P_THETA0) ? d.n_theta0 : d.n_p;
+    const size_t nP = (flags & AWEGPU_P_SHARED) ? p_len : (size_t)B * p_len;
+    const size_t nG = (size_t)B * d.n_g, nJ = (size_t)B * d.nnz;
+    const size_t nL = lambda ? ((red_flags & AWEGPU_RED_LAMBDA_SHARED) ? (size_t)d.n_g : nG) : 0;
+    const size_t nV = v ? ((red_flags & AWEGPU_RED_V_SHARED) ? (size_t)d.n_v : nW) : 0;
+    // results: [JTl B n_v | Jv B n_g | cnorm B n_v | rnorm B n_g | ginf B]
+    const size_t oJTl = 0, oJv = oJTl + (JTl ? nW : 0), oCn = oJv + (Jv ? nG : 0), oRn = oCn + (cnorm ? nW : 0),
+                 oGi = oRn + (rnorm ? nG : 0), nRed = oGi + (ginf ? (size_t)B : 0);
+    int rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, nW, false) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, nP, false) |
+             grow(h, &h->dG, &h->hG, &h->capG, &h->hcapG, nG, false) | grow(h, &h->dJ, &h->hJ, &h->capJ, &h->hcapJ, nJ, false) |
+             grow_dev(h, &h->dLam, &h->capLam, nL) | grow_dev(h, &h->dVec, &h->capVec, nV) | grow_dev(h, &h->dRed, &h->capRed, nRed);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->dW, W, nW * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nL) CK(cudaMemcpyAsync(h->dLam, lambda, nL * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nV) CK(cudaMemcpyAsync(h->dVec, v, nV * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = awegpu_eval_batch(h, B, h->dW, h->dP, h->dG, h->dJ, flags, st);
+    if (rc) return rc;
+    rc = awegpu_reduce_batch(h, B, h->dG, h->dJ, nL ? h->dLam : nullptr, nV ? h->dVec : nullptr, red_flags,
+                             JTl ? h->dRed + oJTl : nullptr, Jv ? h->dRed + oJv : nullptr, cnorm ? h->dRed + oCn : nullptr,
+                             rnorm ? h->dRed + oRn : nullptr, ginf ? h->dRed + oGi : nullptr, st);
+    if (rc) return rc;
+    if (G) CK(cudaMemcpyAsync(G, h->dG, nG * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (JTl) CK(cudaMemcpyAsync(JTl, h->dRed + oJTl, nW * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (Jv) CK(cudaMemcpyAsync(Jv, h->dRed + oJv, nG * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (cnorm) CK(cudaMemcpyAsync(cnorm, h->dRed + oCn, nW * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (rnorm) CK(cudaMemcpyAsync(rnorm, h->dRed + oRn, nG * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ginf) CK(cudaMemcpyAsync(ginf, h->dRed + oGi, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return 0;
 }
 

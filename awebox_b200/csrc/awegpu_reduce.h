@@ -1,0 +1,17 @@
+// awegpu_reduce.h — interface between the C ABI (awegpu_kernels.cu) and the batch reduction kernel (awegpu_reduce.cu)
+#ifndef AWEGPU_REDUCE_H
+#define AWEGPU_REDUCE_H
+#include <cuda_runtime.h>
+
+struct ReduceArgs {
+    int B, n_v, n_g;
+    long long nnz;
+    const int *colind, *row;        // CCS pattern, int32, device
+    const double *G, *J, *lambda, *v;
+    long long ld_lambda, ld_v;      // 0: one vector shared by the batch
+    double *JTl, *Jv, *cnorm, *rnorm, *ginf;
+};
+
+// 0 = launched; -1 = the row accumulators (16 n_g bytes) do not fit the shared memory of an SM; > 0 = cudaError_t
+int awe_reduce_launch(cudaStream_t st, const ReduceArgs &a, int n_sm);
+#endif

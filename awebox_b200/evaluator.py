@@ -42,6 +42,11 @@ def load_library(spec_name):
     lib.awegpu_eval_batch_host.restype = C.c_int
     lib.awegpu_eval_batch_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int32]
+    lib.awegpu_reduce_batch.restype = C.c_int
+    lib.awegpu_reduce_batch.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 6
+    lib.awegpu_eval_batch_reduce_host.restype = C.c_int
+    lib.awegpu_eval_batch_reduce_host.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32] + \
+        [C.c_void_p] * 6
     lib.awegpu_last_eval_ms.restype = C.c_float
     lib.awegpu_last_eval_ms.argtypes = [C.c_void_p]
     lib.awegpu_last_kernel_ms.restype = C.c_float
@@ -158,6 +163,60 @@ class Evaluator(object):
         rc = self.lib.awegpu_eval_batch(self.handle, B, W.data_ptr(), P.data_ptr(), G.data_ptr(),
                                         Jv.data_ptr() if Jv is not None else None, flags, C.c_void_p(stream))
         self._check(rc, 'awegpu_eval_batch')
+
+    # ---- device-resident products for a batched consumer
+    def reduce_device(self, G, Jv, lam=None, v=None, want=('JTl', 'Jv', 'cnorm', 'rnorm', 'ginf'), stream=None):
+        """products of the Jacobians a preceding ``eval_device`` left on the device (torch CUDA tensors):
+        ``JTl = J^T lam`` [B, n_v], ``Jv = J v`` [B, n_g], column / row max-norms, ``ginf = max |g|`` [B].
+        ``lam`` [B, n_g] or [n_g], ``v`` [B, n_v] or [n_v].  -> dict of torch tensors."""
+        import torch
+        B = int(G.shape[0])
+        red = 0
+        if lam is not None and lam.dim() == 1:
+            red |= cabi.AWEGPU_RED_LAMBDA_SHARED
+        if v is not None and v.dim() == 1:
+            red |= cabi.AWEGPU_RED_V_SHARED
+        out = {}
+        shapes = {'JTl': (B, self.n_v), 'Jv': (B, self.n_g), 'cnorm': (B, self.n_v), 'rnorm': (B, self.n_g), 'ginf': (B,)}
+        for key in want:
+            if (key == 'JTl' and lam is None) or (key == 'Jv' and v is None):
+                continue
+            out[key] = torch.empty(shapes[key], dtype=torch.float64, device=G.device)
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        rc = self.lib.awegpu_reduce_batch(self.handle, B, ptr(G), ptr(Jv), ptr(lam), ptr(v), red, ptr(out.get('JTl')),
+                                          ptr(out.get('Jv')), ptr(out.get('cnorm')), ptr(out.get('rnorm')),
+                                          ptr(out.get('ginf')), st)
+        self._check(rc, 'awegpu_reduce_batch')
+        return out
+
+    def eval_reduce(self, W, P, lam=None, v=None, want=('JTl', 'Jv', 'cnorm', 'rnorm', 'ginf')):
+        """host entry: g and the products (numpy); the Jacobian values never leave the device."""
+        W = np.ascontiguousarray(np.atleast_2d(np.asarray(W, dtype=np.float64)))
+        B = W.shape[0]
+        P = np.ascontiguousarray(np.asarray(P, dtype=np.float64))
+        flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        red = 0
+        if lam is not None:
+            lam = np.ascontiguousarray(np.asarray(lam, dtype=np.float64))
+            red |= cabi.AWEGPU_RED_LAMBDA_SHARED if lam.ndim == 1 else 0
+        if v is not None:
+            v = np.ascontiguousarray(np.asarray(v, dtype=np.float64))
+            red |= cabi.AWEGPU_RED_V_SHARED if v.ndim == 1 else 0
+        G = np.empty((B, self.n_g))
+        shapes = {'JTl': (B, self.n_v), 'Jv': (B, self.n_g), 'cnorm': (B, self.n_v), 'rnorm': (B, self.n_g), 'ginf': (B,)}
+        out = {}
+        for key in want:
+            if (key == 'JTl' and lam is None) or (key == 'Jv' and v is None):
+                continue
+            out[key] = np.empty(shapes[key])
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        rc = self.lib.awegpu_eval_batch_reduce_host(self.handle, B, ptr(W), ptr(P), ptr(lam), ptr(v), flags, red, ptr(G),
+                                                    ptr(out.get('JTl')), ptr(out.get('Jv')), ptr(out.get('cnorm')),
+                                                    ptr(out.get('rnorm')), ptr(out.get('ginf')))
+        self._check(rc, 'awegpu_eval_batch_reduce_host')
+        out['G'] = G
+        return out
 
     def last_eval_ms(self):
         return float(self.lib.awegpu_last_eval_ms(self.handle))

@@ -121,6 +121,25 @@ int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W, const doub
 int awegpu_eval_batch_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P,
                            double *G, double *Jv, int32_t flags);
 
+/* Device-resident products of a batch for an on-device consumer (a batched solver; the sequel to
+ * awebox/sweep.py:117-204 and awebox/pmpc.py:221-302), O(n_v + n_g) values per instance instead of O(nnz):
+ *   JTl   [B, n_v] = J_b^T lambda_b      lambda [B, n_g] (or one vector with AWEGPU_RED_LAMBDA_SHARED)
+ *   Jv    [B, n_g] = J_b v_b             v [B, n_v]      (or one vector with AWEGPU_RED_V_SHARED)
+ *   cnorm [B, n_v], rnorm [B, n_g]       max |J_b| per column / per row
+ *   ginf  [B]                            max |g_b|
+ * G [B, n_g] and Jvals [B, nnz] are what awegpu_eval_batch wrote (instance-major); all pointers are device
+ * pointers; any output (and lambda / v with the outputs that need them) may be NULL. */
+#define AWEGPU_RED_LAMBDA_SHARED 1
+#define AWEGPU_RED_V_SHARED      2
+int awegpu_reduce_batch(awegpu_handle_t *h, int32_t B, const double *G, const double *Jvals, const double *lambda,
+                        const double *v, int32_t red_flags, double *JTl, double *Jv, double *cnorm, double *rnorm,
+                        double *ginf, void *stream);
+/* Host-pointer entry (pinned or pageable buffers): evaluates g and jac_g on the device, keeps the Jacobian values
+ * there and returns g [B, n_g] and the requested products only.  flags: as awegpu_eval_batch (instance-major). */
+int awegpu_eval_batch_reduce_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P,
+                                  const double *lambda, const double *v, int32_t flags, int32_t red_flags,
+                                  double *G, double *JTl, double *Jv, double *cnorm, double *rnorm, double *ginf);
+
 /* device time of the most recent eval (ms, CUDA events on the launching stream); <0 if none */
 float awegpu_last_eval_ms(awegpu_handle_t *h);
 /* device time of the dominant kernel (collocation-node programs, output stage) of the first chunk of the

@@ -319,3 +319,67 @@ def test_casadi_external_abi():
     arg0 = (PD * 3)(None, p.ctypes.data_as(PD), None)
     res = (PD * 2)(g.ctypes.data_as(PD), None)
     assert lib.awegpu_g(arg0, res, None, None, 0) != 0
+
+
+# ---------------------------------------------------------------------------------------------- device-resident products
+def _csc(ocp, jv):
+    import scipy.sparse as sp
+    return sp.csc_matrix((jv, ocp.row, ocp.colind), shape=(ocp.n_g, ocp.n_v))
+
+
+@pytest.mark.parametrize('name,n_k,B,shared', [('ampyx_ap2', 4, 37, False), ('ampyx_ap2', 40, 9, True),
+                                               ('dual_kites', 3, 33, False), ('mpc_3dof', 10, 65, True)])
+def test_reduced_products_against_the_checker(name, n_k, B, shared):
+    """awegpu_eval_batch_reduce_host (g, J^T lambda, J v, row / column max-norms, max |g|; the Jacobian values stay
+    on the device) against the same products formed on the host from the checker's Jacobian."""
+    ev = evaluator(name, n_k)
+    ocp = ev.ocp
+    W = synthetic.batch(ocp, B, seed=77)
+    p = ocp.default_p()
+    if ocp.needs_full_p:
+        P = np.tile(p, (B, 1))
+        G0, J0 = get_oracle(name, n_k).eval(W, P)
+    else:
+        P = p
+        G0, J0 = get_oracle(name, n_k).eval(W, p, flags=cabi.AWEGPU_P_SHARED)
+    rng = np.random.default_rng(5)
+    lam = rng.standard_normal(ocp.n_g) if shared else rng.standard_normal((B, ocp.n_g))
+    v = rng.standard_normal(ocp.n_v) if shared else rng.standard_normal((B, ocp.n_v))
+    out = ev.eval_reduce(W, P, lam=lam, v=v)
+    assert np.all(np.abs(out['G'] - G0) <= 1e-12 * np.maximum(1.0, np.abs(G0)))
+    for b in range(B):
+        J = _csc(ocp, J0[b])
+        A = abs(J)
+        lb, vb = (lam if shared else lam[b]), (v if shared else v[b])
+        # sums of products: tolerance relative to the sum of the magnitudes of the terms
+        jtl, jtl_mag = J.T @ lb, A.T @ np.abs(lb)
+        assert np.all(np.abs(out['JTl'][b] - jtl) <= 1e-12 * np.maximum(1.0, jtl_mag))
+        jv, jv_mag = J @ vb, A @ np.abs(vb)
+        assert np.all(np.abs(out['Jv'][b] - jv) <= 1e-12 * np.maximum(1.0, jv_mag))
+        cn = np.asarray(A.max(axis=0).todense()).ravel()
+        rn = np.asarray(A.max(axis=1).todense()).ravel()
+        assert np.all(np.abs(out['cnorm'][b] - cn) <= 1e-12 * np.maximum(1.0, cn))
+        assert np.all(np.abs(out['rnorm'][b] - rn) <= 1e-12 * np.maximum(1.0, rn))
+        assert abs(out['ginf'][b] - np.max(np.abs(G0[b]))) <= 1e-12 * max(1.0, np.max(np.abs(G0[b])))
+
+
+def test_reduced_products_device_entry_matches_host_entry():
+    import torch
+    ev = evaluator('ampyx_ap2', 40)
+    ocp = ev.ocp
+    B = 70
+    W = synthetic.batch(ocp, B, seed=78)
+    p = ocp.default_p()
+    rng = np.random.default_rng(6)
+    lam, v = rng.standard_normal((B, ocp.n_g)), rng.standard_normal(ocp.n_v)
+    ref = ev.eval_reduce(W, p, lam=lam, v=v)
+    dW, dP = torch.from_numpy(W).cuda(), torch.from_numpy(p).cuda()
+    dG = torch.empty((B, ocp.n_g), dtype=torch.float64, device='cuda')
+    dJ = torch.empty((B, ocp.nnz), dtype=torch.float64, device='cuda')
+    ev.eval_device(dW, dP, dG, dJ)
+    out = ev.reduce_device(dG, dJ, lam=torch.from_numpy(lam).cuda(), v=torch.from_numpy(v).cuda())
+    torch.cuda.synchronize()
+    for key in ('JTl', 'cnorm', 'rnorm', 'ginf'):
+        assert np.array_equal(out[key].cpu().numpy(), ref[key]), key
+    # J v is accumulated with shared-memory atomics: the order of the additions is not fixed
+    assert np.all(np.abs(out['Jv'].cpu().numpy() - ref['Jv']) <= 1e-12 * np.maximum(1.0, np.abs(ref['Jv'])))
