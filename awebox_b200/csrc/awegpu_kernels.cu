@@ -127,10 +127,15 @@ __constant__ double c_coeff_coll[(N_D + 1) * (N_D + 1)];
 __constant__ double c_coeff_cont[N_D + 1];
 
 #define SIGN(x) ((double)(((x) > 0.0) - ((x) < 0.0)))
-// Reciprocal / reciprocal square root from the MUFU seed (>= 20 bits) and two Newton steps, without
-// the special-case paths of the CUDA library versions (their arguments here are norms, squared
-// norms + eps, densities, times: finite, normal and positive).  Division and square root get one
-// extra residual correction, which leaves them within 1 ulp of the correctly rounded result.
+// Reciprocal / reciprocal square root from the MUFU seed (>= 20 bits) and two Newton steps, without the
+// special-case paths of the CUDA library versions.  Division and square root get one extra residual
+// correction, which leaves them within 1 ulp of the correctly rounded result for finite, normal arguments
+// (norms, squared norms + eps, densities, times).  Degenerate arguments: x / 0, x / inf, rsqrt(0), sqrt(inf) and
+// NaN arguments give NaN where IEEE arithmetic gives +-inf, 0 or NaN -- the same set of non-finite results except
+// for x / inf -- and sqrt(0) = 0 exactly (the seed is clamped), so that a zero norm stays a zero norm; denormal
+// arguments are read as zero.  Testing every division and root for these cases (a compare, a branch and an
+// out-of-line IEEE sequence per operation) was measured: 7 % (AP2) to 15 % (3-DOF) of the step, and rejected;
+// tests/test_gpu_parity.py::test_non_finite_and_degenerate_inputs_match_the_checker pins the behaviour.
 __device__ __forceinline__ double rcp_nr(const double x)
 {
     double r;
@@ -157,7 +162,13 @@ __device__ __forceinline__ double rsqrt_nr(const double x)
 }
 __device__ __forceinline__ double sqrt_nr(const double x)
 {
-    const double y = rsqrt_nr(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fmin(y, 1e300);                         // rsqrt(0) = inf: keep 0 * y = 0
+    double e = fma(-x * y, y, 1.0);
+    y = fma(y * 0.5, e, y);
+    e = fma(-x * y, y, 1.0);
+    y = fma(y * 0.5, e, y);
     const double s = x * y;
     return fma(fma(-s, s, x), 0.5 * y, s);
 }
@@ -1793,28 +1804,63 @@ extern "C" int awegpu_eval_batch_reduce_host(awegpu_handle_t *h, int32_t B, cons
     // results: [JTl B n_v | Jv B n_g | cnorm B n_v | rnorm B n_g | ginf B]
     const size_t oJTl = 0, oJv = oJTl + (JTl ? nW : 0), oCn = oJv + (Jv ? nG : 0), oRn = oCn + (cnorm ? nW : 0),
                  oGi = oRn + (rnorm ? nG : 0), nRed = oGi + (ginf ? (size_t)B : 0);
+    // instances per pipeline chunk: H2D of chunk c+1, the kernels of chunk c and D2H of chunk c-1 overlap on three
+    // streams (caller buffers should be page-locked for that; pageable buffers work, without overlap)
+    static const int chunk_env = getenv("AWEGPU_COPY_CHUNK") ? atoi(getenv("AWEGPU_COPY_CHUNK")) : 0;
+    const int chunk = chunk_env > 0 ? chunk_env : 512;
+    const int n_chunks = (B + chunk - 1) / chunk;
+    const size_t cb = (size_t)(B < chunk ? B : chunk);
     int rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, nW, false) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, nP, false) |
-             grow(h, &h->dG, &h->hG, &h->capG, &h->hcapG, nG, false) | grow(h, &h->dJ, &h->hJ, &h->capJ, &h->hcapJ, nJ, false) |
+             grow(h, &h->dG, &h->hG, &h->capG, &h->hcapG, nG, false) |
+             grow(h, &h->dJ, &h->hJ, &h->capJ, &h->hcapJ, cb * d.nnz, false) |       // one chunk: consumed on the device
              grow_dev(h, &h->dLam, &h->capLam, nL) | grow_dev(h, &h->dVec, &h->capVec, nV) | grow_dev(h, &h->dRed, &h->capRed, nRed);
     if (rc) return rc;
+    if (!h->stream_in) CK(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
+    if (!h->stream_out) CK(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+    while ((int)h->ev_pool.size() < 2 * n_chunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_pool.push_back(e);
+    }
+    const bool p_shared = (flags & AWEGPU_P_SHARED) != 0, l_shared = (red_flags & AWEGPU_RED_LAMBDA_SHARED) != 0,
+               v_shared = (red_flags & AWEGPU_RED_V_SHARED) != 0;
     cudaStream_t st = h->stream;
-    CK(cudaMemcpyAsync(h->dW, W, nW * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (nL) CK(cudaMemcpyAsync(h->dLam, lambda, nL * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (nV) CK(cudaMemcpyAsync(h->dVec, v, nV * sizeof(double), cudaMemcpyHostToDevice, st));
-    rc = awegpu_eval_batch(h, B, h->dW, h->dP, h->dG, h->dJ, flags, st);
-    if (rc) return rc;
-    rc = awegpu_reduce_batch(h, B, h->dG, h->dJ, nL ? h->dLam : nullptr, nV ? h->dVec : nullptr, red_flags,
-                             JTl ? h->dRed + oJTl : nullptr, Jv ? h->dRed + oJv : nullptr, cnorm ? h->dRed + oCn : nullptr,
-                             rnorm ? h->dRed + oRn : nullptr, ginf ? h->dRed + oGi : nullptr, st);
-    if (rc) return rc;
-    if (G) CK(cudaMemcpyAsync(G, h->dG, nG * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (JTl) CK(cudaMemcpyAsync(JTl, h->dRed + oJTl, nW * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (Jv) CK(cudaMemcpyAsync(Jv, h->dRed + oJv, nG * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (cnorm) CK(cudaMemcpyAsync(cnorm, h->dRed + oCn, nW * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (rnorm) CK(cudaMemcpyAsync(rnorm, h->dRed + oRn, nG * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (ginf) CK(cudaMemcpyAsync(ginf, h->dRed + oGi, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (p_shared) CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nL && l_shared) CK(cudaMemcpyAsync(h->dLam, lambda, nL * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nV && v_shared) CK(cudaMemcpyAsync(h->dVec, v, nV * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int c = 0; c < n_chunks; ++c) {
+        const size_t b0 = (size_t)c * chunk;
+        const size_t nb = (size_t)B - b0 < (size_t)chunk ? (size_t)B - b0 : (size_t)chunk;
+        CK(cudaMemcpyAsync(h->dW + b0 * d.n_v, W + b0 * d.n_v, nb * d.n_v * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        if (!p_shared)
+            CK(cudaMemcpyAsync(h->dP + b0 * p_len, P + b0 * p_len, nb * p_len * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        if (nL && !l_shared)
+            CK(cudaMemcpyAsync(h->dLam + b0 * d.n_g, lambda + b0 * d.n_g, nb * d.n_g * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        if (nV && !v_shared)
+            CK(cudaMemcpyAsync(h->dVec + b0 * d.n_v, v + b0 * d.n_v, nb * d.n_v * sizeof(double), cudaMemcpyHostToDevice, h->stream_in));
+        CK(cudaEventRecord(h->ev_pool[2 * c], h->stream_in));
+        CK(cudaStreamWaitEvent(st, h->ev_pool[2 * c], 0));
+        rc = awegpu_eval_batch(h, (int)nb, h->dW + b0 * d.n_v, p_shared ? h->dP : h->dP + b0 * p_len, h->dG + b0 * d.n_g, h->dJ, flags, st);
+        if (rc) return rc;
+        rc = awegpu_reduce_batch(h, (int)nb, h->dG + b0 * d.n_g, h->dJ, nL ? (l_shared ? h->dLam : h->dLam + b0 * d.n_g) : nullptr,
+                                 nV ? (v_shared ? h->dVec : h->dVec + b0 * d.n_v) : nullptr, red_flags,
+                                 JTl ? h->dRed + oJTl + b0 * d.n_v : nullptr, Jv ? h->dRed + oJv + b0 * d.n_g : nullptr,
+                                 cnorm ? h->dRed + oCn + b0 * d.n_v : nullptr, rnorm ? h->dRed + oRn + b0 * d.n_g : nullptr,
+                                 ginf ? h->dRed + oGi + b0 : nullptr, st);
+        if (rc) return rc;
+        CK(cudaEventRecord(h->ev_pool[2 * c + 1], st));
+        CK(cudaStreamWaitEvent(h->stream_out, h->ev_pool[2 * c + 1], 0));
+        cudaStream_t so = h->stream_out;
+        if (G) CK(cudaMemcpyAsync(G + b0 * d.n_g, h->dG + b0 * d.n_g, nb * d.n_g * sizeof(double), cudaMemcpyDeviceToHost, so));
+        if (JTl) CK(cudaMemcpyAsync(JTl + b0 * d.n_v, h->dRed + oJTl + b0 * d.n_v, nb * d.n_v * sizeof(double), cudaMemcpyDeviceToHost, so));
+        if (Jv) CK(cudaMemcpyAsync(Jv + b0 * d.n_g, h->dRed + oJv + b0 * d.n_g, nb * d.n_g * sizeof(double), cudaMemcpyDeviceToHost, so));
+        if (cnorm) CK(cudaMemcpyAsync(cnorm + b0 * d.n_v, h->dRed + oCn + b0 * d.n_v, nb * d.n_v * sizeof(double), cudaMemcpyDeviceToHost, so));
+        if (rnorm) CK(cudaMemcpyAsync(rnorm + b0 * d.n_g, h->dRed + oRn + b0 * d.n_g, nb * d.n_g * sizeof(double), cudaMemcpyDeviceToHost, so));
+        if (ginf) CK(cudaMemcpyAsync(ginf + b0, h->dRed + oGi + b0, nb * sizeof(double), cudaMemcpyDeviceToHost, so));
+    }
+    CK(cudaStreamSynchronize(h->stream_in));
     CK(cudaStreamSynchronize(st));
+    CK(cudaStreamSynchronize(h->stream_out));
     return 0;
 }
 

@@ -12,6 +12,6 @@ struct ReduceArgs {
     double *JTl, *Jv, *cnorm, *rnorm, *ginf;
 };
 
-// 0 = launched; -1 = the row accumulators (16 n_g bytes) do not fit the shared memory of an SM; > 0 = cudaError_t
+// 0 = launched; > 0 = cudaError_t
 int awe_reduce_launch(cudaStream_t st, const ReduceArgs &a, int n_sm);
 #endif

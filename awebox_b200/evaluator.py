@@ -183,7 +183,8 @@ class Evaluator(object):
                 continue
             out[key] = torch.empty(shapes[key], dtype=torch.float64, device=G.device)
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream)
+        st = stream.cuda_stream if stream is not None else torch.cuda.current_stream(G.device).cuda_stream
+        st = C.c_void_p(st if st else 1)           # legacy NULL stream by name, as in eval_device
         rc = self.lib.awegpu_reduce_batch(self.handle, B, ptr(G), ptr(Jv), ptr(lam), ptr(v), red, ptr(out.get('JTl')),
                                           ptr(out.get('Jv')), ptr(out.get('cnorm')), ptr(out.get('rnorm')),
                                           ptr(out.get('ginf')), st)

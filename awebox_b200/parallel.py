@@ -37,6 +37,24 @@ def gather_results(local, B, group=None):
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
 
 
+def gather_to_root(local, B, root=0, group=None):
+    """gather the per-rank blocks ``local [b_r, n]`` on ``root`` only -> ``[B, n]`` there, None elsewhere (the
+    "NCCL over NVLink only to gather per-shard results" step of BASELINE.json: north_star)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = shard_sizes(B, world)
+    pad, n = max(sizes), local.shape[1]
+    buf = local.contiguous()
+    if local.shape[0] != pad:
+        buf = torch.zeros((pad, n), dtype=local.dtype, device=local.device)
+        buf[:local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == root else None
+    dist.gather(buf, parts, dst=root, group=group)
+    if rank != root:
+        return None
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
 def checksum(local, group=None):
     """order-independent checksum of the whole batch result (sum over ranks of the local sums)."""
     s = local.sum(dtype=torch.float64).reshape(1).clone()

@@ -134,3 +134,14 @@ def scenario_params(ocp, W, seed, rel=1e-2):
         iu = ocp.p_theta0 + ocp.spec.theta0_labels.index('[theta0,wind,u_ref,0]')
         P[:, iu] *= 1.0 + rel * rng.uniform(-1.0, 1.0, B)
     return P
+
+
+def power_curve_params(ocp, B, n_speeds=64, lo=5.0, hi=8.0, first=0):
+    """per-instance theta0 vectors of a power-curve batch (BASELINE.json configs[3]; the sweep of
+    examples/dual_kites_power_curve.py:44-52 over ``params.wind.u_ref``): instance ``first + i`` of the global batch
+    gets wind speed number ``(first + i) mod n_speeds`` of ``linspace(lo, hi, n_speeds)``.  -> [B, n_theta0]"""
+    P = np.tile(np.asarray(ocp.spec.theta0_values, dtype=float), (B, 1))
+    iu = ocp.spec.theta0_labels.index('[theta0,wind,u_ref,0]')
+    speeds = np.linspace(lo, hi, n_speeds)
+    P[:, iu] = speeds[(first + np.arange(B)) % n_speeds]
+    return P

@@ -26,8 +26,20 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# BASELINE.json configs -> (spec, n_k, instances per GPU (None: total / world), parameter mode, scaling, description)
+CONFIGS = {
+    'ampyx_ap2': ('ampyx_ap2', 40, 4096, 'shared', 'weak',
+                  'ampyx_ap2 OCP (Radau d=4, n_k=40): batched g+jac_g at 4096 perturbed primal points per GPU'),
+    'dual_kites': ('dual_kites', 20, 4096, 'shared', 'weak',
+                   'dual-kite lift-mode reel-out OCP (Radau d=4, n_k=20): batched g+jac_g at 4096 perturbed primal points per GPU'),
+    'power_curve': ('dual_kites', 20, 4096, 'theta0', 'weak',
+                    'dual-kite power curve: 64 wind speeds x 64 perturbed primal points per GPU, per-instance theta0 (wind.u_ref)'),
+    'mpc_3dof': ('mpc_3dof', 10, None, 'full', 'strong',
+                 'tracking MPC (3-DOF, N=10): 8192 scenario evaluations per step over all GPUs, per-instance parameter vectors'),
+}
+MPC_SCENARIOS = 8192
 SPEC, N_K, BATCH = 'ampyx_ap2', 40, 4096
-WORKLOAD = 'ampyx_ap2 OCP (Radau d=4, n_k=40): batched g+jac_g at 4096 perturbed primal points per GPU'
+WORKLOAD = CONFIGS['ampyx_ap2'][5]
 
 
 def measured_peak():
@@ -36,6 +48,22 @@ def measured_peak():
         with open(path) as f:
             return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def measured_fp64_peak():
+    """vector-FP64 peak of this pool's B200 (TFLOP/s), measured with independent DFMA chains on every SM
+    (scripts/ubench/ubench.cu, result committed under profiles/)."""
+    path = os.path.join(ROOT, 'profiles', 'r02_ubench.jsonl')
+    best = None
+    if os.path.exists(path):
+        for line in open(path):
+            try:
+                d = json.loads(line)
+            except ValueError:
+                continue
+            if d.get('bench') == 'fp64':
+                best = max(best or 0.0, float(d['tflops']))
+    return (best, 'measured (profiles/r02_ubench.jsonl)') if best else (37.2, 'nominal (148 SM x 64 FMA/clk x 1.965 GHz)')
 
 
 class ClockSampler(threading.Thread):
@@ -94,18 +122,30 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.samples), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
-def cpu_leg(ocp, n_threads, budget_s, W, p):
+def make_inputs(cfg, ocp, B, rank, first=0):
+    """synthetic inputs of one rank: W [B, n_v], P (shared vector | [B, n_theta0] | [B, n_p]), cabi parameter flags"""
+    from awebox_b200 import synthetic, cabi
+    mode = CONFIGS[cfg][3]
+    W = synthetic.batch(ocp, B, seed=20261018 + 2 + 1000 * rank)
+    if mode == 'shared':
+        return W, ocp.default_p(), cabi.AWEGPU_P_SHARED
+    if mode == 'theta0':
+        return W, synthetic.power_curve_params(ocp, B, first=first), cabi.AWEGPU_P_THETA0
+    return W, synthetic.scenario_params(ocp, W, seed=99 + rank), 0
+
+
+def cpu_leg(ocp, n_threads, budget_s, W, P, flags):
     """time the CPU port on a bounded sample; returns (node-evals/s, seconds, instances, threads)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import build_oracle
-    from awebox_b200 import cabi
     orc = build_oracle.Oracle(ocp)
-    sample = W[:256]
-    orc.eval(sample, p, flags=cabi.AWEGPU_P_SHARED, n_threads=n_threads)      # warm-up
+    n = min(256, W.shape[0])
+    sample, psample = W[:n], (P if P.ndim == 1 else P[:n])
+    orc.eval(sample, psample, flags=flags, n_threads=n_threads)      # warm-up
     t0 = time.perf_counter()
     done = 0
     while True:
-        orc.eval(sample, p, flags=cabi.AWEGPU_P_SHARED, n_threads=n_threads)
+        orc.eval(sample, psample, flags=flags, n_threads=n_threads)
         done += sample.shape[0]
         dt = time.perf_counter() - t0
         if dt >= budget_s:
@@ -120,18 +160,16 @@ def run_reference(args, json_out):
         return
     from awebox_b200.spec import ModelSpec
     from awebox_b200.ocp.nlp import OcpProblem
-    from awebox_b200 import synthetic
-    ocp = OcpProblem(ModelSpec.load(SPEC), n_k=N_K)
-    W = synthetic.batch(ocp, 256, seed=20261018 + 2)
-    p = ocp.default_p()
+    spec, n_k, _, _, scaling, workload = CONFIGS[args.config]
+    ocp = OcpProblem(ModelSpec.load(spec), n_k=n_k)
+    W, P, flags = make_inputs(args.config, ocp, 256, 0)
     threads = os.cpu_count()
     per_step = max(1.0, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        cpu_leg(ocp, threads, 0.2, W, p)
-    vals, secs, inst = [], 0.0, 0
+        cpu_leg(ocp, threads, 0.2, W, P, flags)
+    secs, inst = 0.0, 0
     for _ in range(args.steps):
-        v, dt, n, _ = cpu_leg(ocp, threads, per_step / 2, W, p)
-        vals.append(v)
+        v, dt, n, _ = cpu_leg(ocp, threads, per_step / 2, W, P, flags)
         secs += dt
         inst += n
     value = inst * ocp.n_k * ocp.d / secs
@@ -139,8 +177,8 @@ def run_reference(args, json_out):
     line = {
         'impl': 'reference', 'metric': 'collocation-node g+Jacobian evals/s', 'value': value, 'unit': 'node-evals/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / max(1, args.steps),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'n_k': N_K, 'd': ocp.d, 'n_v': ocp.n_v, 'n_g': ocp.n_g, 'nnz': int(ocp.nnz)},
+        'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': workload, 'n_k': n_k, 'd': ocp.d, 'n_v': ocp.n_v, 'n_g': ocp.n_g, 'nnz': int(ocp.nnz)},
         'cpu_baseline': {'value': value, 'unit': 'node-evals/s', 'cores': threads, 'kind': 'port', 'sample': sample,
                          'note': 'plain-C port of the path (gcc -O2, OpenMP over instances); CasADi 3.6.4 itself is '
                                  'not installable on this box'},
@@ -190,7 +228,11 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=BATCH, help='instances per GPU')
+    ap.add_argument('--config', default='ampyx_ap2', choices=sorted(CONFIGS),
+                    help='BASELINE.json configs: ampyx_ap2 = configs[1] (the metric), dual_kites = [2], power_curve = [3], mpc_3dof = [4]')
+    ap.add_argument('--batch', type=int, default=0, help='instances per GPU (0: the configuration\'s own)')
+    ap.add_argument('--gather', default='none', choices=['none', 'root', 'all'],
+                    help='also time the NCCL gather of the per-rank results (g and the reduced products) after a step')
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--layout', default='instance', choices=['instance', 'batch-minor'],
@@ -205,7 +247,7 @@ def main():
     import torch
     import torch.distributed as dist
     from awebox_b200.evaluator import Evaluator
-    from awebox_b200 import synthetic, cabi
+    from awebox_b200 import cabi, parallel
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -216,14 +258,21 @@ def main():
     affinity_before, numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else (None, None)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    ev = Evaluator(SPEC, n_k=N_K, device=local_rank)
+    spec, n_k, per_gpu, p_mode, scaling, workload = CONFIGS[args.config]
+    ev = Evaluator(spec, n_k=n_k, device=local_rank)
     ocp = ev.ocp
-    B = args.batch
-    # weak scaling: rank r owns instances [r*B, (r+1)*B) of the global batch of world*B instances
-    W = synthetic.batch(ocp, B, seed=20261018 + 2 + 1000 * rank)
-    p = ocp.default_p()
+    if per_gpu is None:
+        # strong scaling: the scenario batch is split over the ranks
+        lo, hi = parallel.shard_range(MPC_SCENARIOS, rank, world)
+        B, B_total, first = hi - lo, MPC_SCENARIOS, lo
+    else:
+        B = args.batch or per_gpu
+        B_total, first = B * world, B * rank
+    if args.batch and per_gpu is None:
+        B, B_total, first = args.batch, args.batch * world, args.batch * rank
+    W, P, pflags = make_inputs(args.config, ocp, B, rank, first=first)
     dW = torch.from_numpy(W).cuda()
-    dP = torch.from_numpy(p).cuda()
+    dP = torch.from_numpy(P).cuda()
     dG = torch.empty((B, ocp.n_g), dtype=torch.float64, device='cuda')
     dJ = torch.empty((B, ocp.nnz), dtype=torch.float64, device='cuda')
     stream = torch.cuda.current_stream()
@@ -238,7 +287,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches0 = ev.launch_count()
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -262,19 +316,60 @@ def main():
         step_ms.append(ev.last_eval_ms())
         kernel_ms.append(ev.last_kernel_ms())
     sampler.stop_flag = True
-    t = torch.tensor([total_ms], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    nodes_per_step = world * B * ocp.n_k * ocp.d
+    total_ms = max_over_ranks(total_ms)
+    nodes_per_step = B_total * ocp.n_k * ocp.d
     value = nodes_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- device-resident products (J^T lambda, J v, norms): the on-device consumer's view of a step
+    rng = np.random.default_rng(4 + rank)
+    lam = torch.from_numpy(rng.standard_normal((B, ocp.n_g))).cuda()
+    vec = torch.from_numpy(rng.standard_normal((B, ocp.n_v))).cuda()
+    red = None
+    red_ms = None
+    if not args.no_jac and not bm:
+        for _ in range(2):
+            red = ev.reduce_device(dG, dJ, lam=lam, v=vec)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        for _ in range(5):
+            red = ev.reduce_device(dG, dJ, lam=lam, v=vec)
+        r1.record(stream)
+        torch.cuda.synchronize()
+        red_ms = r0.elapsed_time(r1) / 5
+
+    # ---- NCCL gather of the per-rank results (north_star: "NCCL over NVLink used only to gather per-shard results")
+    gather = None
+    if args.gather != 'none' and world > 1:
+        def do_gather(t):
+            return parallel.gather_to_root(t, B_total) if args.gather == 'root' else parallel.gather_results(t, B_total)
+        items = {'g': dG}
+        if red is not None:
+            items.update({'JTl': red['JTl'], 'Jv': red['Jv']})
+        gather = {'mode': args.gather}
+        for key, t in items.items():
+            do_gather(t)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(3):
+                out = do_gather(t)
+            g1.record(stream)
+            barrier()
+            ms = max_over_ranks(g0.elapsed_time(g1) / 3)
+            nbytes = B_total * t.shape[1] * 8
+            gather[key] = {'ms': ms, 'bytes': int(nbytes), 'GBps_into_a_rank': nbytes * (world - 1) / world / (ms * 1e-3) / 1e9}
+            del out
+        gather['limiter'] = ('the receiving GPU\'s NVLink ingress (nominal 900 GB/s per direction, 770 GB/s measured peer copy)'
+                             ' and NCCL launch latency at these sizes')
+        # the full Jacobian value arrays are not gathered: they stay sharded for the on-device consumer
 
     # ---- end to end through the host-buffer entry (pinned host memory)
     hW = torch.from_numpy(W).pin_memory()
-    hP = torch.from_numpy(p).pin_memory()
+    hP = torch.from_numpy(P).pin_memory()
     hG = torch.empty((B, ocp.n_g), dtype=torch.float64).pin_memory()
     hJ = torch.empty((B, ocp.nnz), dtype=torch.float64).pin_memory()
-    flags = cabi.AWEGPU_P_SHARED | cabi.AWEGPU_HOST_PINNED
+    flags = pflags | cabi.AWEGPU_HOST_PINNED
 
     def e2e_step():
         rc = ev.lib.awegpu_eval_batch_host(ev.handle, B, hW.data_ptr(), hP.data_ptr(), hG.data_ptr(), hJ.data_ptr(), flags)
@@ -287,22 +382,54 @@ def main():
     for _ in range(args.e2e_steps):
         e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = nodes_per_step * args.e2e_steps / float(t.item())
+    e2e_value = nodes_per_step * args.e2e_steps / max_over_ranks(time.perf_counter() - t0)
     assert bool(np.isfinite(hG.numpy()).all())
+    del hJ
+
+    # ---- the same with the reduced result set: g, J^T lambda and max|g| cross PCIe (what a host-side outer loop
+    #      monitors: primal and dual residuals), the Jacobian values stay on the device for the batched consumer
+    hL = torch.from_numpy(rng.standard_normal(ocp.n_g)).pin_memory()
+    hJTl = torch.empty((B, ocp.n_v), dtype=torch.float64).pin_memory()
+    hGi = torch.empty((B,), dtype=torch.float64).pin_memory()
+
+    def e2e_red_step():
+        rc = ev.lib.awegpu_eval_batch_reduce_host(ev.handle, B, hW.data_ptr(), hP.data_ptr(), hL.data_ptr(), None,
+                                                  flags, cabi.AWEGPU_RED_LAMBDA_SHARED, hG.data_ptr(), hJTl.data_ptr(), None,
+                                                  None, None, hGi.data_ptr())
+        if rc != 0:
+            raise SystemExit('awegpu_eval_batch_reduce_host failed: %s' % ev.lib.awegpu_last_error(ev.handle).decode())
+
+    e2e_red_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_red_step()
+    barrier()
+    e2e_red_value = nodes_per_step * args.e2e_steps / max_over_ranks(time.perf_counter() - t0)
+    assert bool(np.isfinite(hJTl.numpy()).all())
+
+    # ---- one instance per call (what one IPOPT callback costs): g alone, g + jac_g, host numpy in and out
+    lat = {}
+    if rank == 0:
+        w1 = W[0].copy()
+        p1 = P if P.ndim == 1 else P[0].copy()
+        for name, fn in (('g_fun', lambda: ev.g_fun(w1, p1)), ('jac_g_fun', lambda: ev.jac_g_fun(w1, p1))):
+            for _ in range(20):
+                fn()
+            t0 = time.perf_counter()
+            for _ in range(200):
+                fn()
+            lat[name] = (time.perf_counter() - t0) / 200 * 1e6
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        # dominant kernel: the output stage of the collocation-node programs (awegpu_coll_ws_kernel), one launch
-        # per step.  Algorithmic bytes of that launch: every collocation node reads
+        fp64_peak, fp64_src = measured_fp64_peak()
+        # dominant kernel: the output stage of the collocation-node programs (awegpu_node_kernel<collocation, full,
+        # stage 0>), one launch per step.  Algorithmic bytes of that launch: every collocation node reads
         # its input column once ([x; xdot; z] per node, [u; theta; phi] per interval) and writes its
-        # residual rows and Jacobian entries once (DESIGN.md section 5).
+        # residual rows and Jacobian entries once (DESIGN.md section 4).
         k_ms = float(np.median(kernel_ms))
         s_ms = float(np.median(step_ms))
-        n_nodes = B * ocp.n_k * ocp.d
         entries = int((ocp.coll_slot >= 0).sum())                       # Jacobian entries of all coll nodes, one instance
         per_inst = 8 * (entries + ocp.n_k * ocp.d * (ocp.n_eq + 2 * ocp.n_x + ocp.n_z)
                         + ocp.n_k * (ocp.n_u + ocp.n_theta + ocp.n_phi))
@@ -310,51 +437,72 @@ def main():
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         info = ev.kernel_info()
         flops = B * (ocp.n_k * ocp.d * ev.flops_coll + ocp.n_k * ev.flops_shoot)
+        executed = B * (ocp.n_k * ocp.d * info['ops_coll_node'] + ocp.n_k * info['ops_shoot_node'])
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.config == 'ampyx_ap2':
             with open(tpath) as f:
                 traffic = json.load(f).get('dram_bytes_per_launch')
-        step_bytes = B * ocp.algorithmic_bytes()
+        p_bytes = 8 * (ocp.n_theta0 if p_mode != 'full' else ocp.n_p)
+        step_bytes = B * (8 * (ocp.n_v + ocp.n_g + ocp.nnz) + (p_bytes if p_mode != 'shared' else 0))
         if affinity_before is not None:
             os.sched_setaffinity(0, affinity_before)          # the CPU leg uses every host core again
-        cpu_v, cpu_dt, cpu_n, cpu_thr = cpu_leg(ocp, os.cpu_count(), args.cpu_seconds, W, p)
+        cpu_v, cpu_dt, cpu_n, cpu_thr = cpu_leg(ocp, os.cpu_count(), args.cpu_seconds, W, P, pflags)
+        t_one = time.perf_counter()
+        cpu_leg(ocp, 1, 0.0, W[:1], P if P.ndim == 1 else P[:1], pflags)
+        red_bytes = 8 * (ocp.n_v + ocp.n_g + 1)
         line = {
             'metric': 'collocation-node g+Jacobian evals/s', 'value': value, 'unit': 'node-evals/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'n_k': N_K, 'd': ocp.d, 'instances_per_gpu': B, 'n_v': ocp.n_v,
+            'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload, 'baseline_config': args.config, 'n_k': n_k, 'd': ocp.d,
+                       'instances_per_gpu': B, 'instances_total': B_total, 'n_v': ocp.n_v,
                        'n_g': ocp.n_g, 'nnz': int(ocp.nnz), 'jac_layout': 'instance-major CCS values',
-                       'l2': 'inputs+outputs per step (3.2 GB) exceed the 126 MB L2; no flush needed',
+                       'parameters': {'shared': 'one parameter vector for the batch', 'theta0': 'per-instance theta0 [B, n_theta0]',
+                                      'full': 'per-instance parameter vectors [B, n_p]'}[p_mode],
+                       'l2': 'inputs+outputs per step (%.2f GB per GPU) exceed the 126 MB L2; no flush needed' % (step_bytes / 1e9),
                        'kernels_per_step': 'gather + %d collocation stages + %d shooting stages' % (
                            sum(1 for g in info['groups_coll'] if g), sum(1 for g in info['groups_shoot'] if g)),
                        'parallelism': 'batch sharded over %d GPU(s), no data-path collective' % world},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': 'node-evals/s',
-                    'h2d_bytes_per_step': int(8 * (W.size + p.size)) * world,
+                    'h2d_bytes_per_step': int(8 * (W.size + P.size)) * world,
                     'd2h_bytes_per_step': int(8 * B * (ocp.n_g + ocp.nnz)) * world,
                     'api': 'awegpu_eval_batch_host (pinned host buffers)', 'timing': 'wall clock around the synchronous calls, max over ranks',
                     'numa_node_of_rank0': numa_node},
+            'e2e_reduced': {'value': e2e_red_value, 'unit': 'node-evals/s',
+                            'h2d_bytes_per_step': int(8 * (W.size + P.size + ocp.n_g)) * world,
+                            'd2h_bytes_per_step': int(B * red_bytes) * world,
+                            'api': 'awegpu_eval_batch_reduce_host (pinned host buffers, chunked over three streams): g, J^T lambda '
+                                   'and max|g| per instance cross PCIe; the jac_g values stay on the device for a batched consumer',
+                            'reduce_kernel_ms': red_ms,
+                            'reduce_kernel': 'awegpu_reduce_kernel, all five products (J^T lambda, J v, row / column max-norms, '
+                                             'max|g|) with per-instance lambda and v: one pass over the jac_g values'},
+            'latency_b1_us': {'g_fun': lat.get('g_fun'), 'jac_g_fun': lat.get('jac_g_fun'),
+                              'what': 'one OCP instance per call through Evaluator.g_fun / jac_g_fun (host numpy in and out), '
+                                      'mean of 200 calls; the CPU port needs cpu_port_us on one core',
+                              'cpu_port_us': (time.perf_counter() - t_one) * 1e6 / 2},
             'gpu_launches': int(gpu_launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
-                         'kernel': 'awegpu_coll_ws_kernel (output stage of the collocation-node programs: computing warps + store warps)',
+                         'kernel': 'awegpu_node_kernel<collocation, full, stage 0> (output stage of the collocation-node programs)',
                          'kernel_ms': k_ms, 'kernel_share_of_step': k_ms / s_ms,
                          'algorithmic_bytes_per_launch': int(alg_bytes),
                          'algorithmic_bytes_per_node': per_inst / (ocp.n_k * ocp.d),
                          'step': {'ms': s_ms, 'algorithmic_bytes': int(step_bytes),
                                   'achieved': step_bytes / (s_ms * 1e-3) / 1e9, 'frac': step_bytes / (s_ms * 1e-3) / 1e9 / peak},
-                         'fp64': {'algorithmic_flops_per_step': int(flops),
-                                  'executed_flops_per_step': int(B * (ocp.n_k * ocp.d * info['ops_coll_node']
-                                                                      + ocp.n_k * info['ops_shoot_node'])),
-                                  'gflops_algorithmic': flops / (s_ms * 1e-3) / 1e9,
-                                  'peak_note': 'B200 vector FP64 ~37 TFLOP/s nominal (148 SM x 64 FMA/clk x 1.965 GHz); '
-                                               'not the binding limit'},
+                         'fp64': {'algorithmic_flops_per_step': int(flops), 'executed_flops_per_step': int(executed),
+                                  'executed_over_algorithmic': executed / max(1, flops),
+                                  'tflops_executed': executed / (s_ms * 1e-3) / 1e12,
+                                  'peak_tflops': fp64_peak, 'frac': executed / (s_ms * 1e-3) / 1e12 / fp64_peak,
+                                  'peak_source': fp64_src},
                          'programs': info},
             'cpu_baseline': {'value': cpu_v, 'unit': 'node-evals/s', 'cores': cpu_thr, 'kind': 'port',
                              'sample': '256-instance blocks of the same workload repeated for %.1f s (%d instances)'
                                        % (cpu_dt, cpu_n)},
         }
+        if gather is not None:
+            line['gather'] = gather
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()

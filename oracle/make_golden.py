@@ -15,6 +15,16 @@ NLP, takes the reference's own initial guess as base point and writes
 
 These files are what the oracle (oracle/awebox_oracle.c) and the CUDA path are pinned against.  The
 script cannot run on the GPU box (no /root/reference there); its outputs are committed.
+
+Live-CasADi export (for a machine that has ``casadi==3.6.4`` and the reference; NOT runnable in this
+container, where the package cannot be installed):
+
+    AWEBOX_REAL_CASADI=1 AWEBOX_REFERENCE=/path/to/awebox python oracle/make_golden.py
+
+then imports the real package, takes the CCS pattern from ``Function.sparsity_out`` of the Jacobian function
+CasADi derives (``jacobian(g, V)``, what ``nlpsol`` uses: awebox/opti/preparation.py:373-379) and its non-zeros
+from a numeric call, and writes ``tests/golden_casadi/<config>_nk<N>.npz`` (same keys).  tests/test_parity_casadi.py
+consumes those files and is skipped, with that reason, while they do not exist.
 """
 import hashlib
 import os
@@ -33,8 +43,8 @@ import ref_build                                   # noqa: E402
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 JOBS = {
     # config: [(n_k, number of points with Jacobian)]
-    'ampyx_ap2': [(4, 3), (40, 2)],
-    'dual_kites': [(3, 2), (20, 1)],
+    'ampyx_ap2': [(4, 3), (40, 8)],
+    'dual_kites': [(3, 2), (20, 8)],
     'mpc_3dof': [(3, 3), (10, 3)],
 }
 
@@ -55,9 +65,22 @@ def run(config, n_k, n_pts, write_spec):
     theta0 = np.array(T.p_fix_num['theta0'].full()).ravel()
     sp = bspec.from_awebox(config, T.options, T.architecture, T.model, theta0_values=theta0)
     n_v = T.nlp.V.cat.shape[0]
-    T.nlp.g_fun(cas.DM(T.w0), cas.DM(T.p0))            # the first numeric call records the instruction tape
-    tape = T.nlp.g_fun._tape
-    colind, row = tape.jac_ccs(n_v)
+    real = 'shim' not in cas.__version__
+    if real:
+        # live CasADi: the Jacobian function nlpsol derives from g_fun
+        Vs, Ps = cas.MX.sym('V', n_v), cas.MX.sym('P', T.nlp.P.cat.shape[0])
+        jac_fun = cas.Function('jac_g', [Vs, Ps], [cas.jacobian(T.nlp.g_fun(Vs, Ps), Vs)])
+        try:
+            jac_fun = jac_fun.expand()      # the reference solves with expand=True (awebox/opts/funcs.py:268-286)
+        except Exception:
+            pass
+        sp_j = jac_fun.sparsity_out(0)
+        colind, row = np.array(sp_j.colind(), dtype=np.int64), np.array(sp_j.row(), dtype=np.int64)
+        tape = None
+    else:
+        T.nlp.g_fun(cas.DM(T.w0), cas.DM(T.p0))            # the first numeric call records the instruction tape
+        tape = T.nlp.g_fun._tape
+        colind, row = tape.jac_ccs(n_v)
     g_labels = T.nlp.g.labels()
     n_init = sum(1 for l in g_labels if l.startswith('[initial,'))
     if n_init:
@@ -73,7 +96,7 @@ def run(config, n_k, n_pts, write_spec):
                 order.append(names[0][2])
         sp.d['nlp']['initial_order'] = order
         sp.nlp = sp.d['nlp']
-    if write_spec:
+    if write_spec and not real:
         os.makedirs(bspec.SPEC_DIR, exist_ok=True)
         sp.to_json(os.path.join(bspec.SPEC_DIR, config + '.json'))
     W = perturbed_points(T.w0, n_pts, 20261018 + n_k)
@@ -81,7 +104,10 @@ def run(config, n_k, n_pts, write_spec):
     G = []
     for w in W:
         G.append(np.array(T.nlp.g_fun(cas.DM(w), cas.DM(p)).full()).ravel())
-    JV = [tape.jac_values(np.concatenate([w, p]), colind, row) for w in W]
+    if real:
+        JV = [np.array(jac_fun(cas.DM(w), cas.DM(p)).nonzeros(), dtype=float) for w in W]
+    else:
+        JV = [tape.jac_values(np.concatenate([w, p]), colind, row) for w in W]
     # node-level vectors
     M = T.model
     mdl_eq = M.constraints_list.get_function(T.options['nlp'], M.variables, M.parameters, 'eq')
@@ -93,14 +119,16 @@ def run(config, n_k, n_pts, write_spec):
     node_eq = np.array([np.array(mdl_eq(cas.DM(v), cas.DM(node_p)).full()).ravel() for v in node_vars])
     node_ineq = np.array([np.array(mdl_ineq(cas.DM(v), cas.DM(node_p)).full()).ravel() for v in node_vars])
     labels = '\n'.join(T.nlp.V.labels()) + '\n--\n' + '\n'.join(T.nlp.g.labels())
-    os.makedirs(GOLDEN, exist_ok=True)
-    out = os.path.join(GOLDEN, '%s_nk%d.npz' % (config, n_k))
+    gdir = GOLDEN + '_casadi' if real else GOLDEN
+    os.makedirs(gdir, exist_ok=True)
+    out = os.path.join(gdir, '%s_nk%d.npz' % (config, n_k))
     np.savez_compressed(out, w=W, p=p, g=np.array(G), colind=colind, row=row, jv=np.array(JV),
                         node_vars=node_vars, node_p=node_p, node_eq=node_eq, node_ineq=node_ineq,
                         eq_names=np.array(M.constraints_list.get_name_list('eq')),
                         ineq_names=np.array(M.constraints_list.get_name_list('ineq')),
                         var_labels=np.array(M.variables.labels()),
-                        labels_sha256=np.array(hashlib.sha256(labels.encode()).hexdigest()))
+                        labels_sha256=np.array(hashlib.sha256(labels.encode()).hexdigest()),
+                        casadi_version=np.array(str(cas.__version__)))
     print('%s n_k=%d: n_v=%d n_g=%d nnz=%d  %d points  (%.1f s)  -> %s'
           % (config, n_k, n_v, len(G[0]), len(row), n_pts, time.time() - t0, os.path.relpath(out, ROOT)))
 

@@ -68,9 +68,24 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE, 'awebox'))
 
 
+def real_casadi_requested():
+    """AWEBOX_REAL_CASADI=1: run the reference over the REAL casadi package (a machine that has casadi==3.6.4 and
+    the reference checked out; not this container) instead of the restatement under oracle/casadi_shim."""
+    return os.environ.get('AWEBOX_REAL_CASADI', '') not in ('', '0')
+
+
 def activate():
     if not available():
         raise RuntimeError('reference tree not present at %s' % REFERENCE)
+    if real_casadi_requested():
+        if REFERENCE not in sys.path:
+            sys.path.insert(0, REFERENCE)
+        if not any(isinstance(f, _InertFinder) for f in sys.meta_path):
+            sys.meta_path.append(_InertFinder())
+        import casadi
+        if 'shim' in casadi.__version__:
+            raise RuntimeError('AWEBOX_REAL_CASADI=1 but the imported casadi is the restatement')
+        return casadi
     shim = os.path.join(HERE, 'casadi_shim')
     if shim not in sys.path:
         sys.path.insert(0, shim)

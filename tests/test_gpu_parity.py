@@ -383,3 +383,73 @@ def test_reduced_products_device_entry_matches_host_entry():
         assert np.array_equal(out[key].cpu().numpy(), ref[key]), key
     # J v is accumulated with shared-memory atomics: the order of the additions is not fixed
     assert np.all(np.abs(out['Jv'].cpu().numpy() - ref['Jv']) <= 1e-12 * np.maximum(1.0, np.abs(ref['Jv'])))
+
+
+# ---------------------------------------------------------------------------------------------- degenerate inputs, error report
+def _strict_report(ocp, G, Jv, G0, J0):
+    """largest strictly entry-relative error |a - b| / |b| over the entries that are not below the row-scale floor
+    (conftest.jac_tolerance: |b| >= 1e-6 of the largest entry of the row), and the number of entries below it"""
+    rowmax = np.zeros((J0.shape[0], ocp.n_g))
+    for b in range(J0.shape[0]):
+        np.maximum.at(rowmax[b], ocp.row, np.abs(J0[b]))
+    big = np.abs(J0) >= 1e-6 * rowmax[:, ocp.row]
+    big &= J0 != 0.0
+    rel_j = float(np.max(np.abs(Jv - J0)[big] / np.abs(J0)[big]))
+    # rows of g are sums of O(1) terms: relative to the entry from 1e-3 upwards, absolute below
+    gb = np.abs(G0) >= 1e-3
+    rel_g = float(np.max(np.abs(G - G0)[gb] / np.abs(G0)[gb])) if gb.any() else 0.0
+    abs_g = float(np.max(np.abs(G - G0)[~gb])) if (~gb).any() else 0.0
+    return {'max_rel_g': rel_g, 'max_abs_g_below_1e-3': abs_g, 'max_rel_jac': rel_j, 'jac_entries': int(big.size),
+            'jac_entries_below_row_floor': int((~big).sum())}
+
+
+@pytest.mark.parametrize('name,n_k', [('ampyx_ap2', 40), ('dual_kites', 20), ('mpc_3dof', 10)])
+def test_strict_relative_error_against_golden_vectors(name, n_k):
+    """what 'within 1e-12' means entry by entry: the strictly relative error of every Jacobian entry that is not pure
+    cancellation noise (>= 1e-6 of its row's largest entry) is below 1e-10; printed and written to
+    gpurun_out/strict_rel_err.json for DESIGN.md"""
+    import json
+    ev = evaluator(name, n_k)
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d.npz' % (name, n_k)))
+    G, Jv = ev.eval(gold['w'], gold['p'])
+    rep = _strict_report(ev.ocp, G, Jv, gold['g'], gold['jv'])
+    rep['points'] = int(gold['w'].shape[0])
+    print('strict relative error %s n_k=%d: %s' % (name, n_k, rep))
+    out = os.path.join(os.path.dirname(GOLDEN), '..', 'gpurun_out')
+    if os.path.isdir(out):
+        path = os.path.join(out, 'strict_rel_err.json')
+        allrep = json.load(open(path)) if os.path.exists(path) else {}
+        allrep['%s_nk%d' % (name, n_k)] = rep
+        with open(path, 'w') as f:
+            json.dump(allrep, f, indent=1, sort_keys=True)
+    assert rep['max_rel_jac'] < 1e-10 and rep['max_rel_g'] < 1e-10 and rep['max_abs_g_below_1e-3'] < 1e-12
+
+
+@pytest.mark.parametrize('name,n_k', [('ampyx_ap2', 4), ('mpc_3dof', 3)])
+def test_non_finite_and_degenerate_inputs_match_the_checker(name, n_k):
+    """zero position vector (zero norms), t_f -> 0, NaN and Inf in w: the set of non-finite results is the checker's
+    (IEEE arithmetic on the CPU), and every finite result agrees as usual"""
+    ev = evaluator(name, n_k)
+    ocp = ev.ocp
+    W = synthetic.batch(ocp, 8, seed=31)
+    p = ocp.default_p()
+    P = np.tile(p, (W.shape[0], 1)) if ocp.needs_full_p else p
+    oq, _ = ocp.model.offset[('x', 'q10')]
+    W[1, ocp.v_cx[1][2] + oq:ocp.v_cx[1][2] + oq + 3] = 0.0            # a collocation node at the origin
+    W[2, ocp.v_x[0] + oq:ocp.v_x[0] + oq + 3] = 0.0                    # a shooting node at the origin
+    W[3, int(ocp.tf_idx[0])] = 0.0                                    # t_f = 0
+    W[4, ocp.v_cx[0][0] + 1] = np.nan
+    W[5, ocp.v_u[1]] = np.inf
+    W[6, ocp.v_z[0]] = -np.inf                                        # (denormal arguments are read as zero on the GPU: not tested)
+    W[7, ocp.v_cx[2][1]:ocp.v_cx[2][1] + ocp.n_x] = 0.0               # a whole state block zero
+    flags = 0 if ocp.needs_full_p else cabi.AWEGPU_P_SHARED
+    with np.errstate(all='ignore'):
+        G0, J0 = get_oracle(name, n_k).eval(W, P, flags=flags)
+    G, Jv = ev.eval(W, P)
+    assert np.array_equal(np.isfinite(G), np.isfinite(G0))
+    assert np.array_equal(np.isfinite(Jv), np.isfinite(J0))
+    fg, fj = np.isfinite(G0), np.isfinite(J0)
+    assert np.all(np.abs(G - G0)[fg] <= 1e-11 * np.maximum(1.0, np.abs(G0))[fg])
+    # finite entries of otherwise degenerate rows are judged against the entry itself
+    assert np.all(np.abs(Jv - J0)[fj] <= 1e-9 * np.maximum(1.0, np.abs(J0))[fj])
+    assert fg.sum() > 0.5 * fg.size and (~fg).sum() > 0
