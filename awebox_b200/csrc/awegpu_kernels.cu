@@ -1087,10 +1087,22 @@ struct awegpu_handle {
     // casadi sparsity buffers
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
     std::vector<double> scratch_g;
+    std::mutex casadi_mu;         // serialises the evaluations CasADi issues for this handle
 };
 
 static std::string g_create_error;
-static awegpu_handle *g_casadi = nullptr;
+// CasADi external-function ABI: the handles that have been bound, addressed by the `mem` index CasADi passes to the
+// evaluation functions (awegpu_g_checkout returns the slot of the handle bound at that time, so that two Functions
+// of one library -- two OCPs of one model -- do not share state); evaluations of one handle are serialised
+#define MAX_CASADI_MEM 64
+static awegpu_handle *g_casadi_tab[MAX_CASADI_MEM] = {nullptr};
+static int g_casadi_cur = -1, g_casadi_refs = 0;
+static std::mutex g_casadi_mu;
+static awegpu_handle *casadi_handle(int mem)
+{
+    if (mem < 0 || mem >= MAX_CASADI_MEM || g_casadi_tab[mem] == nullptr) mem = g_casadi_cur;
+    return mem >= 0 ? g_casadi_tab[mem] : nullptr;
+}
 
 #define CK(call)                                                                         \
     do {                                                                                 \
@@ -1138,7 +1150,14 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (g_casadi == h) g_casadi = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_casadi_mu);
+        for (int i = 0; i < MAX_CASADI_MEM; ++i)
+            if (g_casadi_tab[i] == h) {
+                g_casadi_tab[i] = nullptr;
+                if (g_casadi_cur == i) g_casadi_cur = -1;
+            }
+    }
     for (void *p : h->dev_allocs) cudaFree(p);
     cudaFree(h->dW), cudaFree(h->dP), cudaFree(h->dG), cudaFree(h->dJ);
     cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
@@ -1155,6 +1174,9 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     delete h;
 }
+
+static int ensure_scratch(awegpu_handle *h, int tiles);
+static int grow(awegpu_handle *h, double **dev, double **host, size_t *cap, size_t *hcap, size_t need, bool with_host);
 
 static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
 {
@@ -1458,6 +1480,12 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         }
         h->chunk_tiles = ct;
     }
+    // one-instance calls (the CasADi entry points, one IPOPT callback each) never allocate: side buffers of one tile
+    // and the host-entry staging of one instance are created here; larger batches: awegpu_reserve
+    if (ensure_scratch(h, 1)) return 2;
+    if (grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, (size_t)p->n_v, true) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, (size_t)p->n_p, true) |
+        grow(h, &h->dG, &h->hG, &h->capG, &h->hcapG, (size_t)p->n_g, true) | grow(h, &h->dJ, &h->hJ, &h->capJ, &h->hcapJ, (size_t)p->nnz, true))
+        return 2;
     // host copies of pointers are not kept: null them so nobody dereferences caller memory later
     h->host.x_base = h->host.x_next = h->host.u_base = h->host.xdot_base = h->host.z_base = nullptr;
     return 0;
@@ -1505,6 +1533,28 @@ static int ensure_scratch(awegpu_handle *h, int tiles)
     CK(cudaMalloc((void **)&h->sc.exs, line * t * nk * (nes ? nes : 1)));
     h->scratch_tiles = tiles;
     return 0;
+}
+
+static int grow(awegpu_handle *h, double **dev, double **host, size_t *cap, size_t *hcap, size_t need, bool with_host);
+
+// side buffers (and, with AWEGPU_RESERVE_HOST, the staging buffers of the host entry) for batches of up to B
+// instances, so that the evaluation calls that follow never allocate
+extern "C" int awegpu_reserve(awegpu_handle_t *h, int32_t B, int32_t flags)
+{
+    if (!h || B <= 0) return 1;
+    CK(cudaSetDevice(h->device));
+    const int tiles = (B + TILE - 1) / TILE;
+    int rc = ensure_scratch(h, tiles < h->chunk_tiles ? tiles : h->chunk_tiles);
+    if (rc) return rc;
+    if (flags & AWEGPU_RESERVE_HOST) {
+        const DevProblem &d = h->dp;
+        const bool stage = (flags & AWEGPU_HOST_PINNED) == 0;
+        rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, (size_t)B * d.n_v, stage) |
+             grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, (size_t)B * d.n_p, stage) |
+             grow(h, &h->dG, &h->hG, &h->capG, &h->hcapG, (size_t)B * d.n_g, stage) |
+             grow(h, &h->dJ, &h->hJ, &h->capJ, &h->hcapJ, (size_t)B * d.nnz, stage);
+    }
+    return rc;
 }
 
 extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W, const double *P, double *G,
@@ -1873,7 +1923,17 @@ static void dense_sp(std::vector<long long> &v, long long n)
 extern "C" int awegpu_casadi_bind(awegpu_handle_t *h)
 {
     if (!h) return 1;
-    g_casadi = h;
+    std::lock_guard<std::mutex> lock(g_casadi_mu);
+    int slot = -1;
+    for (int i = 0; i < MAX_CASADI_MEM && slot < 0; ++i)
+        if (g_casadi_tab[i] == h) slot = i;
+    for (int i = 0; i < MAX_CASADI_MEM && slot < 0; ++i)
+        if (g_casadi_tab[i] == nullptr) slot = i;
+    if (slot < 0) {
+        set_err(h, "awegpu_casadi_bind: no free slot");
+        return 1;
+    }
+    g_casadi_tab[slot] = h, g_casadi_cur = slot;
     dense_sp(h->sp_v, h->dp.n_v);
     dense_sp(h->sp_p, h->dp.n_p);
     dense_sp(h->sp_g, h->dp.n_g);
@@ -1882,15 +1942,18 @@ extern "C" int awegpu_casadi_bind(awegpu_handle_t *h)
     h->sp_jv.push_back(h->dp.n_v);
     h->sp_jv.insert(h->sp_jv.end(), h->colind.begin(), h->colind.end());
     h->sp_jv.insert(h->sp_jv.end(), h->row.begin(), h->row.end());
+    // jac_g_P is declared structurally empty: nlpsol only differentiates g with respect to V.  g does depend on P
+    // (theta0 everywhere, p.ref in the initial-condition rows of an mpc trial): this library is NOT a source of
+    // parametric sensitivities.
     h->sp_jp.assign(2 + (size_t)h->dp.n_p + 1, 0);      // n_g x n_p, no non-zeros
     h->sp_jp[0] = h->dp.n_g;
     h->sp_jp[1] = h->dp.n_p;
     return 0;
 }
 
-static int casadi_eval(const double **arg, double **res, bool jac)
+static int casadi_eval(const double **arg, double **res, bool jac, int mem)
 {
-    awegpu_handle *h = g_casadi;
+    awegpu_handle *h = casadi_handle(mem);
     if (!h) return 1;
     if (!arg || !arg[0] || !arg[1]) {
         set_err(h, "awegpu_g: V and P must be given (NULL means all-zero, for which g is undefined)");
@@ -1898,22 +1961,43 @@ static int casadi_eval(const double **arg, double **res, bool jac)
     }
     double *out = res ? res[0] : nullptr;
     if (!out) return 0;
+    std::lock_guard<std::mutex> lock(h->casadi_mu);
     if (jac) h->scratch_g.resize(h->dp.n_g);
     return awegpu_eval_batch_host(h, 1, arg[0], arg[1], jac ? h->scratch_g.data() : out, jac ? out : nullptr,
                                   jac ? 0 : AWEGPU_SKIP_JAC);
 }
 
-extern "C" int awegpu_g(const double **arg, double **res, long long *, double *, int) { return casadi_eval(arg, res, false); }
+// optional memory-management entry points of a CasADi external (casadi/core/external.cpp looks them up by name):
+// checkout -> index of the handle that is bound now; release: nothing to return; incref / decref: bookkeeping only
+// (handles are owned by whoever called awegpu_create); alloc_mem / init_mem / free_mem: the same slots
+#define CASADI_MEM_FUNCS(F)                                                                                  \
+    extern "C" int F##_checkout(void) { std::lock_guard<std::mutex> lock(g_casadi_mu); return g_casadi_cur < 0 ? 0 : g_casadi_cur; } \
+    extern "C" void F##_release(int) {}                                                                      \
+    extern "C" void F##_incref(void) { std::lock_guard<std::mutex> lock(g_casadi_mu); ++g_casadi_refs; }     \
+    extern "C" void F##_decref(void) { std::lock_guard<std::mutex> lock(g_casadi_mu); --g_casadi_refs; }     \
+    extern "C" int F##_alloc_mem(void) { return F##_checkout(); }                                            \
+    extern "C" int F##_init_mem(int mem) { return casadi_handle(mem) ? 0 : 1; }                              \
+    extern "C" void F##_free_mem(int) {}
+CASADI_MEM_FUNCS(awegpu_g)
+CASADI_MEM_FUNCS(jac_awegpu_g)
+#undef CASADI_MEM_FUNCS
+
+extern "C" int awegpu_g(const double **arg, double **res, long long *, double *, int mem) { return casadi_eval(arg, res, false, mem); }
 extern "C" long long awegpu_g_n_in(void) { return 2; }
 extern "C" long long awegpu_g_n_out(void) { return 1; }
 extern "C" const char *awegpu_g_name_in(long long i) { return i == 0 ? "V" : i == 1 ? "P" : nullptr; }
 extern "C" const char *awegpu_g_name_out(long long i) { return i == 0 ? "g" : nullptr; }
 extern "C" const long long *awegpu_g_sparsity_in(long long i)
 {
-    if (!g_casadi) return nullptr;
-    return i == 0 ? g_casadi->sp_v.data() : i == 1 ? g_casadi->sp_p.data() : nullptr;
+    awegpu_handle *h = casadi_handle(-1);
+    if (!h) return nullptr;
+    return i == 0 ? h->sp_v.data() : i == 1 ? h->sp_p.data() : nullptr;
 }
-extern "C" const long long *awegpu_g_sparsity_out(long long i) { return (g_casadi && i == 0) ? g_casadi->sp_g.data() : nullptr; }
+extern "C" const long long *awegpu_g_sparsity_out(long long i)
+{
+    awegpu_handle *h = casadi_handle(-1);
+    return (h && i == 0) ? h->sp_g.data() : nullptr;
+}
 extern "C" int awegpu_g_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w)
 {
     if (sz_arg) *sz_arg = 2;
@@ -1923,20 +2007,22 @@ extern "C" int awegpu_g_work(long long *sz_arg, long long *sz_res, long long *sz
     return 0;
 }
 
-extern "C" int jac_awegpu_g(const double **arg, double **res, long long *, double *, int) { return casadi_eval(arg, res, true); }
+extern "C" int jac_awegpu_g(const double **arg, double **res, long long *, double *, int mem) { return casadi_eval(arg, res, true, mem); }
 extern "C" long long jac_awegpu_g_n_in(void) { return 3; }
 extern "C" long long jac_awegpu_g_n_out(void) { return 2; }
 extern "C" const char *jac_awegpu_g_name_in(long long i) { return i == 0 ? "V" : i == 1 ? "P" : i == 2 ? "out_g" : nullptr; }
 extern "C" const char *jac_awegpu_g_name_out(long long i) { return i == 0 ? "jac_g_V" : i == 1 ? "jac_g_P" : nullptr; }
 extern "C" const long long *jac_awegpu_g_sparsity_in(long long i)
 {
-    if (!g_casadi) return nullptr;
-    return i == 0 ? g_casadi->sp_v.data() : i == 1 ? g_casadi->sp_p.data() : i == 2 ? g_casadi->sp_g.data() : nullptr;
+    awegpu_handle *h = casadi_handle(-1);
+    if (!h) return nullptr;
+    return i == 0 ? h->sp_v.data() : i == 1 ? h->sp_p.data() : i == 2 ? h->sp_g.data() : nullptr;
 }
 extern "C" const long long *jac_awegpu_g_sparsity_out(long long i)
 {
-    if (!g_casadi) return nullptr;
-    return i == 0 ? g_casadi->sp_jv.data() : i == 1 ? g_casadi->sp_jp.data() : nullptr;
+    awegpu_handle *h = casadi_handle(-1);
+    if (!h) return nullptr;
+    return i == 0 ? h->sp_jv.data() : i == 1 ? h->sp_jp.data() : nullptr;
 }
 extern "C" int jac_awegpu_g_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w)
 {

@@ -111,6 +111,12 @@ const char *awegpu_last_error(awegpu_handle_t *h);   /* h may be NULL: last crea
 
 int awegpu_sparsity(awegpu_handle_t *h, int64_t *colind /*[n_v+1]*/, int64_t *row /*[nnz]*/);
 
+/* Allocate the side buffers for batches of up to B instances now (and, with AWEGPU_RESERVE_HOST, the device / pinned
+ * staging buffers of awegpu_eval_batch_host; add AWEGPU_HOST_PINNED if the caller's own buffers are page-locked), so
+ * that no evaluation call allocates.  create() reserves for one instance (the CasADi entry points). */
+#define AWEGPU_RESERVE_HOST 64
+int awegpu_reserve(awegpu_handle_t *h, int32_t B, int32_t flags);
+
 /* Device-pointer entry: W [B,n_v], P (see flags), G [B,n_g], Jv [B*nnz] are device pointers.
  * stream: a cudaStream_t (NULL = the handle's own stream).  Asynchronous w.r.t. the host. */
 int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W, const double *P,
@@ -154,7 +160,28 @@ int64_t awegpu_launch_count(awegpu_handle_t *h);
 int awegpu_synchronize(awegpu_handle_t *h);
 
 /* ---- CasADi external-function ABI (casadi_real = double, casadi_int = long long) ---- */
-int awegpu_casadi_bind(awegpu_handle_t *h);      /* handle used by awegpu_g / jac_awegpu_g */
+/* awegpu_casadi_bind(h) makes h the handle of the Functions that are created from this library next:
+ * casadi.external looks up <name>_checkout (casadi/core/external.cpp), which returns the slot of the handle bound at
+ * that time, and passes it as `mem` to every evaluation, so two OCPs of one model (two handles) can live in one
+ * process: bind A, create external A, bind B, create external B.  Evaluations of one handle are serialised.
+ * jac_awegpu_g declares jac_g_P structurally empty (nlpsol differentiates g w.r.t. V only): g DOES depend on P, this
+ * library is not a source of parametric sensitivities. */
+int awegpu_casadi_bind(awegpu_handle_t *h);
+
+int  awegpu_g_checkout(void);
+void awegpu_g_release(int mem);
+void awegpu_g_incref(void);
+void awegpu_g_decref(void);
+int  awegpu_g_alloc_mem(void);
+int  awegpu_g_init_mem(int mem);
+void awegpu_g_free_mem(int mem);
+int  jac_awegpu_g_checkout(void);
+void jac_awegpu_g_release(int mem);
+void jac_awegpu_g_incref(void);
+void jac_awegpu_g_decref(void);
+int  jac_awegpu_g_alloc_mem(void);
+int  jac_awegpu_g_init_mem(int mem);
+void jac_awegpu_g_free_mem(int mem);
 
 int awegpu_g(const double **arg, double **res, long long *iw, double *w, int mem);
 long long awegpu_g_n_in(void);

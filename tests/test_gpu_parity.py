@@ -321,6 +321,37 @@ def test_casadi_external_abi():
     assert lib.awegpu_g(arg0, res, None, None, 0) != 0
 
 
+def test_casadi_external_abi_two_problems_in_one_process():
+    """two OCPs of one model (two handles of one library) behind the CasADi symbols: each Function addresses its own
+    handle through the `mem` index its checkout returned (the hippo triple of awebox/opti/preparation.py:285-380 shares
+    one g_fun; a sweep over n_k does not)"""
+    import ctypes as C
+    ev_a, ev_b = evaluator('ampyx_ap2', 4), evaluator('ampyx_ap2', 40)
+    lib = ev_a.lib
+    PD, PLL = C.POINTER(C.c_double), C.POINTER(C.c_longlong)
+    lib.awegpu_g.argtypes = [C.POINTER(PD), C.POINTER(PD), PLL, PD, C.c_int]
+    lib.awegpu_g_sparsity_out.restype, lib.awegpu_g_sparsity_out.argtypes = PLL, [C.c_longlong]
+    mems = []
+    for ev in (ev_a, ev_b):
+        assert lib.awegpu_casadi_bind(ev.handle) == 0
+        lib.awegpu_g_incref()
+        mems.append(lib.awegpu_g_checkout())
+        assert lib.awegpu_g_init_mem(mems[-1]) == 0
+        assert lib.awegpu_g_sparsity_out(0)[0] == ev.ocp.n_g         # what a Function created now would read
+    assert mems[0] != mems[1]
+    for ev, mem in ((ev_b, mems[1]), (ev_a, mems[0]), (ev_b, mems[1])):
+        gold = np.load(os.path.join(GOLDEN, 'ampyx_ap2_nk%d.npz' % ev.ocp.n_k))
+        w, p = np.ascontiguousarray(gold['w'][1]), np.ascontiguousarray(gold['p'])
+        g = np.empty(ev.ocp.n_g)
+        arg = (PD * 2)(w.ctypes.data_as(PD), p.ctypes.data_as(PD))
+        res = (PD * 1)(g.ctypes.data_as(PD))
+        assert lib.awegpu_g(arg, res, None, None, mem) == 0
+        assert np.all(np.abs(g - gold['g'][1]) <= 1e-12 * np.maximum(1.0, np.abs(gold['g'][1])))
+        lib.awegpu_g_release(mem)
+    lib.awegpu_g_decref()
+    lib.awegpu_g_decref()
+
+
 # ---------------------------------------------------------------------------------------------- device-resident products
 def _csc(ocp, jv):
     import scipy.sparse as sp

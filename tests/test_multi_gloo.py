@@ -29,7 +29,7 @@ def _worker(rank, world, port, B, out, spec='ampyx_ap2', n_k=4):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    from awebox_b200.parallel import shard_range, gather_results, checksum
+    from awebox_b200.parallel import shard_range, gather_results, gather_to_root, checksum
     from conftest import get_oracle
     ocp, W, P, flags = _inputs(spec, n_k, B)
     lo, hi = shard_range(B, rank, world)
@@ -37,7 +37,10 @@ def _worker(rank, world, port, B, out, spec='ampyx_ap2', n_k=4):
     Gall = gather_results(torch.from_numpy(G), B)
     Jall = gather_results(torch.from_numpy(Jv), B)
     cs = checksum(torch.from_numpy(G))
+    Groot = gather_to_root(torch.from_numpy(G), B)                 # the north_star's "gather per-shard results"
+    assert (Groot is None) == (rank != 0)
     if rank == 0:
+        assert torch.equal(Groot, Gall)
         np.savez(out, G=Gall.numpy(), J=Jall.numpy(), cs=cs)
     dist.barrier()
     dist.destroy_process_group()
@@ -61,6 +64,23 @@ def test_two_ranks_even_split(tmp_path):
 
 def test_two_ranks_ragged_split(tmp_path):
     _run(7, tmp_path)
+
+
+def test_power_curve_parameters_are_sharded_consistently():
+    """BASELINE configs[3]: instance i of the global batch gets wind speed i mod 64 whatever the sharding"""
+    from awebox_b200 import synthetic
+    from awebox_b200.parallel import shard_range
+    from conftest import get_ocp
+    ocp = get_ocp('dual_kites', 3)
+    whole = synthetic.power_curve_params(ocp, 200)
+    iu = ocp.spec.theta0_labels.index('[theta0,wind,u_ref,0]')
+    assert len(np.unique(whole[:, iu])) == 64 and whole[:, iu].min() == 5.0 and whole[:, iu].max() == 8.0
+    for world in (2, 4, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_range(200, r, world)
+            parts.append(synthetic.power_curve_params(ocp, hi - lo, first=lo))
+        assert np.array_equal(np.concatenate(parts), whole)
 
 
 def test_two_ranks_mpc_scenarios(tmp_path):
