@@ -49,6 +49,7 @@ PF_AHEAD = 150       # operations between the asynchronous copy of an input and 
 HINT_AHEAD = 0       # > 0: L2 prefetch hint this many operations before the load of a record / export input
 GROUP_OPS = 900      # weight budget of one program group (~27 KB of SASS; the L1.5 I-cache has 32 KB)
 _GROUP_OPS_DEFAULT = GROUP_OPS    # (an experiment that changes GROUP_OPS overrides the per-model table below)
+GROUP_OPS_SHOOT = 0  # > 0: separate budget for the shooting-node programs
 MAX_EXPORTS = 64     # intermediate values exported per stage (scaled up for large models, see NodeCode.plan)
 MAX_EXPORTS_SHOOT = 0 # > 0: the same for the shooting-node function (0: as MAX_EXPORTS)
 EXPORT_MIN_GAIN = 40
@@ -88,6 +89,7 @@ class NodeCode(object):
     def __init__(self, ocp):
         self.ocp = ocp
         self.group_ops = TUNED.get(ocp.spec.name, {}).get('GROUP_OPS')
+        self.group_ops_shoot = TUNED.get(ocp.spec.name, {}).get('GROUP_OPS_SHOOT')
         m = ocp.model
         d = ocp.d
         eq, ineq = m.eq_exprs(), m.ineq_exprs()
@@ -577,7 +579,10 @@ class NodeCode(object):
                     n_head = ocp.n_kcoll_head
                     cuts = set(range(n_head + 1)) | set(n_head + f for f, _ in ocp.kcoll_cols)
                     forced = {n_head}
-                exports, groups = self.plan(cur, limit=self.group_ops if GROUP_OPS == _GROUP_OPS_DEFAULT else None,
+                lim = self.group_ops if GROUP_OPS == _GROUP_OPS_DEFAULT else None
+                if name.startswith('k_shoot') and (GROUP_OPS_SHOOT > 0 or self.group_ops_shoot):
+                    lim = GROUP_OPS_SHOOT if GROUP_OPS_SHOOT > 0 else self.group_ops_shoot
+                exports, groups = self.plan(cur, limit=lim,
                                             max_exports=0 if level == MAX_STAGES - 1 else cap, cuts=cuts,
                                             forced=forced or ())
                 new = [n for n in exports if n.idx not in ex_index]

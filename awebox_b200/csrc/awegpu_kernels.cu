@@ -1088,6 +1088,9 @@ struct awegpu_handle {
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
     std::vector<double> scratch_g;
     std::mutex casadi_mu;         // serialises the evaluations CasADi issues for this handle
+    // single-instance host calls as CUDA graphs (AWEGPU_GRAPH=0 disables)
+    bool use_graph = true, capturing = false;
+    cudaGraphExec_t graph_exec[8] = {nullptr};
 };
 
 static std::string g_create_error;
@@ -1162,6 +1165,8 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     cudaFree(h->dW), cudaFree(h->dP), cudaFree(h->dG), cudaFree(h->dJ);
     cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
     cudaFree(h->counters), cudaFree(h->dLam), cudaFree(h->dVec), cudaFree(h->dRed);
+    for (cudaGraphExec_t ge : h->graph_exec)
+        if (ge) cudaGraphExecDestroy(ge);
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1177,6 +1182,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
 
 static int ensure_scratch(awegpu_handle *h, int tiles);
 static int grow(awegpu_handle *h, double **dev, double **host, size_t *cap, size_t *hcap, size_t need, bool with_host);
+static void drop_graphs(awegpu_handle *h);
 
 static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
 {
@@ -1431,6 +1437,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         CK(cudaGetDeviceProperties(&prop, device));
         h->n_sm = prop.multiProcessorCount;
         if (getenv("AWEGPU_LEAD")) h->lead_tiles = atoi(getenv("AWEGPU_LEAD"));
+        if (getenv("AWEGPU_GRAPH")) h->use_graph = atoi(getenv("AWEGPU_GRAPH")) != 0;
         const char *en = getenv("AWEGPU_CTAS");
         if (en && atoi(en) > 0) h->n_sm = atoi(en);
         static const int w_full[6][MAX_GROUPS] = {AWE_K_COLL_S0_WEIGHTS, AWE_K_COLL_S1_WEIGHTS, AWE_K_COLL_S2_WEIGHTS,
@@ -1522,6 +1529,7 @@ static int ensure_scratch(awegpu_handle *h, int tiles)
     constexpr size_t nec = AWE_K_COLL_EXPORTS > AWE_K_COLL_RES_EXPORTS ? AWE_K_COLL_EXPORTS : AWE_K_COLL_RES_EXPORTS;
     constexpr size_t nes = AWE_K_SHOOT_EXPORTS > AWE_K_SHOOT_RES_EXPORTS ? AWE_K_SHOOT_EXPORTS : AWE_K_SHOOT_RES_EXPORTS;
     CK(cudaDeviceSynchronize());
+    drop_graphs(h);
     cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
     h->sc = Scratch{};
     h->scratch_tiles = 0;
@@ -1598,7 +1606,7 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
         if (rc_) return rc_;
     }
     const double *p_sh = (flags & AWEGPU_P_SHARED) ? P + p_off : nullptr;
-    CK(cudaEventRecord(h->ev0, st));
+    if (!h->capturing) CK(cudaEventRecord(h->ev0, st));
 #define LAUNCH_STAGE(S_, F, T_, M, n_, st_)                                                                       \
     do {                                                                                                          \
         if (node_groups<S_, F, T_>() > 0) {                                                                       \
@@ -1623,9 +1631,9 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
         LAUNCH_STAGE(false, F, 1, M, nc_, st);            \
         LAUNCH_STAGE(true, F, 1, M, ns_, st);             \
         LAUNCH_STAGE(true, F, 0, M, ns_, st);             \
-        if (t0 == 0) CK(cudaEventRecord(h->ev_k0, st));   \
+        if (t0 == 0 && !h->capturing) CK(cudaEventRecord(h->ev_k0, st));   \
         LAUNCH_STAGE(false, F, 0, M, nc_, st);            \
-        if (t0 == 0) CK(cudaEventRecord(h->ev_k1, st));   \
+        if (t0 == 0 && !h->capturing) CK(cudaEventRecord(h->ev_k1, st));   \
     } while (0)
     for (int t0 = 0; t0 < tiles; t0 += h->chunk_tiles) {
         const int ct = (tiles - t0 < h->chunk_tiles) ? (tiles - t0) : h->chunk_tiles;
@@ -1645,8 +1653,10 @@ extern "C" int awegpu_eval_batch(awegpu_handle_t *h, int32_t B, const double *W,
 #undef LAUNCH_NODES
 #undef LAUNCH_STAGE
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev1, st));
-    h->last_ms = -2.f;
+    if (!h->capturing) {
+        CK(cudaEventRecord(h->ev1, st));
+        h->last_ms = -2.f;
+    }
     return 0;
 }
 
@@ -1693,8 +1703,16 @@ extern "C" int awegpu_kernel_info(int32_t *n_groups, int32_t *n_exports, int64_t
     return 0;
 }
 
+// the CUDA graphs of the single-instance calls hold addresses of the staging and side buffers: dropped when one moves
+static void drop_graphs(awegpu_handle *h)
+{
+    for (cudaGraphExec_t &ge : h->graph_exec)
+        if (ge) cudaGraphExecDestroy(ge), ge = nullptr;
+}
+
 static int grow(awegpu_handle *h, double **dev, double **host, size_t *cap, size_t *hcap, size_t need, bool with_host)
 {
+    if (need > *cap || (with_host && need > *hcap)) drop_graphs(h);
     if (need > *cap) {
         if (*dev) cudaFree(*dev);
         *dev = nullptr, *cap = 0;
@@ -1777,6 +1795,40 @@ extern "C" int awegpu_eval_batch_host(awegpu_handle_t *h, int32_t B, const doubl
     }
     memcpy(h->hW, W, nW * sizeof(double));
     memcpy(h->hP, P, nP * sizeof(double));
+    if (B == 1 && h->use_graph) {
+        // one instance per call (an IPOPT callback): the copies and the launches of the call are replayed as one CUDA
+        // graph (all addresses are the handle's own staging buffers); one graph per flag combination
+        const int key = (want_j ? 1 : 0) | ((flags & AWEGPU_P_THETA0) ? 2 : 0) | ((flags & AWEGPU_P_SHARED) ? 4 : 0);
+        if (!h->graph_exec[key]) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            h->capturing = true;
+            cudaError_t e1 = cudaMemcpyAsync(h->dW, h->hW, nW * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+            cudaError_t e2 = cudaMemcpyAsync(h->dP, h->hP, nP * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+            rc = awegpu_eval_batch(h, B, h->dW, h->dP, h->dG, want_j ? h->dJ : nullptr, flags, h->stream);
+            cudaError_t e3 = cudaMemcpyAsync(h->hG, h->dG, nG * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+            cudaError_t e4 = want_j ? cudaMemcpyAsync(h->hJ, h->dJ, nJ * sizeof(double), cudaMemcpyDeviceToHost, h->stream) : cudaSuccess;
+            h->capturing = false;
+            cudaError_t e5 = cudaStreamEndCapture(h->stream, &graph);
+            if (rc || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                h->use_graph = false;                 // fall through to the plain path, for good
+            } else {
+                cudaError_t e6 = cudaGraphInstantiate(&h->graph_exec[key], graph, 0);
+                cudaGraphDestroy(graph);
+                if (e6 != cudaSuccess) h->graph_exec[key] = nullptr, h->use_graph = false, cudaGetLastError();
+            }
+        }
+        if (h->graph_exec[key]) {
+            CK(cudaGraphLaunch(h->graph_exec[key], h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            h->launches += 7;
+            memcpy(G, h->hG, nG * sizeof(double));
+            if (want_j) memcpy(Jv, h->hJ, nJ * sizeof(double));
+            return 0;
+        }
+    }
     CK(cudaMemcpyAsync(h->dW, h->hW, nW * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->dP, h->hP, nP * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     rc = awegpu_eval_batch(h, B, h->dW, h->dP, h->dG, want_j ? h->dJ : nullptr, flags, h->stream);
@@ -1857,7 +1909,7 @@ extern "C" int awegpu_eval_batch_reduce_host(awegpu_handle_t *h, int32_t B, cons
     // instances per pipeline chunk: H2D of chunk c+1, the kernels of chunk c and D2H of chunk c-1 overlap on three
     // streams (caller buffers should be page-locked for that; pageable buffers work, without overlap)
     static const int chunk_env = getenv("AWEGPU_COPY_CHUNK") ? atoi(getenv("AWEGPU_COPY_CHUNK")) : 0;
-    const int chunk = chunk_env > 0 ? chunk_env : 512;
+    const int chunk = chunk_env > 0 ? chunk_env : 1024;         // measured: 256 / 512 / 1024 / 2048 -> 21.6 / 15.0 / 12.6 / 13.9 ms (AP2, B=4096)
     const int n_chunks = (B + chunk - 1) / chunk;
     const size_t cb = (size_t)(B < chunk ? B : chunk);
     int rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, nW, false) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, nP, false) |
