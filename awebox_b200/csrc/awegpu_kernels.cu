@@ -1078,7 +1078,7 @@ struct awegpu_handle {
     int n_sm = 0;
     int lead_tiles = 2;           // tiles a program group may run ahead of the slowest group (AWEGPU_LEAD)
     int *counters = nullptr;      // [6][MAX_GROUPS] work counters of the persistent node kernels
-    const int *colind32 = nullptr, *row32 = nullptr;     // CCS pattern on the device (awegpu_reduce_batch)
+    const int *colind32 = nullptr, *row32 = nullptr, *col32 = nullptr;     // CCS pattern on the device (awegpu_reduce_batch)
     double *dLam = nullptr, *dVec = nullptr, *dRed = nullptr;     // staging of awegpu_eval_batch_reduce_host
     size_t capLam = 0, capVec = 0, capRed = 0;
     std::vector<unsigned char> cta_group;     // [2 (full | residual only)][6][n_sm] group every CTA starts with
@@ -1410,8 +1410,12 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     h->colind.assign(p->colind, p->colind + p->n_v + 1);
     h->row.assign(p->row, p->row + p->nnz);
     {
-        std::vector<int> c32(h->colind.begin(), h->colind.end()), r32(h->row.begin(), h->row.end());
-        if (to_device(h, c32.data(), c32.size(), &h->colind32) || to_device(h, r32.data(), r32.size(), &h->row32)) return 2;
+        std::vector<int> c32(h->colind.begin(), h->colind.end()), r32(h->row.begin(), h->row.end()), col((size_t)p->nnz);
+        for (int c = 0; c < p->n_v; ++c)
+            for (long long e = p->colind[c]; e < p->colind[c + 1]; ++e) col[e] = c;
+        if (to_device(h, c32.data(), c32.size(), &h->colind32) || to_device(h, r32.data(), r32.size(), &h->row32) ||
+            to_device(h, col.data(), col.size(), &h->col32))
+            return 2;
     }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0));
@@ -1855,7 +1859,7 @@ extern "C" int awegpu_reduce_batch(awegpu_handle_t *h, int32_t B, const double *
     CK(cudaSetDevice(h->device));
     ReduceArgs a;
     a.B = B, a.n_v = h->dp.n_v, a.n_g = h->dp.n_g, a.nnz = h->dp.nnz;
-    a.colind = h->colind32, a.row = h->row32;
+    a.colind = h->colind32, a.row = h->row32, a.col = h->col32;
     a.G = G, a.J = Jvals, a.lambda = lambda, a.v = v;
     a.ld_lambda = (flags & AWEGPU_RED_LAMBDA_SHARED) ? 0 : h->dp.n_g;
     a.ld_v = (flags & AWEGPU_RED_V_SHARED) ? 0 : h->dp.n_v;

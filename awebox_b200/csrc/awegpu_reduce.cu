@@ -7,12 +7,14 @@
 //     Jv    [B, n_g] = J_b v_b                 (linearised constraint change along a step)
 //     cnorm [B, n_v] = max_i |J_b[i, c]|,  rnorm [B, n_g] = max_c |J_b[r, c]|     (scaling)
 //     ginf  [B]      = max_i |g_b[i]|
-// Thread = one column of one instance: it walks the contiguous entries of its column, so J^T lambda and the column
-// norm stay in registers; J v and the row norms are accumulated with reductions in L2 (red.global.add.f64 /
-// red.global.max.u64, no return value: the thread does not wait for them; non-negative doubles order like their bit
-// patterns).  A first version accumulated them in shared memory, one CTA per instance: FP64 shared-memory atomics are
-// compare-and-swap loops, and that kernel took 23 ms for 4096 AP2 instances.  HBM-bound: Jvals is read exactly once (8 nnz
-// bytes per instance), everything else is L1/L2 traffic.
+// Warp = 32 consecutive CCS entries of one instance (coalesced reads of the values, rows and columns): J v and the row
+// norms go to L2 as reductions, one per entry (red.global.add.f64 / red.global.max.u64 on the bit pattern of the
+// magnitude, no return value: nobody waits for them); J^T lambda and the column norms are first reduced inside the warp
+// by a segmented scan over the column index (entries of a column are consecutive), so that only the last lane of every
+// column segment issues a reduction.  HBM-bound by design: the values are read exactly once (8 nnz bytes per instance).
+// History: thread = column with shared-memory accumulators, one CTA per instance: 23 ms for 4096 AP2 instances (FP64
+// shared atomics are compare-and-swap loops); thread = column with L2 reductions: 6.1 ms (every lane walks its own
+// column: 32 sectors per load instruction); this version: see profiles/.
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -22,46 +24,51 @@
 
 __global__ void __launch_bounds__(RED_THREADS) awegpu_reduce_kernel(const ReduceArgs a)
 {
-    __shared__ double s_red[RED_THREADS / 32];
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * RED_THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * RED_THREADS) >> 5;
+    const int chunks = (int)((a.nnz + 31) / 32);                 // per instance
     const bool want_y = a.Jv != nullptr && a.v != nullptr, want_rn = a.rnorm != nullptr;
-    const int col_blocks = (a.n_v + RED_THREADS - 1) / RED_THREADS;
-    const long long n_work = (long long)a.B * col_blocks;
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const int b = (int)(w / col_blocks), cb = (int)(w - (long long)b * col_blocks);
-        const int c = cb * RED_THREADS + tid;
-        const double *Jb = a.J + (size_t)b * (size_t)a.nnz;
-        const double *lam = a.lambda ? a.lambda + (size_t)b * a.ld_lambda : nullptr;
-        if (c < a.n_v) {
-            const int e0 = __ldg(a.colind + c), e1 = __ldg(a.colind + c + 1);
-            const double vc = want_y ? __ldg(a.v + (size_t)b * a.ld_v + c) : 0.0;
-            double *yb = want_y ? a.Jv + (size_t)b * a.n_g : nullptr;
-            unsigned long long *rb = want_rn ? reinterpret_cast<unsigned long long *>(a.rnorm + (size_t)b * a.n_g) : nullptr;
-            double acc = 0.0, cn = 0.0;
-            for (int e = e0; e < e1; ++e) {
-                const double x = Jb[e];
-                const int r = __ldg(a.row + e);
-                if (lam) acc = fma(x, __ldg(lam + r), acc);
-                if (want_y) atomicAdd(yb + r, x * vc);
-                const double ax = fabs(x);
-                cn = fmax(cn, ax);
-                if (want_rn) atomicMax(rb + r, (unsigned long long)__double_as_longlong(ax));
-            }
-            if (a.JTl && lam) a.JTl[(size_t)b * a.n_v + c] = acc;
-            if (a.cnorm) a.cnorm[(size_t)b * a.n_v + c] = cn;
+    const bool want_jtl = a.JTl != nullptr && a.lambda != nullptr, want_cn = a.cnorm != nullptr;
+    for (long long w = warp; w < (long long)a.B * chunks; w += n_warps) {
+        const int b = (int)(w / chunks);
+        const long long e = (long long)(w - (long long)b * chunks) * 32 + lane;
+        const bool on = e < a.nnz;
+        double x = 0.0;
+        int r = 0, c = -1;
+        if (on) {
+            x = a.J[(size_t)b * (size_t)a.nnz + e];
+            r = __ldg(a.row + e), c = __ldg(a.col + e);
         }
-        if (a.ginf && cb == 0) {
-            double m = 0.0;
-            for (int i = tid; i < a.n_g; i += RED_THREADS) m = fmax(m, fabs(a.G[(size_t)b * a.n_g + i]));
-            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if ((tid & 31) == 0) s_red[tid >> 5] = m;
-            __syncthreads();
-            if (tid == 0) {
-                m = 0.0;
-                for (int q = 0; q < RED_THREADS / 32; ++q) m = fmax(m, s_red[q]);
-                a.ginf[b] = m;
+        const double ax = fabs(x);
+        if (on && want_y) atomicAdd(a.Jv + (size_t)b * a.n_g + r, x * __ldg(a.v + (size_t)b * a.ld_v + c));
+        if (on && want_rn)
+            atomicMax(reinterpret_cast<unsigned long long *>(a.rnorm + (size_t)b * a.n_g) + r, (unsigned long long)__double_as_longlong(ax));
+        if (want_jtl || want_cn) {
+            double t = (on && want_jtl) ? x * __ldg(a.lambda + (size_t)b * a.ld_lambda + r) : 0.0;
+            double m = ax;
+            // segmented inclusive scan over the column index
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double tu = __shfl_up_sync(0xffffffffu, t, d), mu = __shfl_up_sync(0xffffffffu, m, d);
+                const int cu = __shfl_up_sync(0xffffffffu, c, d);
+                if (lane >= d && cu == c) t += tu, m = fmax(m, mu);
             }
-            __syncthreads();
+            const int cn = __shfl_down_sync(0xffffffffu, c, 1);
+            if (on && (lane == 31 || cn != c)) {
+                if (want_jtl) atomicAdd(a.JTl + (size_t)b * a.n_v + c, t);
+                if (want_cn)
+                    atomicMax(reinterpret_cast<unsigned long long *>(a.cnorm + (size_t)b * a.n_v) + c, (unsigned long long)__double_as_longlong(m));
+            }
+        }
+    }
+    if (a.ginf) {
+        // max |g| per instance: one warp per instance
+        for (long long b = warp; b < a.B; b += n_warps) {
+            double m = 0.0;
+            for (int i = lane; i < a.n_g; i += 32) m = fmax(m, fabs(a.G[(size_t)b * a.n_g + i]));
+            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) a.ginf[b] = m;
         }
     }
 }
@@ -73,10 +80,12 @@ int awe_reduce_launch(cudaStream_t st, const ReduceArgs &a, int n_sm)
     // accumulated with reductions: start from zero (0.0 is also the identity of the max of magnitudes)
     if (a.Jv && a.v) e = cudaMemsetAsync(a.Jv, 0, (size_t)a.B * a.n_g * sizeof(double), st);
     if (e == cudaSuccess && a.rnorm) e = cudaMemsetAsync(a.rnorm, 0, (size_t)a.B * a.n_g * sizeof(double), st);
+    if (e == cudaSuccess && a.JTl && a.lambda) e = cudaMemsetAsync(a.JTl, 0, (size_t)a.B * a.n_v * sizeof(double), st);
+    if (e == cudaSuccess && a.cnorm) e = cudaMemsetAsync(a.cnorm, 0, (size_t)a.B * a.n_v * sizeof(double), st);
     if (e != cudaSuccess) return (int)e;
-    const long long n_work = (long long)a.B * ((a.n_v + RED_THREADS - 1) / RED_THREADS);
+    const long long n_work = (long long)a.B * ((a.nnz + 31) / 32);
     long long grid = (long long)n_sm * 8;
-    if (grid > n_work) grid = n_work;
+    if (grid * (RED_THREADS / 32) > n_work) grid = (n_work + RED_THREADS / 32 - 1) / (RED_THREADS / 32);
     if (grid < 1) return 0;
     awegpu_reduce_kernel<<<(int)grid, RED_THREADS, 0, st>>>(a);
     return (int)cudaGetLastError();

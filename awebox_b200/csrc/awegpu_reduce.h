@@ -6,7 +6,7 @@
 struct ReduceArgs {
     int B, n_v, n_g;
     long long nnz;
-    const int *colind, *row;        // CCS pattern, int32, device
+    const int *colind, *row, *col;  // CCS pattern, int32, device (col: column of every entry)
     const double *G, *J, *lambda, *v;
     long long ld_lambda, ld_v;      // 0: one vector shared by the batch
     double *JTl, *Jv, *cnorm, *rnorm, *ginf;

@@ -410,10 +410,11 @@ def test_reduced_products_device_entry_matches_host_entry():
     ev.eval_device(dW, dP, dG, dJ)
     out = ev.reduce_device(dG, dJ, lam=torch.from_numpy(lam).cuda(), v=torch.from_numpy(v).cuda())
     torch.cuda.synchronize()
-    for key in ('JTl', 'cnorm', 'rnorm', 'ginf'):
+    for key in ('cnorm', 'rnorm', 'ginf'):
         assert np.array_equal(out[key].cpu().numpy(), ref[key]), key
-    # J v is accumulated with shared-memory atomics: the order of the additions is not fixed
-    assert np.all(np.abs(out['Jv'].cpu().numpy() - ref['Jv']) <= 1e-12 * np.maximum(1.0, np.abs(ref['Jv'])))
+    # sums are accumulated with reductions in L2: the order of the additions is not fixed
+    for key in ('Jv', 'JTl'):
+        assert np.all(np.abs(out[key].cpu().numpy() - ref[key]) <= 1e-12 * np.maximum(1.0, np.abs(ref[key]))), key
 
 
 # ---------------------------------------------------------------------------------------------- degenerate inputs, error report
