@@ -43,6 +43,10 @@ class ProblemStruct(C.Structure):
         ('affp_begin', P_I32), ('affp_col', P_I32), ('affp_coef', P_F64), ('aff_const', P_F64),
         ('constraint_scale', C.c_double),
         ('n_kcoll_out', C.c_int32), ('n_kcoll_head', C.c_int32), ('kcoll_slot', P_I32),
+        ('obj_enabled', C.c_int32), ('obj_cat', P_I32), ('obj_norm', P_F64), ('obj_quad', P_F64),
+        ('obj_n_tf', C.c_int32), ('obj_tf_idx', P_I32), ('obj_tf_coef', P_F64),
+        ('obj_p_weights', C.c_int32), ('obj_p_cost', C.c_int32), ('obj_psi_idx', C.c_int32), ('obj_phi_cost', P_I32),
+        ('obj_c_power', C.c_int32), ('obj_c_tf', C.c_int32), ('obj_c_beta', C.c_int32), ('obj_c_cat', P_I32),
     ]
 
 
@@ -91,6 +95,25 @@ def make_problem(ocp):
     ps.constraint_scale = ocp.constraint_scale
     ps.n_aff = ocp.n_aff
     ps.n_kcoll_out, ps.n_kcoll_head = len(ocp.kcoll_out), ocp.n_kcoll_head
+    # objective (power-cycle trajectories only)
+    ps.obj_enabled = 0
+    try:
+        from .ocp.objective import Objective, REG_CATEGORIES, COST_NAMES
+        obj = Objective(ocp)
+    except NotImplementedError:
+        obj = None
+    if obj is not None:
+        terms = obj.time_period_terms()
+        arrays.update({
+            'obj_cat': _i32(obj.cat_index), 'obj_norm': _f64([obj.norm[c] for c in REG_CATEGORIES + ['beta']]),
+            'obj_quad': _f64(obj.quad), 'obj_tf_idx': _i32([i for i, _ in terms]), 'obj_tf_coef': _f64([c for _, c in terms]),
+            'obj_phi_cost': _i32([COST_NAMES.index(n) for n in obj.phi_names]),
+            'obj_c_cat': _i32([COST_NAMES.index(c) for c in REG_CATEGORIES]),
+        })
+        ps.obj_enabled, ps.obj_n_tf = 1, len(terms)
+        ps.obj_p_weights, ps.obj_p_cost = obj.p_weights, obj.p_cost
+        ps.obj_psi_idx = obj.phi_idx[obj.phi_names.index('psi')]
+        ps.obj_c_power, ps.obj_c_tf, ps.obj_c_beta = COST_NAMES.index('power'), COST_NAMES.index('t_f'), COST_NAMES.index('beta')
     for name, arr in arrays.items():
         ctype = dict(ProblemStruct._fields_)[name]
         setattr(ps, name, arr.ctypes.data_as(ctype))

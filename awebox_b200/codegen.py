@@ -558,6 +558,20 @@ class NodeCode(object):
         banner = '// generated by awebox_b200/codegen.py from spec "%s" -- do not edit\n' % ocp.spec.name
         files = {'model_defs.h': head, 'node_coll.inc': banner + coll, 'node_shoot.inc': banner + shoot}
         stats = {'coll': cs, 'shoot': ss}
+        # ---- objective integrands (awebox_b200/ocp/objective.py): power integrand, side-slip angles and their sparse
+        #      gradients with respect to the node column, plain emission (a few hundred operations)
+        from .ocp.objective import NodeIntegrands
+        integ = NodeIntegrands(ocp.model)
+        flat, layout = integ.flat_outputs()
+        cost_text, cost_stats = self.emit([S._e(e) for e in flat])
+        files['node_cost.inc'] = banner + cost_text
+        stats['cost'] = cost_stats
+        cols = []
+        for first, cc_ in layout:
+            cols += [first, len(cc_)] + list(cc_)
+        head += '#define AWE_COST_N_OUT %d\n#define AWE_COST_N_FUN %d\n' % (len(flat), len(layout))
+        head += ('/* per integrand: first output, entries, variable indices */\n#ifdef __CUDACC__\n__device__\n#endif\n'
+                 'static const int awe_cost_layout[] = {%s};\n' % ', '.join(map(str, cols)))
         # ---- CUDA emission: grouped, scheduled, register-allocated programs; full (g + jac_g) and
         #      residual-only variants.  File layout: ``case <g>: { ...program... } break;``
         n_sh = len(ocp.shoot_rows)

@@ -592,6 +592,7 @@ awegpu_gather_kernel(const DevProblem pr, const Scratch sc, const int B, const i
     }
     // ---- continuity rows  x_{k+1} - sum_r D[r] X_r   (awebox/ocp/collocation.py:319-336)
     const int row_cont = __ldg(pr.row_cont + k);
+    if (G == nullptr) return;                      // records only (objective path)
     if (BATCH_MINOR) {
         if (lane < n_valid)
             for (int m = warp; m < N_X; m += GATHER_THREADS / 32) {
@@ -1052,6 +1053,181 @@ static void launch_node(const bool bm, const NodeLaunch &a)
 
 
 #if TU_OWNS(0)
+// --------------------------------------------------------------------------- objective f(w, p) and its gradient
+// (awebox_b200/ocp/objective.py restates awebox/ocp/objective.py)
+// Thread = one instance at one collocation node (warp = node j of interval k of a tile, lane = instance), reading the
+// lane-contiguous records the gather kernel made: weighted squares of (variable - reference) per cost category, the
+// side-slip and power integrands (generated: node_cost.inc), and the chain rule of every term into the columns of V.
+// Sums go to per-instance accumulators and to grad f [B, n_v] as L2 reductions; a second kernel (thread = instance)
+// combines them: f = psi * tracking + (1 - psi) * power + general + homotopy.
+#define OBJ_NACC 8           /* reg[5], beta, energy, spare */
+struct ObjParams {
+    const int *cat;          // [N_VAR] cost category of every entry of the node column (-1: none)
+    double norm[6];          // normalisation of the five categories and of the beta cost
+    double quad[N_D];        // quadrature weights of the collocation nodes
+    int n_tf, tf_idx[2];     // time period T = sum tf_coef * V[tf_idx]
+    double tf_coef[2];
+    int p_weights, p_cost, psi_idx, n_phi_cost;
+    int phi_cost[16];        // index into the cost block of every homotopy parameter (order of V.phi)
+    int c_power, c_tf, c_beta, c_cat[5];
+};
+
+__device__ __forceinline__ const double *obj_var_ptr(const int i, const double *w_rec, const double *w_own, const double *w_xd,
+                                                     const double *w_z)
+{
+    if (i < N_X) return w_own + i * 32;
+    if (i < 2 * N_X) return w_xd + (i - N_X) * 32;
+    if (i < 2 * N_X + N_U) return w_rec + (OFF_U + i - 2 * N_X) * 32;
+    if (i < 2 * N_X + N_U + N_Z) return w_z + (i - 2 * N_X - N_U) * 32;
+    return w_rec + (REC_TH + i - 2 * N_X - N_U - N_Z) * 32;
+}
+
+__global__ void __launch_bounds__(128)
+awegpu_obj_node_kernel(const DevProblem pr, const Scratch sc, const ObjParams ob, const int B, const double *__restrict__ W,
+                       const double *__restrict__ P, const long long ldp, double *__restrict__ acc, double *__restrict__ grad)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tile = blockIdx.x, k = blockIdx.y;
+    const int b0 = tile * TILE;
+    const int b = min(b0 + lane, B - 1);
+    const bool valid = b0 + lane < B;
+    const double *Pb = P + (size_t)b * ldp;
+    const double *Wb = W + (size_t)b * pr.n_v;
+    double *gb = grad + (size_t)b * pr.n_v;
+    const double *w_rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32 + lane;
+    const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
+    const int x0 = __ldg(pr.x_base + k * (N_D + 1));
+    const int tf_v = __ldg(pr.tf_idx + k);
+    const double tf = __ldg(Wb + tf_v);
+    const double itf = 1.0 / tf, itf_nk = itf * (double)pr.n_k;
+    const double psi = __ldg(Wb + ob.psi_idx);
+    double T = 0.0;
+    for (int i = 0; i < ob.n_tf; ++i) T += ob.tf_coef[i] * __ldg(Wb + ob.tf_idx[i]);
+    const double c_power = __ldg(Pb + ob.p_cost + ob.c_power);
+    const double f_beta = __ldg(Pb + ob.p_cost + ob.c_beta) / ob.norm[5];
+    double cat_f[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) cat_f[c] = __ldg(Pb + ob.p_cost + ob.c_cat[c]) / ob.norm[c];
+    for (int j = wid; j < N_D; j += 4) {
+        const int j1 = j + 1;
+        const double *w_own = w_rec + OFF_CX(j) * 32;
+        const double *w_z = w_own + N_X * 32;
+        const double *w_xd = sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
+        const double q = ob.quad[j];
+        double reg[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        // chain a derivative with respect to entry i of the node column into grad f
+        auto scatter = [&](const int i, const double gv) {
+            if (!valid || gv == 0.0) return;
+            if (i < N_X)
+                atomicAdd(gb + x0 + OFF_CX(j) + i, gv);
+            else if (i < 2 * N_X) {
+                const int m = i - N_X;
+#pragma unroll
+                for (int r = 0; r <= N_D; ++r) atomicAdd(gb + x0 + OFF_XR(r) + m, gv * c_coeff_coll[r * (N_D + 1) + j1] * itf_nk);
+                atomicAdd(gb + tf_v, -gv * w_xd[m * 32] * itf);
+            } else if (i < 2 * N_X + N_U)
+                atomicAdd(gb + x0 + OFF_U + (i - 2 * N_X), gv);
+            else if (i < 2 * N_X + N_U + N_Z)
+                atomicAdd(gb + x0 + OFF_CZ(j) + (i - 2 * N_X - N_U), gv);
+            else
+                atomicAdd(gb + __ldg(pr.theta_idx + k * N_TH + (i - 2 * N_X - N_U - N_Z)), gv);
+        };
+        // ---- regularisation: weighted squares of (variable - reference)
+#pragma unroll 1
+        for (int i = 0; i < AWE_N_VAR; ++i) {
+            const int c = __ldg(ob.cat + i);
+            if (c < 0) continue;
+            const double v = *obj_var_ptr(i, w_rec, w_own, w_xd, w_z);
+            double ref = 0.0;                                        // reference of xdot: 0
+            if (i < N_X) ref = __ldg(Pb + x0 + OFF_CX(j) + i);
+            else if (i >= 2 * N_X && i < 2 * N_X + N_U) ref = __ldg(Pb + x0 + OFF_U + (i - 2 * N_X));
+            else if (i >= 2 * N_X + N_U && i < 2 * N_X + N_U + N_Z) ref = __ldg(Pb + x0 + OFF_CZ(j) + (i - 2 * N_X - N_U));
+            else if (i >= 2 * N_X + N_U + N_Z) ref = __ldg(Pb + __ldg(pr.theta_idx + k * N_TH + (i - 2 * N_X - N_U - N_Z)));
+            const double wgt = __ldg(Pb + ob.p_weights + i) * cat_f[c];
+            const double diff = v - ref;
+            reg[c] = fma(q * wgt * diff, diff, reg[c]);
+            scatter(i, 2.0 * q * wgt * diff * (c == 0 ? psi : 1.0));
+        }
+        // ---- integrands from the model: power, side-slip angles
+        double out[AWE_COST_N_OUT];
+        {
+#define VIN(i) (*obj_var_ptr((i), w_rec, w_own, w_xd, w_z))
+#define PIN(i) ((i) < AWE_N_THETA0 ? w_pt[(i) * 32] : w_rec[(REC_PHI + (i) - AWE_N_THETA0) * 32])
+#pragma push_macro("OUT")
+#undef OUT
+#define OUT(n, val) out[n] = (val)
+#include "node_cost.inc"
+#pragma pop_macro("OUT")
+#undef VIN
+#undef PIN
+        }
+        double energy = 0.0, beta_sum = 0.0;
+        int pos = 0;
+#pragma unroll
+        for (int fn = 0; fn < AWE_COST_N_FUN; ++fn) {
+            const int first = awe_cost_layout[pos], cnt = awe_cost_layout[pos + 1];
+            const double val = out[first];
+            if (fn == 0) {
+                // energy += h q p;  power cost = -c_power E / T, weighted by (1 - psi)
+                const double h = tf / (double)pr.n_k;
+                energy = h * q * val;
+                const double fac = (1.0 - psi) * (-c_power) / T;
+#pragma unroll
+                for (int e = 0; e < cnt; ++e) scatter(awe_cost_layout[pos + 2 + e], fac * h * q * out[first + 1 + e]);
+                if (valid) atomicAdd(gb + tf_v, fac * q * val / (double)pr.n_k);
+            } else {
+                beta_sum = fma(q * val, val, beta_sum);
+#pragma unroll
+                for (int e = 0; e < cnt; ++e) scatter(awe_cost_layout[pos + 2 + e], f_beta * 2.0 * q * val * out[first + 1 + e]);
+            }
+            pos += 2 + cnt;
+        }
+        if (valid) {
+            double *ab = acc + (size_t)b * OBJ_NACC;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) atomicAdd(ab + c, reg[c]);
+            atomicAdd(ab + 5, beta_sum);
+            atomicAdd(ab + 6, energy);
+        }
+    }
+}
+
+__global__ void awegpu_obj_final_kernel(const DevProblem pr, const ObjParams ob, const int B, const double *__restrict__ W,
+                                        const double *__restrict__ P, const long long ldp, const double *__restrict__ acc,
+                                        double *__restrict__ F, double *__restrict__ grad, double *__restrict__ comp)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double *Pb = P + (size_t)b * ldp, *Wb = W + (size_t)b * pr.n_v, *ab = acc + (size_t)b * OBJ_NACC;
+    double *gb = grad + (size_t)b * pr.n_v;
+    const double psi = Wb[ob.psi_idx];
+    double T = 0.0, T_ref = 0.0;
+    for (int i = 0; i < ob.n_tf; ++i) T += ob.tf_coef[i] * Wb[ob.tf_idx[i]], T_ref += ob.tf_coef[i] * Pb[ob.tf_idx[i]];
+    const double c_tf = Pb[ob.p_cost + ob.c_tf], c_power = Pb[ob.p_cost + ob.c_power];
+    const double tracking = ab[0];
+    const double beta_cost = Pb[ob.p_cost + ob.c_beta] / ob.norm[5] * ab[5];
+    const double time_cost = c_tf * (T - T_ref) * (T - T_ref);
+    const double energy = ab[6];
+    const double power_cost = -c_power * energy / T;
+    double hom = 0.0;
+    for (int n = 0; n < ob.n_phi_cost; ++n) {
+        const double c = Pb[ob.p_cost + ob.phi_cost[n]];
+        hom += c * Wb[pr.v_phi + n];
+        gb[pr.v_phi + n] += c;
+    }
+    // general = fictitious + u_regularisation + xdot_regularisation + theta_regularisation + beta + time
+    const double general = ab[3] + ab[2] + ab[1] + ab[4] + beta_cost + time_cost;
+    F[b] = psi * tracking + (1.0 - psi) * power_cost + general + hom;
+    for (int i = 0; i < ob.n_tf; ++i)
+        gb[ob.tf_idx[i]] += ob.tf_coef[i] * (2.0 * c_tf * (T - T_ref) - (1.0 - psi) * (-c_power) * energy / (T * T));
+    gb[ob.psi_idx] += tracking - power_cost;
+    if (comp) {
+        double *cb = comp + (size_t)b * 10;
+        cb[0] = ab[0], cb[1] = ab[1], cb[2] = ab[2], cb[3] = ab[3], cb[4] = ab[4], cb[5] = beta_cost, cb[6] = time_cost;
+        cb[7] = power_cost, cb[8] = hom, cb[9] = general;
+    }
+}
+
 static constexpr size_t gather_smem_bytes() { return sizeof(double) * TILE * SLAB_STRIDE; }
 
 // =========================================================================== host side / C ABI
@@ -1088,6 +1264,11 @@ struct awegpu_handle {
     std::vector<long long> sp_v, sp_p, sp_g, sp_jv, sp_jp;
     std::vector<double> scratch_g;
     std::mutex casadi_mu;         // serialises the evaluations CasADi issues for this handle
+    // objective path
+    bool obj_enabled = false;
+    ObjParams ob{};
+    double *dAcc = nullptr, *dF = nullptr, *dGrad = nullptr, *dComp = nullptr;
+    size_t capAcc = 0, capF = 0, capGrad = 0, capComp = 0;
     // single-instance host calls as CUDA graphs (AWEGPU_GRAPH=0 disables)
     bool use_graph = true, capturing = false;
     cudaGraphExec_t graph_exec[8] = {nullptr};
@@ -1165,6 +1346,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     cudaFree(h->dW), cudaFree(h->dP), cudaFree(h->dG), cudaFree(h->dJ);
     cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
     cudaFree(h->counters), cudaFree(h->dLam), cudaFree(h->dVec), cudaFree(h->dRed);
+    cudaFree(h->dAcc), cudaFree(h->dF), cudaFree(h->dGrad), cudaFree(h->dComp);
     for (cudaGraphExec_t ge : h->graph_exec)
         if (ge) cudaGraphExecDestroy(ge);
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
@@ -1183,6 +1365,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
 static int ensure_scratch(awegpu_handle *h, int tiles);
 static int grow(awegpu_handle *h, double **dev, double **host, size_t *cap, size_t *hcap, size_t need, bool with_host);
 static void drop_graphs(awegpu_handle *h);
+static int grow_dev(awegpu_handle *h, double **dev, size_t *cap, size_t need);
 
 static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
 {
@@ -1490,6 +1673,23 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
             if (ct < 1) ct = 1;
         }
         h->chunk_tiles = ct;
+    }
+    if (p->obj_enabled) {
+        ObjParams &ob = h->ob;
+        if (p->n_phi > 16 || p->obj_n_tf > 2 || p->obj_n_tf < 1) {
+            set_err(h, "objective: unsupported number of homotopy parameters / time-period terms");
+            return 4;
+        }
+        if (to_device(h, p->obj_cat, (size_t)AWE_N_VAR, &ob.cat)) return 2;
+        for (int c = 0; c < 6; ++c) ob.norm[c] = p->obj_norm[c];
+        for (int j = 0; j < N_D; ++j) ob.quad[j] = p->obj_quad[j];
+        ob.n_tf = p->obj_n_tf;
+        for (int i = 0; i < p->obj_n_tf; ++i) ob.tf_idx[i] = p->obj_tf_idx[i], ob.tf_coef[i] = p->obj_tf_coef[i];
+        ob.p_weights = p->obj_p_weights, ob.p_cost = p->obj_p_cost, ob.psi_idx = p->obj_psi_idx, ob.n_phi_cost = p->n_phi;
+        for (int n = 0; n < p->n_phi; ++n) ob.phi_cost[n] = p->obj_phi_cost[n];
+        ob.c_power = p->obj_c_power, ob.c_tf = p->obj_c_tf, ob.c_beta = p->obj_c_beta;
+        for (int c = 0; c < 5; ++c) ob.c_cat[c] = p->obj_c_cat[c];
+        h->obj_enabled = true;
     }
     // one-instance calls (the CasADi entry points, one IPOPT callback each) never allocate: side buffers of one tile
     // and the host-entry staging of one instance are created here; larger batches: awegpu_reserve
@@ -1967,6 +2167,71 @@ extern "C" int awegpu_eval_batch_reduce_host(awegpu_handle_t *h, int32_t B, cons
     CK(cudaStreamSynchronize(h->stream_in));
     CK(cudaStreamSynchronize(st));
     CK(cudaStreamSynchronize(h->stream_out));
+    return 0;
+}
+
+// --------------------------------------------------------------------------- objective
+extern "C" int awegpu_eval_objective(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags, double *F,
+                                     double *GradF, double *comp, void *stream)
+{
+    if (!h) return 1;
+    if (B <= 0) return 0;
+    if (!h->obj_enabled) {
+        set_err(h, "awegpu_eval_objective: this problem has no objective on this path (trajectory type power_cycle only)");
+        return 1;
+    }
+    if (!W || !P || !F || !GradF || (flags & AWEGPU_P_THETA0)) {
+        set_err(h, "awegpu_eval_objective: W, P (full parameter vectors), F and GradF are required");
+        return 1;
+    }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const DevProblem &dp = h->dp;
+    const long long ldp = (flags & AWEGPU_P_SHARED) ? 0 : dp.n_p;
+    if (grow_dev(h, &h->dAcc, &h->capAcc, (size_t)B * OBJ_NACC)) return 2;
+    CK(cudaMemsetAsync(h->dAcc, 0, (size_t)B * OBJ_NACC * sizeof(double), st));
+    CK(cudaMemsetAsync(GradF, 0, (size_t)B * dp.n_v * sizeof(double), st));
+    const int tiles = (B + TILE - 1) / TILE;
+    for (int t0 = 0; t0 < tiles; t0 += h->chunk_tiles) {
+        const int ct = (tiles - t0 < h->chunk_tiles) ? (tiles - t0) : h->chunk_tiles;
+        const int rc_ = ensure_scratch(h, ct);
+        if (rc_) return rc_;
+        const int b_base = t0 * TILE, nb = (B - b_base < ct * TILE) ? (B - b_base) : ct * TILE;
+        // records, contracted derivatives and the lane-contiguous theta0 copy of this chunk (no g / jac_g output)
+        awegpu_gather_kernel<false><<<dim3(ct, dp.n_k), GATHER_THREADS, gather_smem_bytes(), st>>>(
+            dp, h->sc, B, b_base, W, P, ldp, dp.p_theta0, nullptr, nullptr);
+        awegpu_obj_node_kernel<<<dim3(ct, dp.n_k), 128, 0, st>>>(dp, h->sc, h->ob, nb, W + (size_t)b_base * dp.n_v,
+                                                                P + (size_t)b_base * ldp, ldp, h->dAcc + (size_t)b_base * OBJ_NACC,
+                                                                GradF + (size_t)b_base * dp.n_v);
+        h->launches += 2;
+    }
+    awegpu_obj_final_kernel<<<(B + 127) / 128, 128, 0, st>>>(dp, h->ob, B, W, P, ldp, h->dAcc, F, GradF, comp);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int awegpu_eval_objective_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags,
+                                          double *F, double *GradF, double *comp)
+{
+    if (!h) return 1;
+    if (B <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const DevProblem &d = h->dp;
+    const size_t nW = (size_t)B * d.n_v, nP = (flags & AWEGPU_P_SHARED) ? (size_t)d.n_p : (size_t)B * d.n_p;
+    int rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, nW, false) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, nP, false) |
+             grow_dev(h, &h->dF, &h->capF, (size_t)B) | grow_dev(h, &h->dGrad, &h->capGrad, nW) |
+             (comp ? grow_dev(h, &h->dComp, &h->capComp, (size_t)B * 10) : 0);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->dW, W, nW * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = awegpu_eval_objective(h, B, h->dW, h->dP, flags, h->dF, h->dGrad, comp ? h->dComp : nullptr, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(F, h->dF, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(GradF, h->dGrad, nW * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (comp) CK(cudaMemcpyAsync(comp, h->dComp, (size_t)B * 10 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return 0;
 }
 

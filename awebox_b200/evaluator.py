@@ -47,6 +47,10 @@ def load_library(spec_name):
     lib.awegpu_eval_batch_reduce_host.restype = C.c_int
     lib.awegpu_eval_batch_reduce_host.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32, C.c_int32] + \
         [C.c_void_p] * 6
+    lib.awegpu_eval_objective.restype = C.c_int
+    lib.awegpu_eval_objective.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 4
+    lib.awegpu_eval_objective_host.restype = C.c_int
+    lib.awegpu_eval_objective_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 3
     lib.awegpu_last_eval_ms.restype = C.c_float
     lib.awegpu_last_eval_ms.argtypes = [C.c_void_p]
     lib.awegpu_last_kernel_ms.restype = C.c_float
@@ -218,6 +222,41 @@ class Evaluator(object):
         self._check(rc, 'awegpu_eval_batch_reduce_host')
         out['G'] = G
         return out
+
+    # ---- objective (the role of the reference's NLP.f_fun and of the gradient nlpsol derives from it)
+    COMPONENTS = ('tracking', 'xdot_regularisation', 'u_regularisation', 'fictitious', 'theta_regularisation', 'beta', 'time',
+                  'power', 'homotopy', 'general_problem')
+
+    def eval_objective(self, W, P, components=False):
+        """f [B] and grad f [B, n_v] (dense) for a batch; P: full parameter vectors [B, n_p] or one [n_p]
+        (the objective reads p.ref, p.weights, the cost factors and theta0).  numpy in, numpy out."""
+        W = np.ascontiguousarray(np.atleast_2d(np.asarray(W, dtype=np.float64)))
+        B = W.shape[0]
+        P = np.ascontiguousarray(np.asarray(P, dtype=np.float64))
+        flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        F, Gr = np.empty(B), np.empty((B, self.n_v))
+        comp = np.empty((B, len(self.COMPONENTS))) if components else None
+        rc = self.lib.awegpu_eval_objective_host(self.handle, B, W.ctypes.data, P.ctypes.data, flags, F.ctypes.data,
+                                                 Gr.ctypes.data, comp.ctypes.data if components else None)
+        self._check(rc, 'awegpu_eval_objective_host')
+        return (F, Gr, comp) if components else (F, Gr)
+
+    def eval_objective_device(self, W, P, F, GradF, stream=None):
+        """device entry (torch CUDA tensors, float64, contiguous)"""
+        import torch
+        B = W.shape[0]
+        flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        st = stream if stream is not None else torch.cuda.current_stream(W.device).cuda_stream
+        rc = self.lib.awegpu_eval_objective(self.handle, B, W.data_ptr(), P.data_ptr(), flags, F.data_ptr(), GradF.data_ptr(),
+                                            None, C.c_void_p(st if st else 1))
+        self._check(rc, 'awegpu_eval_objective')
+
+    def f_fun(self, V, P):
+        """f(V, P) for one instance (the reference's ``nlp.f_fun``)."""
+        return float(self.eval_objective(np.asarray(V, dtype=float).reshape(1, -1), np.asarray(P, dtype=float).reshape(-1))[0][0])
+
+    def grad_f_fun(self, V, P):
+        return self.eval_objective(np.asarray(V, dtype=float).reshape(1, -1), np.asarray(P, dtype=float).reshape(-1))[1][0]
 
     def last_eval_ms(self):
         return float(self.lib.awegpu_last_eval_ms(self.handle))

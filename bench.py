@@ -338,6 +338,34 @@ def main():
         torch.cuda.synchronize()
         red_ms = r0.elapsed_time(r1) / 5
 
+    # ---- objective f and grad f (power-cycle configurations): device entry, CUDA events
+    obj_line = None
+    if p_mode == 'shared' and ocp.traj_type == 'power_cycle':
+        from awebox_b200.ocp.objective import Objective
+        ob = Objective(ocp)
+        p_obj = ocp.default_p()
+        p_obj[:ocp.n_v] = W[0]                                        # p.ref: the first primal point
+        p_obj[ob.p_weights:ob.p_weights + ocp.n_var] = 1.0
+        p_obj[ob.p_cost:ob.p_cost + ob.n_cost] = 1.0
+        dPo = torch.from_numpy(p_obj).cuda()
+        dF = torch.empty((B,), dtype=torch.float64, device='cuda')
+        dGr = torch.empty((B, ocp.n_v), dtype=torch.float64, device='cuda')
+        for _ in range(3):
+            ev.eval_objective_device(dW, dPo, dF, dGr)
+        torch.cuda.synchronize()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record(stream)
+        for _ in range(10):
+            ev.eval_objective_device(dW, dPo, dF, dGr)
+        o1.record(stream)
+        torch.cuda.synchronize()
+        o_ms = o0.elapsed_time(o1) / 10
+        o_bytes = B * 8 * (2 * ocp.n_v + 1)                           # read w, write grad f and f
+        obj_line = {'ms_per_step': o_ms, 'f_and_grad_evals_per_s': B / (o_ms * 1e-3),
+                    'algorithmic_bytes': int(o_bytes), 'GBps': o_bytes / (o_ms * 1e-3) / 1e9,
+                    'api': 'awegpu_eval_objective (device pointers): gather + node kernel + per-instance kernel',
+                    'finite': bool(torch.isfinite(dF).all().item())}
+
     # ---- NCCL gather of the per-rank results (north_star: "NCCL over NVLink used only to gather per-shard results")
     gather = None
     if args.gather != 'none' and world > 1:
@@ -501,6 +529,9 @@ def main():
                              'sample': '256-instance blocks of the same workload repeated for %.1f s (%d instances)'
                                        % (cpu_dt, cpu_n)},
         }
+        if obj_line is not None:
+            obj_line['frac_of_hbm_peak'] = obj_line['GBps'] / peak
+            line['objective'] = obj_line
         if gather is not None:
             line['gather'] = gather
         print(json.dumps(line), file=json_out, flush=True)

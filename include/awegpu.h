@@ -85,6 +85,21 @@ typedef struct awegpu_problem {
      * sibling nodes of the interval included) */
     int32_t n_kcoll_out, n_kcoll_head;
     const int32_t *kcoll_slot;      /* [n_k*d*n_kcoll_out]  CCS slot, -1 = none */
+    /* objective f(w, p) (awebox/ocp/objective.py, trajectory type power_cycle; awebox_b200/ocp/objective.py);
+     * obj_enabled = 0: the problem has no objective on this path (awegpu_eval_objective fails) */
+    int32_t obj_enabled;
+    const int32_t *obj_cat;         /* [n_var] cost category of every entry of the node column: 0 tracking, 1 xdot
+                                     * regularisation, 2 u regularisation, 3 fictitious, 4 theta regularisation, -1 none */
+    const double  *obj_norm;        /* [6] normalisation of the five categories and of the beta cost */
+    const double  *obj_quad;        /* [d] quadrature weights of the collocation nodes */
+    int32_t obj_n_tf;               /* time period T = sum_i obj_tf_coef[i] * V[obj_tf_idx[i]] */
+    const int32_t *obj_tf_idx;      /* [obj_n_tf] */
+    const double  *obj_tf_coef;     /* [obj_n_tf] */
+    int32_t obj_p_weights, obj_p_cost;   /* offsets of p.weights [n_var] and of the cost block in P */
+    int32_t obj_psi_idx;            /* V index of the homotopy parameter psi */
+    const int32_t *obj_phi_cost;    /* [n_phi] index into the cost block of every homotopy parameter */
+    int32_t obj_c_power, obj_c_tf, obj_c_beta;   /* indices into the cost block */
+    const int32_t *obj_c_cat;       /* [5] ... of the five regularisation categories */
 } awegpu_problem_t;
 
 typedef struct awegpu_handle awegpu_handle_t;
@@ -145,6 +160,17 @@ int awegpu_reduce_batch(awegpu_handle_t *h, int32_t B, const double *G, const do
 int awegpu_eval_batch_reduce_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P,
                                   const double *lambda, const double *v, int32_t flags, int32_t red_flags,
                                   double *G, double *JTl, double *Jv, double *cnorm, double *rnorm, double *ginf);
+
+/* Objective of the discretised OCP and its gradient, B instances per call (replaces the numeric evaluation of
+ * NLP.f_fun and of the gradient cas.nlpsol derives from it: awebox/ocp/nlp.py:112-118, awebox/ocp/objective.py:422-520;
+ * trajectory type power_cycle).  W [B, n_v]; P full parameter vectors [B, n_p] or one vector with AWEGPU_P_SHARED
+ * (the objective reads p.ref, p.weights, the cost factors and theta0); F [B]; GradF [B, n_v] dense;
+ * comp [B, 10] (optional): tracking, xdot regularisation, u regularisation, fictitious, theta regularisation, beta,
+ * time, power, homotopy, general problem cost.  Device pointers / host pointers. */
+int awegpu_eval_objective(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags,
+                          double *F, double *GradF, double *comp, void *stream);
+int awegpu_eval_objective_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags,
+                               double *F, double *GradF, double *comp);
 
 /* device time of the most recent eval (ms, CUDA events on the launching stream); <0 if none */
 float awegpu_last_eval_ms(awegpu_handle_t *h);

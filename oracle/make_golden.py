@@ -133,9 +133,80 @@ def run(config, n_k, n_pts, write_spec):
           % (config, n_k, n_v, len(G[0]), len(row), n_pts, time.time() - t0, os.path.relpath(out, ROOT)))
 
 
+def run_objective(config, n_k, n_pts):
+    """golden vectors of the objective path: nlp.f_fun and its gradient with respect to V
+    (awebox/ocp/objective.py:422-520), the cost components, and the node-level integrands (power integral output,
+    side-slip angle) -> tests/golden/<config>_nk<N>_obj.npz.  P is filled the way the reference does before a solve
+    (awebox/opti/preparation.py:111-147: weights and references) with a perturbed copy of the initial guess as
+    reference and distinct non-zero cost factors, so that every term of the objective is exercised."""
+    t0 = time.time()
+    T = ref_build.build(config, n_k=n_k)
+    import casadi as cas
+    import awebox.opti.preparation as prep
+    nlp = T.nlp
+    rng = np.random.default_rng(20261019 + n_k)
+    n_v = len(T.w0)
+    V_ref = nlp.V(T.w0 * (1.0 + 1e-2 * rng.uniform(-1.0, 1.0, n_v)) + 1e-3 * rng.uniform(-1.0, 1.0, n_v))
+    pfix = prep.add_weights_and_refs_to_opti_parameters(T.p_fix_num, V_ref, nlp, T.model, T.V_init, T.options['solver'])
+    p = np.array(pfix.cat.full()).ravel()
+    labs = nlp.P.labels()
+    cost_idx = [i for i, l in enumerate(labs) if l.startswith('[cost,')]
+    cost_names = [labs[i][1:-1].split(',')[1] for i in cost_idx]
+    for n, i in enumerate(cost_idx):
+        p[i] = 0.5 + 0.1 * n
+    W = np.array([T.w0 * (1.0 + 1e-2 * rng.uniform(-1.0, 1.0, n_v)) + 1e-3 * rng.uniform(-1.0, 1.0, n_v)
+                  for _ in range(n_pts)])
+    # homotopy parameters inside (0, 1): psi weighs tracking against power
+    phi_idx = [i for i, l in enumerate(nlp.V.labels()) if l.startswith('[phi,')]
+    W[:, phi_idx] = rng.uniform(0.2, 0.8, (n_pts, len(phi_idx)))
+    F, GR, COMP = [], [], []
+    comp_funs, _ = nlp.cost_components
+    comp_names = [k[:-4] for k in comp_funs.keys()]
+    nlp.f_fun(cas.DM(W[0]), cas.DM(p))
+    tape = nlp.f_fun._tape
+    colind, row = tape.jac_ccs(n_v)
+    for w in W:
+        F.append(float(nlp.f_fun(cas.DM(w), cas.DM(p))))
+        vals = tape.jac_values(np.concatenate([w, p]), colind, row)
+        g = np.zeros(n_v)
+        for c in range(n_v):
+            if colind[c + 1] > colind[c]:
+                g[c] = vals[colind[c]]
+        GR.append(g)
+        COMP.append([float(fn(cas.DM(w), cas.DM(p))) for fn in comp_funs.values()])
+    # node-level integrands at random node inputs
+    M = T.model
+    theta0 = np.array(T.p_fix_num['theta0'].full()).ravel()
+    n_var = M.variables.cat.shape[0]
+    node_vars = rng.uniform(0.5, 1.5, (8, n_var))
+    node_p = np.concatenate([theta0, np.ones(M.parameters.cat.shape[0] - len(theta0))])
+    node_int = np.array([np.array(M.integral_outputs_fun(cas.DM(v), cas.DM(node_p)).full()).ravel() for v in node_vars])
+    out_labels = M.outputs.labels()
+    beta_idx = [i for i, l in enumerate(out_labels) if l.startswith('[aerodynamics,beta')]
+    node_out = np.array([np.array(M.outputs_fun(cas.DM(v), cas.DM(node_p)).full()).ravel() for v in node_vars])
+    out = os.path.join(GOLDEN, '%s_nk%d_obj.npz' % (config, n_k))
+    np.savez_compressed(out, w=W, p=p, f=np.array(F), grad=np.array(GR), components=np.array(COMP),
+                        component_names=np.array(comp_names), cost_names=np.array(cost_names),
+                        node_vars=node_vars, node_p=node_p, node_integral=node_int,
+                        integral_names=np.array(list(M.integral_outputs.keys())),
+                        node_beta=node_out[:, beta_idx], beta_labels=np.array([out_labels[i] for i in beta_idx]),
+                        quad_weights=np.array(nlp.Collocation.quad_weights, dtype=float).ravel()
+                        if hasattr(nlp, 'Collocation') else np.zeros(0))
+    print('%s n_k=%d objective: f %s  (%.1f s) -> %s' % (config, n_k, F[:2], time.time() - t0, os.path.relpath(out, ROOT)))
+
+
+OBJ_JOBS = {'ampyx_ap2': [(4, 3), (40, 3)], 'dual_kites': [(3, 2), (20, 2)]}
+
+
 if __name__ == '__main__':
     import logging
     logging.disable(logging.CRITICAL)
-    for config in (sys.argv[1:] or list(JOBS)):
+    args = [a for a in sys.argv[1:] if a != '--objective']
+    if '--objective' in sys.argv[1:]:
+        for config in (args or list(OBJ_JOBS)):
+            for n_k, n_pts in OBJ_JOBS[config]:
+                run_objective(config, n_k, n_pts)
+        sys.exit(0)
+    for config in (args or list(JOBS)):
         for i, (n_k, n_pts) in enumerate(JOBS[config]):
             run(config, n_k, n_pts, write_spec=(i == len(JOBS[config]) - 1))
