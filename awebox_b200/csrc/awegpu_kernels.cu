@@ -1055,11 +1055,14 @@ static void launch_node(const bool bm, const NodeLaunch &a)
 #if TU_OWNS(0)
 // --------------------------------------------------------------------------- objective f(w, p) and its gradient
 // (awebox_b200/ocp/objective.py restates awebox/ocp/objective.py)
-// Thread = one instance at one collocation node (warp = node j of interval k of a tile, lane = instance), reading the
-// lane-contiguous records the gather kernel made: weighted squares of (variable - reference) per cost category, the
-// side-slip and power integrands (generated: node_cost.inc), and the chain rule of every term into the columns of V.
-// Sums go to per-instance accumulators and to grad f [B, n_v] as L2 reductions; a second kernel (thread = instance)
-// combines them: f = psi * tracking + (1 - psi) * power + general + homotopy.
+// awegpu_obj_kernel: CTA = one instance, no side buffers.  The regularisation terms are element-wise in V: warp = one
+// interval, lanes on consecutive entries (coalesced reads of w and of the reference straight from the instance-major
+// rows, coalesced plain stores of the interval block of grad f), including xdot = C X / (h t_f) and its chain into all
+// X_{k,r} and t_f.  The integrands that come from the model (power, side-slip angles; generated: node_cost.inc) need a
+// node's variables together: the interval blocks of OBJ_LSQ_WARPS intervals stay in shared memory, and one warp of the
+// CTA (taking turns) evaluates their d nodes, thread = node, adding the few gradient entries as L2 reductions.
+// Sums go to per-instance accumulators; a second kernel (thread = instance) combines them:
+// f = psi * tracking + (1 - psi) * power + general + homotopy.
 #define OBJ_NACC 8           /* reg[5], beta, energy, spare */
 struct ObjParams {
     const int *cat;          // [N_VAR] cost category of every entry of the node column (-1: none)
@@ -1072,87 +1075,233 @@ struct ObjParams {
     int c_power, c_tf, c_beta, c_cat[5];
 };
 
-__device__ __forceinline__ const double *obj_var_ptr(const int i, const double *w_rec, const double *w_own, const double *w_xd,
-                                                     const double *w_z)
+#define OBJ_LSQ_WARPS 8
+#define OBJ_N_SMALL (N_U + N_D * N_Z + N_TH)
+#define OBJ_NXC ((N_X + 31) / 32)
+#define OBJ_NSC ((OBJ_N_SMALL + 31) / 32)
+// CTA = one instance, warp = every OBJ_LSQ_WARPS-th interval, lane = state index m (all X_{k,r}[m] of the interval) and
+// one entry of the short segments (u_k; z_kj; theta).  Everything that does not depend on the interval (category,
+// weight, factors) is set up once per lane; all loads of an interval are independent of each other: one round trip to
+// memory per interval and warp.  Sums of squares are kept per lane and weighted once at the end.
+// entry i of the column of collocation node j (x, xdot, u, z, theta), read from the staged interval block
+__device__ __forceinline__ double obj_vin(const int i, const double *s, const int j, const double itf_nk, const double *Wb,
+                                          const int *th_idx)
 {
-    if (i < N_X) return w_own + i * 32;
-    if (i < 2 * N_X) return w_xd + (i - N_X) * 32;
-    if (i < 2 * N_X + N_U) return w_rec + (OFF_U + i - 2 * N_X) * 32;
-    if (i < 2 * N_X + N_U + N_Z) return w_z + (i - 2 * N_X - N_U) * 32;
-    return w_rec + (REC_TH + i - 2 * N_X - N_U - N_Z) * 32;
+    if (i < N_X) return s[OFF_CX(j) + i];
+    if (i < 2 * N_X) {
+        double xd = 0.0;
+#pragma unroll
+        for (int r = 0; r <= N_D; ++r) xd = fma(c_coeff_coll[r * (N_D + 1) + (j + 1)], s[OFF_XR(r) + (i - N_X)], xd);
+        return xd * itf_nk;
+    }
+    if (i < 2 * N_X + N_U) return s[OFF_U + (i - 2 * N_X)];
+    if (i < 2 * N_X + N_U + N_Z) return s[OFF_CZ(j) + (i - 2 * N_X - N_U)];
+    return __ldg(Wb + __ldg(th_idx + (i - 2 * N_X - N_U - N_Z)));
 }
 
-__global__ void __launch_bounds__(128)
-awegpu_obj_node_kernel(const DevProblem pr, const Scratch sc, const ObjParams ob, const int B, const double *__restrict__ W,
-                       const double *__restrict__ P, const long long ldp, double *__restrict__ acc, double *__restrict__ grad)
+// intervals staged at a time: all of them when they fit into a third of the SM's shared memory (three CTAs per SM)
+static int obj_stage_k(const int n_k)
 {
+    int s = (int)((72 * 1024) / (sizeof(double) * OFF_XNEXT));
+    s -= s % OBJ_LSQ_WARPS;
+    if (s < OBJ_LSQ_WARPS) s = OBJ_LSQ_WARPS;
+    const int all = (n_k + OBJ_LSQ_WARPS - 1) / OBJ_LSQ_WARPS * OBJ_LSQ_WARPS;
+    return s < all ? s : all;
+}
+static size_t obj_smem_bytes(const int n_k) { return sizeof(double) * (size_t)obj_stage_k(n_k) * OFF_XNEXT; }
+static_assert(sizeof(double) * OBJ_LSQ_WARPS * OFF_XNEXT <= 200 * 1024, "objective kernel: interval blocks do not fit in shared memory");
+
+__global__ void __launch_bounds__(32 * OBJ_LSQ_WARPS, 3)
+awegpu_obj_kernel(const DevProblem pr, const ObjParams ob, const int B, const double *__restrict__ W,
+                  const double *__restrict__ P, const long long ldp, const int p_theta0, const int stage_k,
+                  const int *__restrict__ rest, const int n_rest, double *__restrict__ F, double *__restrict__ grad,
+                  double *__restrict__ comp)
+{
+    extern __shared__ double obj_blk[];       // [stage_k][OFF_XNEXT]: interval blocks of w
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int tile = blockIdx.x, k = blockIdx.y;
-    const int b0 = tile * TILE;
-    const int b = min(b0 + lane, B - 1);
-    const bool valid = b0 + lane < B;
-    const double *Pb = P + (size_t)b * ldp;
-    const double *Wb = W + (size_t)b * pr.n_v;
+    const int b = blockIdx.x;
+    const double *Wb = W + (size_t)b * pr.n_v, *Pb = P + (size_t)b * ldp;
+    const double *Pw = Pb + ob.p_weights;
     double *gb = grad + (size_t)b * pr.n_v;
-    const double *w_rec = sc.rec + ((size_t)tile * pr.n_k + k) * REC * 32 + lane;
-    const double *w_pt = sc.pt + (size_t)tile * pr.n_theta0 * 32 + lane;
-    const int x0 = __ldg(pr.x_base + k * (N_D + 1));
-    const int tf_v = __ldg(pr.tf_idx + k);
-    const double tf = __ldg(Wb + tf_v);
-    const double itf = 1.0 / tf, itf_nk = itf * (double)pr.n_k;
     const double psi = __ldg(Wb + ob.psi_idx);
-    double T = 0.0;
-    for (int i = 0; i < ob.n_tf; ++i) T += ob.tf_coef[i] * __ldg(Wb + ob.tf_idx[i]);
-    const double c_power = __ldg(Pb + ob.p_cost + ob.c_power);
-    const double f_beta = __ldg(Pb + ob.p_cost + ob.c_beta) / ob.norm[5];
-    double cat_f[5];
+    double cat_f[5], q_sum = 0.0;
 #pragma unroll
     for (int c = 0; c < 5; ++c) cat_f[c] = __ldg(Pb + ob.p_cost + ob.c_cat[c]) / ob.norm[c];
-    for (int j = wid; j < N_D; j += 4) {
-        const int j1 = j + 1;
-        const double *w_own = w_rec + OFF_CX(j) * 32;
-        const double *w_z = w_own + N_X * 32;
-        const double *w_xd = sc.xdc + (((size_t)tile * pr.n_k + k) * N_D + j) * N_X * 32 + lane;
-        const double q = ob.quad[j];
-        double reg[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        // chain a derivative with respect to entry i of the node column into grad f
-        auto scatter = [&](const int i, const double gv) {
-            if (!valid || gv == 0.0) return;
-            if (i < N_X)
-                atomicAdd(gb + x0 + OFF_CX(j) + i, gv);
-            else if (i < 2 * N_X) {
-                const int m = i - N_X;
 #pragma unroll
-                for (int r = 0; r <= N_D; ++r) atomicAdd(gb + x0 + OFF_XR(r) + m, gv * c_coeff_coll[r * (N_D + 1) + j1] * itf_nk);
-                atomicAdd(gb + tf_v, -gv * w_xd[m * 32] * itf);
-            } else if (i < 2 * N_X + N_U)
-                atomicAdd(gb + x0 + OFF_U + (i - 2 * N_X), gv);
-            else if (i < 2 * N_X + N_U + N_Z)
-                atomicAdd(gb + x0 + OFF_CZ(j) + (i - 2 * N_X - N_U), gv);
-            else
-                atomicAdd(gb + __ldg(pr.theta_idx + k * N_TH + (i - 2 * N_X - N_U - N_Z)), gv);
-        };
-        // ---- regularisation: weighted squares of (variable - reference)
-#pragma unroll 1
-        for (int i = 0; i < AWE_N_VAR; ++i) {
-            const int c = __ldg(ob.cat + i);
-            if (c < 0) continue;
-            const double v = *obj_var_ptr(i, w_rec, w_own, w_xd, w_z);
-            double ref = 0.0;                                        // reference of xdot: 0
-            if (i < N_X) ref = __ldg(Pb + x0 + OFF_CX(j) + i);
-            else if (i >= 2 * N_X && i < 2 * N_X + N_U) ref = __ldg(Pb + x0 + OFF_U + (i - 2 * N_X));
-            else if (i >= 2 * N_X + N_U && i < 2 * N_X + N_U + N_Z) ref = __ldg(Pb + x0 + OFF_CZ(j) + (i - 2 * N_X - N_U));
-            else if (i >= 2 * N_X + N_U + N_Z) ref = __ldg(Pb + __ldg(pr.theta_idx + k * N_TH + (i - 2 * N_X - N_U - N_Z)));
-            const double wgt = __ldg(Pb + ob.p_weights + i) * cat_f[c];
-            const double diff = v - ref;
-            reg[c] = fma(q * wgt * diff, diff, reg[c]);
-            scatter(i, 2.0 * q * wgt * diff * (c == 0 ? psi : 1.0));
-        }
-        // ---- integrands from the model: power, side-slip angles
-        double out[AWE_COST_N_OUT];
+    for (int j = 0; j < N_D; ++j) q_sum += ob.quad[j];
+    // weight * category factor of an entry of the node column with category c (0: no cost)
+    auto factor = [&](const int c, const double w) -> double {
+        double cf = (c == 0) ? cat_f[0] : 0.0;
+#pragma unroll
+        for (int cc = 1; cc < 5; ++cc) cf = (c == cc) ? cat_f[cc] : cf;
+        return w * cf;
+    };
+    // ---- per lane, the same for every interval
+    int cx[OBJ_NXC], cd[OBJ_NXC];
+    double fx[OBJ_NXC], fd[OBJ_NXC], hx[OBJ_NXC], hd[OBJ_NXC], sx[OBJ_NXC], sd[OBJ_NXC];
+#pragma unroll
+    for (int ch = 0; ch < OBJ_NXC; ++ch) {
+        const int m = min(lane + 32 * ch, N_X - 1);
+        cx[ch] = __ldg(ob.cat + m), cd[ch] = __ldg(ob.cat + N_X + m);
+        fx[ch] = factor(cx[ch], __ldg(Pw + m)), fd[ch] = factor(cd[ch], __ldg(Pw + N_X + m));
+        hx[ch] = 2.0 * fx[ch] * (cx[ch] == 0 ? psi : 1.0), hd[ch] = 2.0 * fd[ch] * (cd[ch] == 0 ? psi : 1.0);
+        sx[ch] = sd[ch] = 0.0;
+    }
+    // short segments: controls (the same u_k at every node of the interval: the quadrature weights add up), algebraic
+    // variables of the d collocation nodes, theta (shared with the other intervals: L2 reductions)
+    int cs[OBJ_NSC], so[OBJ_NSC];          // category; offset from x_k (u, z) or -1 - t (theta entry t)
+    double fs[OBJ_NSC], hs[OBJ_NSC], qs[OBJ_NSC], ss[OBJ_NSC];
+#pragma unroll
+    for (int ch = 0; ch < OBJ_NSC; ++ch) {
+        const int e = min(lane + 32 * ch, OBJ_N_SMALL - 1);
+        int i;
+        if (e < N_U) i = 2 * N_X + e, so[ch] = OFF_U + e, qs[ch] = q_sum;
+        else if (e < N_U + N_D * N_Z) {
+            const int j = (e - N_U) / N_Z, m = (e - N_U) - j * N_Z;
+            i = 2 * N_X + N_U + m, so[ch] = OFF_CZ(j) + m, qs[ch] = ob.quad[j];
+        } else
+            i = 2 * N_X + N_U + N_Z + (e - N_U - N_D * N_Z), so[ch] = -1 - (e - N_U - N_D * N_Z), qs[ch] = q_sum;
+        cs[ch] = __ldg(ob.cat + i);
+        fs[ch] = factor(cs[ch], __ldg(Pw + i));
+        hs[ch] = 2.0 * fs[ch] * (cs[ch] == 0 ? psi : 1.0);
+        ss[ch] = 0.0;
+    }
+    // entries of grad f outside the interval blocks (theta, phi, the last state ...) only receive reductions: zero first
+    for (int i = threadIdx.x; i < n_rest; i += 32 * OBJ_LSQ_WARPS) gb[__ldg(rest + i)] = 0.0;
+    __syncthreads();
+    double e_sum = 0.0, b_sum = 0.0;          // integrands: energy and squared side-slip angles of the nodes of this lane
+    const double c_power = __ldg(Pb + ob.p_cost + ob.c_power);
+    const double f_beta = __ldg(Pb + ob.p_cost + ob.c_beta) / ob.norm[5];
+    double T = 0.0;
+    for (int i = 0; i < ob.n_tf; ++i) T += ob.tf_coef[i] * __ldg(Wb + ob.tf_idx[i]);
+    for (int k_base = 0; k_base < pr.n_k; k_base += stage_k) {
+    const int k_end = min(pr.n_k, k_base + stage_k);
+    for (int k = k_base + wid; k < k_end; k += OBJ_LSQ_WARPS) {
+        double *blk = obj_blk + (k - k_base) * OFF_XNEXT;
+        const int x0 = __ldg(pr.x_base + k * (N_D + 1));
+        const int tf_v = __ldg(pr.tf_idx + k);
+        // ---- loads: the interval block of w through shared memory, the references straight from p
         {
-#define VIN(i) (*obj_var_ptr((i), w_rec, w_own, w_xd, w_z))
-#define PIN(i) ((i) < AWE_N_THETA0 ? w_pt[(i) * 32] : w_rec[(REC_PHI + (i) - AWE_N_THETA0) * 32])
+            double t[(OFF_XNEXT + 31) / 32];
+#pragma unroll
+            for (int it = 0; it < (OFF_XNEXT + 31) / 32; ++it) t[it] = __ldg(Wb + x0 + min(lane + 32 * it, OFF_XNEXT - 1));
+#pragma unroll
+            for (int it = 0; it < (OFF_XNEXT + 31) / 32; ++it)
+                if (lane + 32 * it < OFF_XNEXT) blk[lane + 32 * it] = t[it];
+        }
+        int si[OBJ_NSC];
+        double sw[OBJ_NSC], sr[OBJ_NSC], X[OBJ_NXC][N_D + 1], R[OBJ_NXC][N_D + 1];
+#pragma unroll
+        for (int ch = 0; ch < OBJ_NSC; ++ch) {
+            si[ch] = so[ch] >= 0 ? x0 + so[ch] : __ldg(pr.theta_idx + k * N_TH + (-1 - so[ch]));
+            sr[ch] = __ldg(Pb + si[ch]);
+            if (so[ch] < 0) sw[ch] = __ldg(Wb + si[ch]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < OBJ_NXC; ++ch) {
+            const int m = min(lane + 32 * ch, N_X - 1);
+#pragma unroll
+            for (int r = 1; r <= N_D; ++r) R[ch][r] = __ldg(Pb + x0 + OFF_XR(r) + m);
+        }
+        const double tf = __ldg(Wb + tf_v);
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < OBJ_NSC; ++ch)
+            if (so[ch] >= 0) sw[ch] = blk[so[ch]];
+#pragma unroll
+        for (int ch = 0; ch < OBJ_NXC; ++ch) {
+            const int m = min(lane + 32 * ch, N_X - 1);
+#pragma unroll
+            for (int r = 0; r <= N_D; ++r) X[ch][r] = blk[OFF_XR(r) + m];
+        }
+        const double itf = 1.0 / tf, itf_nk = (double)pr.n_k * itf;
+        double tf_g = 0.0;
+        // ---- differential states: X_{k,0} = x_k and the collocation states X_{k,r}
+#pragma unroll
+        for (int ch = 0; ch < OBJ_NXC; ++ch) {
+            const int m = lane + 32 * ch;
+            double g[N_D + 1];
+            g[0] = 0.0;
+#pragma unroll
+            for (int r = 1; r <= N_D; ++r) {
+                const double qd = ob.quad[r - 1] * (X[ch][r] - R[ch][r]);
+                sx[ch] = fma(qd, X[ch][r] - R[ch][r], sx[ch]);
+                g[r] = hx[ch] * qd;
+            }
+            // xdot_kj = (sum_r C[r, j+1] X_r) / h / t_f, reference 0;  d xdot_kj / d X_r = C[r, j+1] / h / t_f,
+            // d xdot_kj / d t_f = -xdot_kj / t_f
+            double tf_l = 0.0;
+#pragma unroll
+            for (int j = 0; j < N_D; ++j) {
+                double xd = 0.0;
+#pragma unroll
+                for (int r = 0; r <= N_D; ++r) xd = fma(c_coeff_coll[r * (N_D + 1) + (j + 1)], X[ch][r], xd);
+                xd *= itf_nk;
+                const double qd = ob.quad[j] * xd;
+                sd[ch] = fma(qd, xd, sd[ch]);
+                const double gxd = hd[ch] * qd, gs = gxd * itf_nk;
+#pragma unroll
+                for (int r = 0; r <= N_D; ++r) g[r] = fma(gs, c_coeff_coll[r * (N_D + 1) + (j + 1)], g[r]);
+                tf_l = fma(gxd, xd, tf_l);
+            }
+            if (m < N_X) {
+                tf_g -= tf_l * itf;
+#pragma unroll
+                for (int r = 0; r <= N_D; ++r) gb[x0 + OFF_XR(r) + m] = g[r];
+                gb[x0 + OFF_XDOT + m] = 0.0;          // xdot_k, z_k: variables of the shooting node, no cost
+            } else
+                sx[ch] = sd[ch] = 0.0;       // a clamped lane: only lanes of the last chunk, which stay clamped
+        }
+        for (int m = lane; m < N_Z; m += 32) gb[x0 + OFF_Z + m] = 0.0;
+        // ---- short segments
+#pragma unroll
+        for (int ch = 0; ch < OBJ_NSC; ++ch) {
+            const double diff = sw[ch] - sr[ch], qd = qs[ch] * diff;
+            if (lane + 32 * ch < OBJ_N_SMALL) {
+                ss[ch] = fma(qd, diff, ss[ch]);
+                const double gv = hs[ch] * qd;
+                if (so[ch] >= 0) gb[si[ch]] = gv;
+                else if (gv != 0.0) atomicAdd(gb + si[ch], gv);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tf_g += __shfl_xor_sync(0xffffffffu, tf_g, o);
+        if (lane == 0 && tf_g != 0.0) atomicAdd(gb + tf_v, tf_g);
+    }
+        __syncthreads();      // the blocks of these intervals are staged and their part of grad f is stored
+        // ---- integrands from the model at the d nodes of the staged intervals: thread = node
+        {
+            const int n_nodes = (k_end - k_base) * N_D;
+            for (int n = threadIdx.x; n < n_nodes; n += 32 * OBJ_LSQ_WARPS) {
+                const int kk = n / N_D, j = n - kk * N_D, kn = k_base + kk;
+                const double *sb = obj_blk + kk * OFF_XNEXT;
+                const int x0 = __ldg(pr.x_base + kn * (N_D + 1));
+                const int tf_v = __ldg(pr.tf_idx + kn);
+                const int *th_idx = pr.theta_idx + kn * N_TH;
+                const double tf = __ldg(Wb + tf_v);
+                const double itf = 1.0 / tf, itf_nk = (double)pr.n_k * itf;
+                const double q = ob.quad[j];
+                // chain a derivative with respect to entry i of the node column into grad f
+                auto scatter = [&](const int i, const double gv) {
+                    if (gv == 0.0) return;
+                    if (i < N_X)
+                        atomicAdd(gb + x0 + OFF_CX(j) + i, gv);
+                    else if (i < 2 * N_X) {
+                        const int m = i - N_X;
+                        for (int r = 0; r <= N_D; ++r)
+                            atomicAdd(gb + x0 + OFF_XR(r) + m, gv * c_coeff_coll[r * (N_D + 1) + (j + 1)] * itf_nk);
+                        atomicAdd(gb + tf_v, -gv * obj_vin(i, sb, j, itf_nk, Wb, th_idx) * itf);
+                    } else if (i < 2 * N_X + N_U)
+                        atomicAdd(gb + x0 + OFF_U + (i - 2 * N_X), gv);
+                    else if (i < 2 * N_X + N_U + N_Z)
+                        atomicAdd(gb + x0 + OFF_CZ(j) + (i - 2 * N_X - N_U), gv);
+                    else
+                        atomicAdd(gb + __ldg(th_idx + (i - 2 * N_X - N_U - N_Z)), gv);
+                };
+                double out[AWE_COST_N_OUT];
+                {
+#define VIN(i) obj_vin((i), sb, j, itf_nk, Wb, th_idx)
+#define PIN(i) ((i) < AWE_N_THETA0 ? __ldg(Pb + p_theta0 + (i)) : __ldg(Wb + pr.v_phi + ((i) - AWE_N_THETA0)))
 #pragma push_macro("OUT")
 #undef OUT
 #define OUT(n, val) out[n] = (val)
@@ -1160,67 +1309,88 @@ awegpu_obj_node_kernel(const DevProblem pr, const Scratch sc, const ObjParams ob
 #pragma pop_macro("OUT")
 #undef VIN
 #undef PIN
-        }
-        double energy = 0.0, beta_sum = 0.0;
-        int pos = 0;
+                }
+                int pos = 0;
 #pragma unroll
-        for (int fn = 0; fn < AWE_COST_N_FUN; ++fn) {
-            const int first = awe_cost_layout[pos], cnt = awe_cost_layout[pos + 1];
-            const double val = out[first];
-            if (fn == 0) {
-                // energy += h q p;  power cost = -c_power E / T, weighted by (1 - psi)
-                const double h = tf / (double)pr.n_k;
-                energy = h * q * val;
-                const double fac = (1.0 - psi) * (-c_power) / T;
+                for (int fn = 0; fn < AWE_COST_N_FUN; ++fn) {
+                    const int first = awe_cost_layout[pos], cnt = awe_cost_layout[pos + 1];
+                    const double val = out[first];
+                    if (fn == 0) {
+                        // energy += h q p;  power cost = -c_power E / T, weighted by (1 - psi)
+                        const double h = tf / (double)pr.n_k;
+                        e_sum = fma(h * q, val, e_sum);
+                        const double fac = (1.0 - psi) * (-c_power) / T;
 #pragma unroll
-                for (int e = 0; e < cnt; ++e) scatter(awe_cost_layout[pos + 2 + e], fac * h * q * out[first + 1 + e]);
-                if (valid) atomicAdd(gb + tf_v, fac * q * val / (double)pr.n_k);
-            } else {
-                beta_sum = fma(q * val, val, beta_sum);
+                        for (int e = 0; e < cnt; ++e) scatter(awe_cost_layout[pos + 2 + e], fac * h * q * out[first + 1 + e]);
+                        atomicAdd(gb + tf_v, fac * q * val / (double)pr.n_k);
+                    } else {
+                        b_sum = fma(q * val, val, b_sum);
 #pragma unroll
-                for (int e = 0; e < cnt; ++e) scatter(awe_cost_layout[pos + 2 + e], f_beta * 2.0 * q * val * out[first + 1 + e]);
+                        for (int e = 0; e < cnt; ++e)
+                            scatter(awe_cost_layout[pos + 2 + e], f_beta * 2.0 * q * val * out[first + 1 + e]);
+                    }
+                    pos += 2 + cnt;
+                }
             }
-            pos += 2 + cnt;
         }
-        if (valid) {
-            double *ab = acc + (size_t)b * OBJ_NACC;
-#pragma unroll
-            for (int c = 0; c < 5; ++c) atomicAdd(ab + c, reg[c]);
-            atomicAdd(ab + 5, beta_sum);
-            atomicAdd(ab + 6, energy);
-        }
+        __syncthreads();      // before the next intervals overwrite the staged blocks
     }
-}
-
-__global__ void awegpu_obj_final_kernel(const DevProblem pr, const ObjParams ob, const int B, const double *__restrict__ W,
-                                        const double *__restrict__ P, const long long ldp, const double *__restrict__ acc,
-                                        double *__restrict__ F, double *__restrict__ grad, double *__restrict__ comp)
-{
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const double *Pb = P + (size_t)b * ldp, *Wb = W + (size_t)b * pr.n_v, *ab = acc + (size_t)b * OBJ_NACC;
-    double *gb = grad + (size_t)b * pr.n_v;
-    const double psi = Wb[ob.psi_idx];
-    double T = 0.0, T_ref = 0.0;
-    for (int i = 0; i < ob.n_tf; ++i) T += ob.tf_coef[i] * Wb[ob.tf_idx[i]], T_ref += ob.tf_coef[i] * Pb[ob.tf_idx[i]];
-    const double c_tf = Pb[ob.p_cost + ob.c_tf], c_power = Pb[ob.p_cost + ob.c_power];
+    // ---- weighted sums of squares per category: lanes -> warp -> L2 reductions
+    double reg[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    auto add = [&](const int c, const double t) {
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc) reg[cc] += (c == cc) ? t : 0.0;
+    };
+#pragma unroll
+    for (int ch = 0; ch < OBJ_NXC; ++ch) add(cx[ch], fx[ch] * sx[ch]), add(cd[ch], fd[ch] * sd[ch]);
+#pragma unroll
+    for (int ch = 0; ch < OBJ_NSC; ++ch) add(cs[ch], fs[ch] * ss[ch]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 5; ++c) reg[c] += __shfl_xor_sync(0xffffffffu, reg[c], o);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        e_sum += __shfl_xor_sync(0xffffffffu, e_sum, o), b_sum += __shfl_xor_sync(0xffffffffu, b_sum, o);
+    __shared__ double s_red[OBJ_LSQ_WARPS][OBJ_NACC];
+    if (lane < 7) {
+        double v = reg[0];
+#pragma unroll
+        for (int c = 1; c < 5; ++c) v = (lane == c) ? reg[c] : v;
+        s_red[wid][lane] = (lane == 5) ? b_sum : (lane == 6) ? e_sum : v;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    // ---- the instance's sums and the terms that do not belong to a node
+    double ab[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        ab[c] = 0.0;
+#pragma unroll
+        for (int w = 0; w < OBJ_LSQ_WARPS; ++w) ab[c] += s_red[w][c];
+    }
+    double T_ref = 0.0;
+    for (int i = 0; i < ob.n_tf; ++i) T_ref += ob.tf_coef[i] * __ldg(Pb + ob.tf_idx[i]);
+    const double c_tf = __ldg(Pb + ob.p_cost + ob.c_tf);
     const double tracking = ab[0];
-    const double beta_cost = Pb[ob.p_cost + ob.c_beta] / ob.norm[5] * ab[5];
+    const double beta_cost = f_beta * ab[5];
     const double time_cost = c_tf * (T - T_ref) * (T - T_ref);
     const double energy = ab[6];
     const double power_cost = -c_power * energy / T;
     double hom = 0.0;
+    // the gradient entries below also receive reductions from the nodes: added the same way (no read of grad f)
     for (int n = 0; n < ob.n_phi_cost; ++n) {
-        const double c = Pb[ob.p_cost + ob.phi_cost[n]];
-        hom += c * Wb[pr.v_phi + n];
-        gb[pr.v_phi + n] += c;
+        const double c = __ldg(Pb + ob.p_cost + ob.phi_cost[n]);
+        hom += c * __ldg(Wb + pr.v_phi + n);
+        atomicAdd(gb + pr.v_phi + n, c);
     }
     // general = fictitious + u_regularisation + xdot_regularisation + theta_regularisation + beta + time
     const double general = ab[3] + ab[2] + ab[1] + ab[4] + beta_cost + time_cost;
     F[b] = psi * tracking + (1.0 - psi) * power_cost + general + hom;
     for (int i = 0; i < ob.n_tf; ++i)
-        gb[ob.tf_idx[i]] += ob.tf_coef[i] * (2.0 * c_tf * (T - T_ref) - (1.0 - psi) * (-c_power) * energy / (T * T));
-    gb[ob.psi_idx] += tracking - power_cost;
+        atomicAdd(gb + ob.tf_idx[i], ob.tf_coef[i] * (2.0 * c_tf * (T - T_ref) - (1.0 - psi) * (-c_power) * energy / (T * T)));
+    atomicAdd(gb + ob.psi_idx, tracking - power_cost);
     if (comp) {
         double *cb = comp + (size_t)b * 10;
         cb[0] = ab[0], cb[1] = ab[1], cb[2] = ab[2], cb[3] = ab[3], cb[4] = ab[4], cb[5] = beta_cost, cb[6] = time_cost;
@@ -1267,8 +1437,10 @@ struct awegpu_handle {
     // objective path
     bool obj_enabled = false;
     ObjParams ob{};
-    double *dAcc = nullptr, *dF = nullptr, *dGrad = nullptr, *dComp = nullptr;
-    size_t capAcc = 0, capF = 0, capGrad = 0, capComp = 0;
+    double *dF = nullptr, *dGrad = nullptr, *dComp = nullptr;
+    size_t capF = 0, capGrad = 0, capComp = 0;
+    const int *obj_rest = nullptr;      // entries of V outside the interval blocks
+    int n_obj_rest = 0;
     // single-instance host calls as CUDA graphs (AWEGPU_GRAPH=0 disables)
     bool use_graph = true, capturing = false;
     cudaGraphExec_t graph_exec[8] = {nullptr};
@@ -1346,7 +1518,7 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     cudaFree(h->dW), cudaFree(h->dP), cudaFree(h->dG), cudaFree(h->dJ);
     cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
     cudaFree(h->counters), cudaFree(h->dLam), cudaFree(h->dVec), cudaFree(h->dRed);
-    cudaFree(h->dAcc), cudaFree(h->dF), cudaFree(h->dGrad), cudaFree(h->dComp);
+    cudaFree(h->dF), cudaFree(h->dGrad), cudaFree(h->dComp);
     for (cudaGraphExec_t ge : h->graph_exec)
         if (ge) cudaGraphExecDestroy(ge);
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
@@ -1617,6 +1789,7 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     CK((attr_node_impl<true, false, 1>()));
     CK((attr_node_impl<true, false, 2>()));
     SET_SMEM(awegpu_gather_kernel<false>, gather_smem_bytes());
+    SET_SMEM(awegpu_obj_kernel, obj_smem_bytes(p->n_k));
     {
         // persistent node kernels: one CTA per SM; the group a CTA starts with, in proportion to the cost the
         // generator estimated for the groups of every (collocation | shooting, stage) launch
@@ -1689,6 +1862,16 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         for (int n = 0; n < p->n_phi; ++n) ob.phi_cost[n] = p->obj_phi_cost[n];
         ob.c_power = p->obj_c_power, ob.c_tf = p->obj_c_tf, ob.c_beta = p->obj_c_beta;
         for (int c = 0; c < 5; ++c) ob.c_cat[c] = p->obj_c_cat[c];
+        {
+            std::vector<char> in_block((size_t)p->n_v, 0);
+            for (int k = 0; k < p->n_k; ++k)
+                for (int c = 0; c < OFF_XNEXT; ++c) in_block[(size_t)p->x_base[k * (N_D + 1)] + c] = 1;
+            std::vector<int> rest;
+            for (int i = 0; i < p->n_v; ++i)
+                if (!in_block[i]) rest.push_back(i);
+            h->n_obj_rest = (int)rest.size();
+            if (!rest.empty() && to_device(h, rest.data(), rest.size(), &h->obj_rest)) return 2;
+        }
         h->obj_enabled = true;
     }
     // one-instance calls (the CasADi entry points, one IPOPT callback each) never allocate: side buffers of one tile
@@ -2188,24 +2371,10 @@ extern "C" int awegpu_eval_objective(awegpu_handle_t *h, int32_t B, const double
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     const DevProblem &dp = h->dp;
     const long long ldp = (flags & AWEGPU_P_SHARED) ? 0 : dp.n_p;
-    if (grow_dev(h, &h->dAcc, &h->capAcc, (size_t)B * OBJ_NACC)) return 2;
-    CK(cudaMemsetAsync(h->dAcc, 0, (size_t)B * OBJ_NACC * sizeof(double), st));
-    CK(cudaMemsetAsync(GradF, 0, (size_t)B * dp.n_v * sizeof(double), st));
-    const int tiles = (B + TILE - 1) / TILE;
-    for (int t0 = 0; t0 < tiles; t0 += h->chunk_tiles) {
-        const int ct = (tiles - t0 < h->chunk_tiles) ? (tiles - t0) : h->chunk_tiles;
-        const int rc_ = ensure_scratch(h, ct);
-        if (rc_) return rc_;
-        const int b_base = t0 * TILE, nb = (B - b_base < ct * TILE) ? (B - b_base) : ct * TILE;
-        // records, contracted derivatives and the lane-contiguous theta0 copy of this chunk (no g / jac_g output)
-        awegpu_gather_kernel<false><<<dim3(ct, dp.n_k), GATHER_THREADS, gather_smem_bytes(), st>>>(
-            dp, h->sc, B, b_base, W, P, ldp, dp.p_theta0, nullptr, nullptr);
-        awegpu_obj_node_kernel<<<dim3(ct, dp.n_k), 128, 0, st>>>(dp, h->sc, h->ob, nb, W + (size_t)b_base * dp.n_v,
-                                                                P + (size_t)b_base * ldp, ldp, h->dAcc + (size_t)b_base * OBJ_NACC,
-                                                                GradF + (size_t)b_base * dp.n_v);
-        h->launches += 2;
-    }
-    awegpu_obj_final_kernel<<<(B + 127) / 128, 128, 0, st>>>(dp, h->ob, B, W, P, ldp, h->dAcc, F, GradF, comp);
+    // one launch: every entry of GradF is written (interval blocks) or zeroed (the rest) by the kernel itself
+    awegpu_obj_kernel<<<B, 32 * OBJ_LSQ_WARPS, obj_smem_bytes(dp.n_k), st>>>(dp, h->ob, B, W, P, ldp, dp.p_theta0,
+                                                                             obj_stage_k(dp.n_k), h->obj_rest, h->n_obj_rest,
+                                                                             F, GradF, comp);
     h->launches += 1;
     CK(cudaGetLastError());
     return 0;

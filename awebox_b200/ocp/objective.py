@@ -235,3 +235,69 @@ def q_energy(obj, j):
     the continuity coefficients pick the last node, so the weights are the last column of Lambda = the quadrature
     weights)"""
     return obj.quad[j]
+
+
+class MpcObjective(object):
+    """The tracking cost of the periodic MPC (awebox/pmpc.py:304-358, 691-706; BASELINE configs[4]) over the MPC trial:
+
+        f = 1/N sum_k sum_j q_j [ (x_kj - ref)' Q (x_kj - ref) + |z_kj - ref|^2 + (u_k - ref)' R (u_k - ref) ]
+            + (x_N - ref)' P (x_N - ref)
+
+    with diagonal Q, R, P and u_param = 'zoh'.  The parameter vector is Pmpc's own (pmpc.py:152-162):
+    ``p = [x0 (n_x) | ref (n_v, laid out like V) | u_ref (1) | Q (n_x) | R (n_u) | P (n_x)]``.
+    Every entry i of V carries at most one term: ``fac[i] * W[kind[i]][idx[i]] * (w_i - ref_i)^2``; the tables below are
+    what the CUDA kernel reads.  ``kind``: 0 none, 1 Q, 2 R, 3 P, 4 unit weight (algebraic variables)."""
+
+    KIND_NONE, KIND_Q, KIND_R, KIND_P, KIND_ONE = 0, 1, 2, 3, 4
+
+    def __init__(self, ocp):
+        if ocp.traj_type != 'mpc':
+            raise NotImplementedError('MpcObjective: trajectory type %r' % ocp.traj_type)
+        self.ocp = ocp
+        n_v, n_x, n_u = ocp.n_v, ocp.n_x, ocp.n_u
+        self.p_x0, self.p_ref = 0, n_x
+        self.p_uref = n_x + n_v
+        self.p_Q = self.p_uref + 1
+        self.p_R = self.p_Q + n_x
+        self.p_P = self.p_R + n_u
+        self.n_p = self.p_P + n_x
+        quad = np.array(ocp.coll.quad_weights, dtype=float).ravel()
+        kind = np.zeros(n_v, dtype=np.int32)
+        idx = np.zeros(n_v, dtype=np.int32)
+        fac = np.zeros(n_v)
+        N = float(ocp.n_k)
+        for k in range(ocp.n_k):
+            for j in range(ocp.d):
+                for m in range(n_x):
+                    i = ocp.v_cx[k][j] + m
+                    kind[i], idx[i], fac[i] = self.KIND_Q, m, quad[j] / N
+                for m in range(ocp.n_z):
+                    i = ocp.v_cz[k][j] + m
+                    kind[i], idx[i], fac[i] = self.KIND_ONE, m, quad[j] / N
+            # the same u_k enters the d terms of the interval one after the other (pmpc.py:338-342)
+            q_sum = 0.0
+            for j in range(ocp.d):
+                q_sum += quad[j] / N
+            for m in range(n_u):
+                i = ocp.v_u[k] + m
+                kind[i], idx[i], fac[i] = self.KIND_R, m, q_sum
+        for m in range(n_x):
+            i = ocp.v_x[ocp.n_k] + m
+            kind[i], idx[i], fac[i] = self.KIND_P, m, 1.0
+        self.kind, self.idx, self.fac = kind, idx, fac
+
+    def weights(self, p):
+        """-> per-entry weight [n_v] for a parameter vector."""
+        table = [np.zeros(1), p[self.p_Q:self.p_Q + self.ocp.n_x], p[self.p_R:self.p_R + self.ocp.n_u],
+                 p[self.p_P:self.p_P + self.ocp.n_x], np.ones(max(1, self.ocp.n_z))]
+        w = np.zeros(self.ocp.n_v)
+        for kd in (self.KIND_Q, self.KIND_R, self.KIND_P, self.KIND_ONE):
+            sel = self.kind == kd
+            w[sel] = table[kd][self.idx[sel]]
+        return w * self.fac
+
+    def evaluate(self, w, p):
+        """-> f, grad [n_v] for one instance (host restatement: test infrastructure)."""
+        wt = self.weights(np.asarray(p, dtype=float))
+        diff = np.asarray(w, dtype=float) - p[self.p_ref:self.p_ref + self.ocp.n_v]
+        return float(np.sum(wt * diff * diff)), 2.0 * wt * diff

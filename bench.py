@@ -361,9 +361,16 @@ def main():
         torch.cuda.synchronize()
         o_ms = o0.elapsed_time(o1) / 10
         o_bytes = B * 8 * (2 * ocp.n_v + 1)                           # read w, write grad f and f
+        # the numpy restatement (awebox_b200/ocp/objective.py, the checker of tests/test_objective.py) on the host, one thread
+        t0c, n_cpu = time.perf_counter(), 0
+        while n_cpu < 4 or (time.perf_counter() - t0c < 1.0 and n_cpu < 64):
+            ob.evaluate(W[n_cpu % B], p_obj)
+            n_cpu += 1
+        cpu_rate = n_cpu / (time.perf_counter() - t0c)
         obj_line = {'ms_per_step': o_ms, 'f_and_grad_evals_per_s': B / (o_ms * 1e-3),
                     'algorithmic_bytes': int(o_bytes), 'GBps': o_bytes / (o_ms * 1e-3) / 1e9,
-                    'api': 'awegpu_eval_objective (device pointers): gather + node kernel + per-instance kernel',
+                    'api': 'awegpu_eval_objective (device pointers): one kernel, CTA = instance',
+                    'cpu_port_evals_per_s': cpu_rate, 'cpu_port': 'numpy restatement, 1 thread, %d instances' % n_cpu,
                     'finite': bool(torch.isfinite(dF).all().item())}
 
     # ---- NCCL gather of the per-rank results (north_star: "NCCL over NVLink used only to gather per-shard results")

@@ -1315,6 +1315,12 @@ class _MapFunction(Function):
     def call(self, args, *unused):
         f, N = self._f, self._N
         mats = [_as_mat(a) for a in args]
+        # CasADi evaluates a Function on arguments with npar times the expected columns npar times, side by side
+        # (FunctionInternal::matching_arg / the implicit map of Function::call); awebox/pmpc.py:328-352 relies on it
+        # (tracking_cost.map(N) called with N * d columns)
+        npar = [a.m // (s.m * N) for a, s in zip(mats, f._ins) if a.m != s.m and a.m % (s.m * N) == 0]
+        if npar and max(npar) > 1:
+            N = N * max(npar)
         cols = [[] for _ in range(f.n_out())]
         for k in range(N):
             sub = []

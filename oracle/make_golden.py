@@ -195,7 +195,69 @@ def run_objective(config, n_k, n_pts):
     print('%s n_k=%d objective: f %s  (%.1f s) -> %s' % (config, n_k, F[:2], time.time() - t0, os.path.relpath(out, ROOT)))
 
 
-OBJ_JOBS = {'ampyx_ap2': [(4, 3), (40, 3)], 'dual_kites': [(3, 2), (20, 2)]}
+def run_mpc_objective(config, n_k, n_pts):
+    """golden vectors of the tracking cost of the periodic MPC (BASELINE configs[4]): the reference's own
+    Pmpc.__generate_objective (awebox/pmpc.py:304-358) run on the MPC trial, with the parameter struct of
+    Pmpc.__construct_solver (pmpc.py:152-162).  Pmpc's constructor needs a solved periodic trial and IPOPT; here the
+    object is created without it and given exactly the attributes the method reads."""
+    t0 = time.time()
+    T = ref_build.build(config, n_k=n_k)
+    import casadi as ct
+    import casadi.tools as ctt
+    import awebox.pmpc as pmpc
+    nlp = T.nlp
+    nx, nu, nz = (T.model.variables_dict[k].cat.shape[0] for k in ('x', 'u', 'z'))
+    p_struct = ctt.struct_symMX([
+        ctt.entry('x0', shape=(nx,)),
+        ctt.entry('ref', struct=nlp.V),
+        ctt.entry('u_ref', shape=(1, 1)),
+        ctt.entry('Q', shape=(nx, 1)),
+        ctt.entry('R', shape=(nu, 1)),
+        ctt.entry('P', shape=(nx, 1)),
+    ])
+
+    class _Trial(object):
+        pass
+    trial = _Trial()
+    trial.nlp = nlp
+    obj = pmpc.Pmpc.__new__(pmpc.Pmpc)
+    for name, val in (('trial', trial), ('mpc_options', {'u_param': 'zoh'}), ('N', n_k), ('d', nlp.d), ('nx', nx),
+                      ('nu', nu), ('nz', nz), ('p', p_struct), ('cost_type', 'tracking')):
+        setattr(obj, '_Pmpc__' + name, val)
+    f = obj._Pmpc__generate_objective()
+    f_fun = ct.Function('f_mpc', [nlp.V, p_struct], [f])
+    rng = np.random.default_rng(20261020 + n_k)
+    n_v, n_p = len(T.w0), p_struct.cat.shape[0]
+    W = np.array([T.w0 * (1.0 + 1e-2 * rng.uniform(-1.0, 1.0, n_v)) + 1e-3 * rng.uniform(-1.0, 1.0, n_v)
+                  for _ in range(n_pts)])
+    P = []
+    for _ in range(n_pts):
+        pn = p_struct(0.0)
+        pn['x0'] = rng.uniform(-1.0, 1.0, nx)
+        pn['ref'] = T.w0 * (1.0 + 1e-2 * rng.uniform(-1.0, 1.0, n_v)) + 1e-3 * rng.uniform(-1.0, 1.0, n_v)
+        pn['u_ref'] = rng.uniform(0.5, 1.5)
+        pn['Q'], pn['R'], pn['P'] = rng.uniform(0.5, 2.0, nx), rng.uniform(0.5, 2.0, nu), rng.uniform(0.5, 2.0, nx)
+        P.append(np.array(pn.cat.full()).ravel())
+    P = np.array(P)
+    f_fun(ct.DM(W[0]), ct.DM(P[0]))
+    tape = f_fun._tape
+    colind, row = tape.jac_ccs(n_v)
+    F, GR = [], []
+    for w, pv in zip(W, P):
+        F.append(float(f_fun(ct.DM(w), ct.DM(pv))))
+        vals = tape.jac_values(np.concatenate([w, pv]), colind, row)
+        g = np.zeros(n_v)
+        for c in range(n_v):
+            if colind[c + 1] > colind[c]:
+                g[c] = vals[colind[c]]
+        GR.append(g)
+    out = os.path.join(GOLDEN, '%s_nk%d_obj.npz' % (config, n_k))
+    np.savez_compressed(out, w=W, p=P, f=np.array(F), grad=np.array(GR), p_labels=np.array(p_struct.labels()))
+    print('%s n_k=%d MPC tracking cost: f %s  (%.1f s) -> %s' % (config, n_k, F[:2], time.time() - t0,
+                                                                 os.path.relpath(out, ROOT)))
+
+
+OBJ_JOBS = {'ampyx_ap2': [(4, 3), (40, 3)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 3)]}
 
 
 if __name__ == '__main__':
@@ -205,7 +267,7 @@ if __name__ == '__main__':
     if '--objective' in sys.argv[1:]:
         for config in (args or list(OBJ_JOBS)):
             for n_k, n_pts in OBJ_JOBS[config]:
-                run_objective(config, n_k, n_pts)
+                (run_mpc_objective if config == 'mpc_3dof' else run_objective)(config, n_k, n_pts)
         sys.exit(0)
     for config in (args or list(JOBS)):
         for i, (n_k, n_pts) in enumerate(JOBS[config]):
