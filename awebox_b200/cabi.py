@@ -47,6 +47,8 @@ class ProblemStruct(C.Structure):
         ('obj_n_tf', C.c_int32), ('obj_tf_idx', P_I32), ('obj_tf_coef', P_F64),
         ('obj_p_weights', C.c_int32), ('obj_p_cost', C.c_int32), ('obj_psi_idx', C.c_int32), ('obj_phi_cost', P_I32),
         ('obj_c_power', C.c_int32), ('obj_c_tf', C.c_int32), ('obj_c_beta', C.c_int32), ('obj_c_cat', P_I32),
+        ('mpc_n_p', C.c_int32), ('mpc_p_ref', C.c_int32), ('mpc_p_Q', C.c_int32), ('mpc_p_R', C.c_int32),
+        ('mpc_p_P', C.c_int32), ('mpc_kind', P_I32), ('mpc_idx', P_I32), ('mpc_fac', P_F64),
     ]
 
 
@@ -114,6 +116,12 @@ def make_problem(ocp):
         ps.obj_p_weights, ps.obj_p_cost = obj.p_weights, obj.p_cost
         ps.obj_psi_idx = obj.phi_idx[obj.phi_names.index('psi')]
         ps.obj_c_power, ps.obj_c_tf, ps.obj_c_beta = COST_NAMES.index('power'), COST_NAMES.index('t_f'), COST_NAMES.index('beta')
+    if ocp.traj_type == 'mpc':
+        from .ocp.objective import MpcObjective
+        mo = MpcObjective(ocp)
+        arrays.update({'mpc_kind': _i32(mo.kind), 'mpc_idx': _i32(mo.idx), 'mpc_fac': _f64(mo.fac)})
+        ps.obj_enabled = 2
+        ps.mpc_n_p, ps.mpc_p_ref, ps.mpc_p_Q, ps.mpc_p_R, ps.mpc_p_P = mo.n_p, mo.p_ref, mo.p_Q, mo.p_R, mo.p_P
     for name, arr in arrays.items():
         ctype = dict(ProblemStruct._fields_)[name]
         setattr(ps, name, arr.ctypes.data_as(ctype))

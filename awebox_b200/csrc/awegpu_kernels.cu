@@ -1398,6 +1398,50 @@ awegpu_obj_kernel(const DevProblem pr, const ObjParams ob, const int B, const do
     }
 }
 
+// --------------------------------------------------------------------------- tracking cost of the periodic MPC
+// (awebox/pmpc.py:304-358; awebox_b200/ocp/objective.py: MpcObjective)  f = sum_i fac_i W_i (w_i - ref_i)^2 over the
+// entries of V with a term (collocation states and algebraic variables, controls, terminal state), weights Q / R / P
+// from Pmpc's parameter vector.  Element-wise in V: CTA = one instance, consecutive threads on consecutive entries
+// (reads of w and ref, store of grad f coalesced), one sum per CTA.  Bound: HBM, 8 (3 n_v + 1) bytes per instance when
+// every instance has its own reference, 8 (2 n_v + 1) with a shared one.
+struct MpcObjParams {
+    const int *kind, *idx;
+    const double *fac;
+    int p_ref, p_w[3];       // offsets of ref and of Q, R, P in the parameter vector
+};
+
+__global__ void __launch_bounds__(256)
+awegpu_obj_mpc_kernel(const MpcObjParams mp, const int n_v, const double *__restrict__ W, const double *__restrict__ P,
+                      const long long ldp, double *__restrict__ F, double *__restrict__ grad)
+{
+    const int b = blockIdx.x;
+    const double *Wb = W + (size_t)b * n_v, *Pb = P + (size_t)b * ldp;
+    double *gb = grad + (size_t)b * n_v;
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < n_v; i += 256) {
+        const int kd = __ldg(mp.kind + i);
+        double g = 0.0;
+        if (kd != 0) {
+            const double wgt = (kd == 4 ? 1.0 : __ldg(Pb + mp.p_w[kd - 1] + __ldg(mp.idx + i))) * __ldg(mp.fac + i);
+            const double diff = __ldg(Wb + i) - __ldg(Pb + mp.p_ref + i);
+            sum = fma(wgt * diff, diff, sum);
+            g = 2.0 * wgt * diff;
+        }
+        gb[i] = g;
+    }
+    __shared__ double s_sum[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_sum[w];
+        F[b] = t;
+    }
+}
+
 static constexpr size_t gather_smem_bytes() { return sizeof(double) * TILE * SLAB_STRIDE; }
 
 // =========================================================================== host side / C ABI
@@ -1441,6 +1485,9 @@ struct awegpu_handle {
     size_t capF = 0, capGrad = 0, capComp = 0;
     const int *obj_rest = nullptr;      // entries of V outside the interval blocks
     int n_obj_rest = 0;
+    bool mpc_obj = false;               // the objective is the tracking cost of the periodic MPC
+    MpcObjParams mp{};
+    int mpc_n_p = 0;
     // single-instance host calls as CUDA graphs (AWEGPU_GRAPH=0 disables)
     bool use_graph = true, capturing = false;
     cudaGraphExec_t graph_exec[8] = {nullptr};
@@ -1847,7 +1894,18 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
         }
         h->chunk_tiles = ct;
     }
-    if (p->obj_enabled) {
+    if (p->obj_enabled == 2) {
+        if (!p->mpc_kind || !p->mpc_idx || !p->mpc_fac || p->mpc_n_p <= 0) {
+            set_err(h, "objective (mpc): the tables of the tracking cost are missing");
+            return 4;
+        }
+        if (to_device(h, p->mpc_kind, (size_t)p->n_v, &h->mp.kind) || to_device(h, p->mpc_idx, (size_t)p->n_v, &h->mp.idx) ||
+            to_device(h, p->mpc_fac, (size_t)p->n_v, &h->mp.fac))
+            return 2;
+        h->mp.p_ref = p->mpc_p_ref, h->mp.p_w[0] = p->mpc_p_Q, h->mp.p_w[1] = p->mpc_p_R, h->mp.p_w[2] = p->mpc_p_P;
+        h->mpc_n_p = p->mpc_n_p;
+        h->mpc_obj = true;
+    } else if (p->obj_enabled) {
         ObjParams &ob = h->ob;
         if (p->n_phi > 16 || p->obj_n_tf > 2 || p->obj_n_tf < 1) {
             set_err(h, "objective: unsupported number of homotopy parameters / time-period terms");
@@ -2359,8 +2417,20 @@ extern "C" int awegpu_eval_objective(awegpu_handle_t *h, int32_t B, const double
 {
     if (!h) return 1;
     if (B <= 0) return 0;
+    if (h->mpc_obj) {
+        if (!W || !P || !F || !GradF || comp || (flags & AWEGPU_P_THETA0)) {
+            set_err(h, "awegpu_eval_objective (mpc): W, P (Pmpc's parameter vectors), F and GradF are required, comp must be NULL");
+            return 1;
+        }
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st_ = stream ? (cudaStream_t)stream : h->stream;
+        awegpu_obj_mpc_kernel<<<B, 256, 0, st_>>>(h->mp, h->dp.n_v, W, P, (flags & AWEGPU_P_SHARED) ? 0 : h->mpc_n_p, F, GradF);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        return 0;
+    }
     if (!h->obj_enabled) {
-        set_err(h, "awegpu_eval_objective: this problem has no objective on this path (trajectory type power_cycle only)");
+        set_err(h, "awegpu_eval_objective: this problem has no objective on this path");
         return 1;
     }
     if (!W || !P || !F || !GradF || (flags & AWEGPU_P_THETA0)) {
@@ -2387,7 +2457,8 @@ extern "C" int awegpu_eval_objective_host(awegpu_handle_t *h, int32_t B, const d
     if (B <= 0) return 0;
     CK(cudaSetDevice(h->device));
     const DevProblem &d = h->dp;
-    const size_t nW = (size_t)B * d.n_v, nP = (flags & AWEGPU_P_SHARED) ? (size_t)d.n_p : (size_t)B * d.n_p;
+    const size_t n_p = h->mpc_obj ? (size_t)h->mpc_n_p : (size_t)d.n_p;
+    const size_t nW = (size_t)B * d.n_v, nP = (flags & AWEGPU_P_SHARED) ? n_p : (size_t)B * n_p;
     int rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, nW, false) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, nP, false) |
              grow_dev(h, &h->dF, &h->capF, (size_t)B) | grow_dev(h, &h->dGrad, &h->capGrad, nW) |
              (comp ? grow_dev(h, &h->dComp, &h->capComp, (size_t)B * 10) : 0);

@@ -81,6 +81,8 @@ class Evaluator(object):
         self.device = int(device)
         self.n_v, self.n_p, self.n_g, self.nnz = self.ocp.n_v, self.ocp.n_p, self.ocp.n_g, self.ocp.nnz
         self.n_theta0 = self.ocp.n_theta0
+        # width of the parameter vectors of eval_objective: the NLP's P, or Pmpc's own parameters for an MPC trial
+        self.n_p_objective = int(self.problem.mpc_n_p) if int(self.problem.obj_enabled) == 2 else self.n_p
         fc, fs = C.c_int64(0), C.c_int64(0)
         self.lib.awegpu_model_dims(None, None, None, None, C.byref(fc), C.byref(fs))
         self.flops_coll, self.flops_shoot = int(fc.value), int(fs.value)
@@ -229,11 +231,12 @@ class Evaluator(object):
 
     def eval_objective(self, W, P, components=False):
         """f [B] and grad f [B, n_v] (dense) for a batch; P: full parameter vectors [B, n_p] or one [n_p]
-        (the objective reads p.ref, p.weights, the cost factors and theta0).  numpy in, numpy out."""
+        (the objective reads p.ref, p.weights, the cost factors and theta0); for an MPC trial: Pmpc's own parameter
+        vectors [B, n_p_objective] (x0, ref, u_ref, Q, R, P).  numpy in, numpy out."""
         W = np.ascontiguousarray(np.atleast_2d(np.asarray(W, dtype=np.float64)))
         B = W.shape[0]
         P = np.ascontiguousarray(np.asarray(P, dtype=np.float64))
-        flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        flags = self.p_flags(P, self.n_p_objective, -1, B)
         F, Gr = np.empty(B), np.empty((B, self.n_v))
         comp = np.empty((B, len(self.COMPONENTS))) if components else None
         rc = self.lib.awegpu_eval_objective_host(self.handle, B, W.ctypes.data, P.ctypes.data, flags, F.ctypes.data,
@@ -245,7 +248,7 @@ class Evaluator(object):
         """device entry (torch CUDA tensors, float64, contiguous)"""
         import torch
         B = W.shape[0]
-        flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        flags = self.p_flags(P, self.n_p_objective, -1, B)
         st = stream if stream is not None else torch.cuda.current_stream(W.device).cuda_stream
         rc = self.lib.awegpu_eval_objective(self.handle, B, W.data_ptr(), P.data_ptr(), flags, F.data_ptr(), GradF.data_ptr(),
                                             None, C.c_void_p(st if st else 1))

@@ -373,6 +373,40 @@ def main():
                     'cpu_port_evals_per_s': cpu_rate, 'cpu_port': 'numpy restatement, 1 thread, %d instances' % n_cpu,
                     'finite': bool(torch.isfinite(dF).all().item())}
 
+    if ocp.traj_type == 'mpc':
+        # tracking cost of the periodic MPC (awebox/pmpc.py:304-358): every scenario its own reference and weights
+        from awebox_b200.ocp.objective import MpcObjective
+        mo = MpcObjective(ocp)
+        rng_o = np.random.default_rng(7 + rank)
+        Pm = np.empty((B, mo.n_p))
+        Pm[:, mo.p_ref:mo.p_ref + ocp.n_v] = W * (1.0 + 1e-2 * rng_o.uniform(-1.0, 1.0, W.shape))
+        Pm[:, :mo.p_ref] = 0.0
+        Pm[:, mo.p_uref:] = rng_o.uniform(0.5, 2.0, (B, mo.n_p - mo.p_uref))
+        dPm = torch.from_numpy(Pm).cuda()
+        dF = torch.empty((B,), dtype=torch.float64, device='cuda')
+        dGr = torch.empty((B, ocp.n_v), dtype=torch.float64, device='cuda')
+        for _ in range(3):
+            ev.eval_objective_device(dW, dPm, dF, dGr)
+        torch.cuda.synchronize()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record(stream)
+        for _ in range(10):
+            ev.eval_objective_device(dW, dPm, dF, dGr)
+        o1.record(stream)
+        torch.cuda.synchronize()
+        o_ms = o0.elapsed_time(o1) / 10
+        o_bytes = B * 8 * (3 * ocp.n_v + 1 + 2 * ocp.n_x + ocp.n_u)   # read w, ref and the weights, write grad f and f
+        t0c, n_cpu = time.perf_counter(), 0
+        while n_cpu < 4 or (time.perf_counter() - t0c < 0.5 and n_cpu < 2000):
+            mo.evaluate(W[n_cpu % B], Pm[n_cpu % B])
+            n_cpu += 1
+        obj_line = {'ms_per_step': o_ms, 'f_and_grad_evals_per_s': B / (o_ms * 1e-3),
+                    'algorithmic_bytes': int(o_bytes), 'GBps': o_bytes / (o_ms * 1e-3) / 1e9,
+                    'api': 'awegpu_eval_objective (device pointers), tracking cost of the periodic MPC: one kernel',
+                    'cpu_port_evals_per_s': n_cpu / (time.perf_counter() - t0c),
+                    'cpu_port': 'numpy restatement, 1 thread, %d instances' % n_cpu,
+                    'finite': bool(torch.isfinite(dF).all().item())}
+
     # ---- NCCL gather of the per-rank results (north_star: "NCCL over NVLink used only to gather per-shard results")
     gather = None
     if args.gather != 'none' and world > 1:

@@ -100,6 +100,15 @@ typedef struct awegpu_problem {
     const int32_t *obj_phi_cost;    /* [n_phi] index into the cost block of every homotopy parameter */
     int32_t obj_c_power, obj_c_tf, obj_c_beta;   /* indices into the cost block */
     const int32_t *obj_c_cat;       /* [5] ... of the five regularisation categories */
+    /* obj_enabled = 2: the tracking cost of the periodic MPC (awebox/pmpc.py:304-358; trajectory type mpc,
+     * awebox_b200/ocp/objective.py: MpcObjective).  The parameter vector of awegpu_eval_objective is then Pmpc's own
+     * (pmpc.py:152-162), mpc_n_p entries: [x0 | ref (n_v) | u_ref | Q (n_x) | R (n_u) | P (n_x)].  Entry i of V carries
+     * the term mpc_fac[i] * weight * (w_i - ref_i)^2 with weight = Q / R / P [mpc_idx[i]] or 1 by mpc_kind[i]
+     * (0 none, 1 Q, 2 R, 3 P, 4 one). */
+    int32_t mpc_n_p, mpc_p_ref, mpc_p_Q, mpc_p_R, mpc_p_P;
+    const int32_t *mpc_kind;        /* [n_v] */
+    const int32_t *mpc_idx;         /* [n_v] */
+    const double  *mpc_fac;         /* [n_v] */
 } awegpu_problem_t;
 
 typedef struct awegpu_handle awegpu_handle_t;
@@ -166,7 +175,9 @@ int awegpu_eval_batch_reduce_host(awegpu_handle_t *h, int32_t B, const double *W
  * trajectory type power_cycle).  W [B, n_v]; P full parameter vectors [B, n_p] or one vector with AWEGPU_P_SHARED
  * (the objective reads p.ref, p.weights, the cost factors and theta0); F [B]; GradF [B, n_v] dense;
  * comp [B, 10] (optional): tracking, xdot regularisation, u regularisation, fictitious, theta regularisation, beta,
- * time, power, homotopy, general problem cost.  Device pointers / host pointers. */
+ * time, power, homotopy, general problem cost.  Device pointers / host pointers.
+ * Trajectory type mpc (obj_enabled = 2): the tracking cost of awebox/pmpc.py:304-358; P are Pmpc's parameter vectors
+ * [B, mpc_n_p] or one vector with AWEGPU_P_SHARED; comp must be NULL. */
 int awegpu_eval_objective(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags,
                           double *F, double *GradF, double *comp, void *stream);
 int awegpu_eval_objective_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags,

@@ -62,10 +62,32 @@ def test_host_restatement_against_reference(name, n_k):
         assert np.all(np.abs(g - gold['grad'][i]) <= grad_tolerance(gold['grad'][i]))
 
 
-def test_objective_is_refused_for_mpc_trials():
-    from awebox_b200.ocp.objective import Objective
+def test_power_cycle_objective_is_refused_for_mpc_trials():
+    from awebox_b200.ocp.objective import Objective, MpcObjective
     with pytest.raises(NotImplementedError):
         Objective(get_ocp('mpc_3dof', 3))
+    with pytest.raises(NotImplementedError):
+        MpcObjective(get_ocp('ampyx_ap2', 4))
+
+
+MPC_CASES = [('mpc_3dof', 3), ('mpc_3dof', 10)]
+
+
+@pytest.mark.parametrize('name,n_k', MPC_CASES)
+def test_mpc_tracking_cost_restatement_against_reference(name, n_k):
+    """awebox_b200/ocp/objective.py: MpcObjective against the reference's own Pmpc.__generate_objective
+    (awebox/pmpc.py:304-358) run on the MPC trial: oracle/make_golden.py --objective mpc_3dof"""
+    from awebox_b200.ocp.objective import MpcObjective
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d_obj.npz' % (name, n_k)))
+    mo = MpcObjective(get_ocp(name, n_k))
+    assert mo.n_p == gold['p'].shape[1]
+    labels = [str(l) for l in gold['p_labels']]
+    assert labels[mo.p_ref].startswith('[ref,') and labels[mo.p_Q] == '[Q,0]' and labels[mo.p_R] == '[R,0]' and labels[mo.p_P] == '[P,0]'
+    for w, p, f, g in zip(gold['w'], gold['p'], gold['f'], gold['grad']):
+        f0, g0 = mo.evaluate(w, p)
+        assert abs(f0 - f) <= 1e-13 * abs(f)
+        assert np.array_equal(g0 != 0.0, g != 0.0)
+        assert np.all(np.abs(g0 - g) <= 1e-13 * np.abs(g))
 
 
 # ---------------------------------------------------------------------------------------------- CUDA path
@@ -122,5 +144,40 @@ def test_cuda_objective_single_instance_entry_points():
     ev = _evaluator('ampyx_ap2', 4)
     assert abs(ev.f_fun(gold['w'][1], gold['p']) - gold['f'][1]) <= 1e-12 * abs(gold['f'][1])
     assert np.all(np.abs(ev.grad_f_fun(gold['w'][1], gold['p']) - gold['grad'][1]) <= grad_tolerance(gold['grad'][1]))
-    with pytest.raises(Exception):
+    with pytest.raises(Exception):      # an MPC trial takes Pmpc's parameter vector, not the NLP's
         _evaluator('mpc_3dof', 3).eval_objective(np.zeros((1, get_ocp('mpc_3dof', 3).n_v)), np.zeros(get_ocp('mpc_3dof', 3).n_p))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,n_k', MPC_CASES)
+def test_cuda_mpc_tracking_cost_against_reference_golden_vectors(name, n_k):
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d_obj.npz' % (name, n_k)))
+    ev = _evaluator(name, n_k)
+    F, G = ev.eval_objective(gold['w'], gold['p'])            # one parameter vector per instance
+    assert np.all(np.abs(F - gold['f']) <= 1e-13 * np.abs(gold['f']))
+    assert np.all(np.abs(G - gold['grad']) <= 1e-13 * np.abs(gold['grad']))
+    f1 = ev.f_fun(gold['w'][2], gold['p'][2])                 # one instance, shared parameter vector
+    assert abs(f1 - gold['f'][2]) <= 1e-13 * abs(gold['f'][2])
+    with pytest.raises(Exception):
+        ev.eval_objective(gold['w'], gold['p'], components=True)
+
+
+@pytest.mark.gpu
+def test_cuda_mpc_tracking_cost_on_seeded_scenario_batch():
+    """8192-scenario shape of BASELINE configs[4] (reduced batch): every scenario its own reference and weights"""
+    from awebox_b200.ocp.objective import MpcObjective
+    gold = np.load(os.path.join(GOLDEN, 'mpc_3dof_nk10_obj.npz'))
+    ev = _evaluator('mpc_3dof', 10)
+    mo = MpcObjective(ev.ocp)
+    rng = np.random.default_rng(5)
+    B = 300
+    W = gold['w'][0][None, :] * (1.0 + 1e-2 * rng.uniform(-1.0, 1.0, (B, ev.n_v)))
+    P = np.tile(gold['p'][0], (B, 1)) * (1.0 + 1e-1 * rng.uniform(-1.0, 1.0, (B, mo.n_p)))
+    F, G = ev.eval_objective(W, P)
+    for b in range(0, B, 13):
+        f0, g0 = mo.evaluate(W[b], P[b])
+        assert abs(F[b] - f0) <= 1e-13 * abs(f0)
+        assert np.all(np.abs(G[b] - g0) <= 1e-13 * np.abs(g0))
+    F2, G2 = ev.eval_objective(W, P[0])                       # shared parameters
+    f0, g0 = mo.evaluate(W[7], P[0])
+    assert abs(F2[7] - f0) <= 1e-13 * abs(f0) and np.all(np.abs(G2[7] - g0) <= 1e-13 * np.abs(g0))
