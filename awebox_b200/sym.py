@@ -425,6 +425,48 @@ def jacobian(exprs, xs):
     return [D.get(e.idx, {}) for e in exprs]
 
 
+def gradient(expr, xs):
+    """Reverse-mode gradient of the scalar ``expr`` with respect to the SYM nodes ``xs``: one sweep over the DAG in
+    reverse topological order.  Returns {column: Expr} with the symbolically non-zero entries."""
+    expr = _e(expr)
+    xs = list(np.asarray(xs, dtype=object).reshape(-1))
+    bar = {expr.idx: ONE}
+    for n in reversed(topo([expr])):
+        bn = bar.get(n.idx)
+        if bn is None or n.op in (CONST, SYM) or bn.is_zero():
+            continue
+        saved, _region[0] = _region[0], n.reg
+        pa, pb = partials(n)
+        for dep, pd in ((n.a, pa), (n.b, pb)):
+            if dep is None or pd is None or dep.op == CONST or pd.is_zero():
+                continue
+            t = mul(pd, bn)
+            old = bar.get(dep.idx)
+            bar[dep.idx] = t if old is None else add(old, t)
+        _region[0] = saved
+    out = {}
+    for j, x in enumerate(xs):
+        v = bar.get(x.idx)
+        if v is not None and not v.is_zero():
+            out[j] = v
+    return out
+
+
+def hessian_triu(expr, xs):
+    """Upper triangle of the Hessian of the scalar ``expr``: forward-mode Jacobian of the reverse-mode gradient.
+    Returns {(a, b): Expr} with a <= b (the union of the symbolic entries of both triangles)."""
+    g = gradient(expr, xs)
+    cols = sorted(g)
+    rows = jacobian([g[c] for c in cols], xs)
+    out = {}
+    for a, d in zip(cols, rows):
+        for b, v in d.items():
+            key = (a, b) if a <= b else (b, a)
+            if key not in out or a <= b:
+                out[key] = v
+    return out
+
+
 def jacobian_dense(exprs, xs):
     exprs = list(np.asarray(exprs, dtype=object).reshape(-1))
     xs = list(np.asarray(xs, dtype=object).reshape(-1))

@@ -231,3 +231,144 @@ def _dbin(op, a, b, f):
 def dependency_pattern(exprs, xs):
     t = Tape(xs, exprs)
     return t.pattern()
+
+
+# ------------------------------------------------------------------ Hessian of the Lagrangian (nlpsol's hess_l)
+class LagrangianHessian(object):
+    """``triu(hessian(lam_g' g(x, p), x))`` the way casadi's ``nlpsol`` builds ``nlp_hess_l`` for an SX oracle:
+    the gradient of the scalar by symbolic reverse mode (``_sx.reverse_gradient``), its Jacobian pattern by structural
+    dependency propagation over the gradient graph (symmetric by construction), the values by forward tangents of
+    the gradient.  Compression of the forward sweeps: columns that couple to (almost) everything (``theta``,
+    ``phi``) get a direction each, the rest a greedy distance-2 colouring of the pattern without those rows and
+    columns; entries in the dense rows are read from the symmetric position."""
+
+    def __init__(self, g_inputs, g_outputs, n_x):
+        self.n_x = n_x
+        self.n_in = len(g_inputs)
+        self.n_g = len(g_outputs)
+        self.lam = [_sx.sym('lam_g_%d' % i) for i in range(self.n_g)]
+        L = _sx.ZERO
+        for l, g in zip(self.lam, g_outputs):
+            L = _sx.binary(_sx.ADD, L, _sx.binary(_sx.MUL, l, g))
+        grad = _sx.reverse_gradient(L, list(g_inputs[:n_x]))
+        self.tape = Tape(list(g_inputs) + self.lam, grad)
+        rows = self.tape.pattern()                  # row i: columns (inputs) d grad_i depends on
+        cols = [[] for _ in range(n_x)]
+        for i, cs in enumerate(rows):
+            for j in cs:
+                if j < n_x:
+                    cols[j].append(i)
+        # symmetric closure (the structural pattern of a reverse-over-forward graph is symmetric up to
+        # simplifications; casadi symmetrises), then the upper triangle
+        full = [set(c) for c in cols]
+        for j in range(n_x):
+            for i in list(full[j]):
+                full[i].add(j)
+        self.full_cols = [sorted(c) for c in full]
+        colind, row = [0], []
+        for j in range(n_x):
+            row.extend(i for i in self.full_cols[j] if i <= j)
+            colind.append(len(row))
+        self.colind, self.row = np.array(colind, dtype=np.int64), np.array(row, dtype=np.int64)
+        self._colour()
+
+    def _colour(self):
+        n = self.n_x
+        deg = np.array([len(c) for c in self.full_cols])
+        limit = max(64, 4 * int(np.median(deg[deg > 0])) if (deg > 0).any() else 64)
+        self.head = [j for j in range(n) if deg[j] > limit]
+        is_head = np.zeros(n, dtype=bool)
+        is_head[self.head] = True
+        colour = [-1] * n
+        for c, j in enumerate(self.head):
+            colour[j] = c
+        base = len(self.head)
+        row_cols = {}
+        for j in range(n):
+            if is_head[j]:
+                continue
+            for r in self.full_cols[j]:
+                if not is_head[r]:
+                    row_cols.setdefault(r, []).append(j)
+        for j in range(n):
+            if is_head[j]:
+                continue
+            forbidden = set()
+            for r in self.full_cols[j]:
+                if is_head[r]:
+                    continue
+                for j2 in row_cols[r]:
+                    if colour[j2] >= 0:
+                        forbidden.add(colour[j2])
+            c = base
+            while c in forbidden:
+                c += 1
+            colour[j] = c
+        self.colour, self.is_head = colour, is_head
+        self.n_colours = max(colour) + 1 if colour else 0
+
+    def tangent(self, xin, seeds):
+        """forward tangents of the gradient tape: d grad / d inputs . seeds;  seeds {input slot: array [nd]}"""
+        t = self.tape
+        w = [None] * t.n_work
+        dw = [None] * t.n_work
+        for j in range(t.n_in):
+            w[j] = xin[j]
+            dw[j] = seeds.get(j)
+        for k, v in t.consts:
+            w[k] = v
+        with np.errstate(all='ignore'):
+            for op, k, a, b in t.instr:
+                wa, da = w[a], dw[a]
+                if b < 0:
+                    f = _UN[op](wa)
+                    w[k] = f
+                    dw[k] = None if da is None else _dun(op, wa, f) * da
+                else:
+                    wb, db = w[b], dw[b]
+                    f = _BIN[op](wa, wb)
+                    w[k] = f
+                    if da is None and db is None:
+                        continue
+                    pa, pb = _dbin(op, wa, wb, f)
+                    if da is None:
+                        dw[k] = pb * db
+                    elif db is None:
+                        dw[k] = pa * da
+                    else:
+                        dw[k] = pa * da + pb * db
+        return [w[s] for s in t.out_slots], [dw[s] for s in t.out_slots]
+
+    def values(self, x, p, lam):
+        """non-zeros of triu(H) in CCS order at (x, p, lam)"""
+        xin = np.concatenate([x, p, lam])
+        nc = self.n_colours
+        seeds = {}
+        for j in range(self.n_x):
+            s = np.zeros(nc)
+            s[self.colour[j]] = 1.0
+            seeds[j] = s
+        _, dg = self.tangent(xin, seeds)
+        vals = np.zeros(len(self.row))
+        for j in range(self.n_x):
+            for q in range(self.colind[j], self.colind[j + 1]):
+                i = int(self.row[q])
+                # entry (i, j), i <= j: column j seeded alone within row i unless row i is dense
+                if self.is_head[i] and not self.is_head[j]:
+                    d = dg[j]
+                    vals[q] = 0.0 if d is None else d[self.colour[i]]
+                else:
+                    d = dg[i]
+                    vals[q] = 0.0 if d is None else d[self.colour[j]]
+        return vals
+
+    def times(self, x, p, lam, V):
+        """H . V for a dense direction block V [n_x, nd] (full symmetric product; independent of the colouring)"""
+        xin = np.concatenate([x, p, lam])
+        seeds = {j: V[j] for j in range(self.n_x)}
+        _, dg = self.tangent(xin, seeds)
+        out = np.zeros((self.n_x, V.shape[1]))
+        for i, d in enumerate(dg):
+            if d is not None:
+                out[i] = d
+        return out

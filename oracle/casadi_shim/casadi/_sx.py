@@ -488,3 +488,26 @@ def forward_jac(exprs, xs):
         if d:
             D[id(n)] = d
     return [D.get(id(e), {}) for e in exprs]
+
+
+def reverse_gradient(root, xs):
+    """Symbolic gradient d root / d xs by reverse-mode AD over the expression graph (what ``SX::gradient`` =
+    ``jtimes(ex, arg, 1, true)`` does in casadi: ``SXFunction::ad_reverse`` walks the instruction list backwards and
+    adds ``partial * seed`` to the adjoint of each dependency, with the construction-time simplifications applied).
+    Returns a list (one per x) of nodes (ZERO where the root does not reach x)."""
+    order = topo([root])
+    bar = {id(root): ONE}
+    for n in reversed(order):
+        bn = bar.get(id(n))
+        if bn is None or n.op == SYM or n.op == CONST or is_zero(bn):
+            continue
+        pa, pb = partials(n)
+        for dep, pd in ((n.a, pa), (n.b, pb)):
+            if dep is None or pd is None or dep.op == CONST or is_zero(pd):
+                continue
+            t = bn if is_one(pd) else binary(MUL, pd, bn)
+            if is_zero(t):
+                continue
+            old = bar.get(id(dep))
+            bar[id(dep)] = t if old is None else binary(ADD, old, t)
+    return [bar.get(id(x), ZERO) for x in xs]

@@ -257,13 +257,58 @@ def run_mpc_objective(config, n_k, n_pts):
                                                                  os.path.relpath(out, ROOT)))
 
 
+def run_hessian(config, n_k, n_pts):
+    """golden vectors of the second-order hook: the upper triangle of the Hessian of
+    lam_g' g(V, P) with respect to V, pattern and values, formed the way casadi's nlpsol forms ``nlp_hess_l`` from the
+    reference's own ``nlp.g_fun`` (awebox/opti/preparation.py:373-379 with hessian_approximation = False,
+    awebox/opts/default.py:323; the Lagrangian the reference writes down itself: awebox/tools/debug_operations.py:567-596)
+    -> tests/golden/<config>_nk<N>_hess.npz.  The compressed sweeps are cross-checked here against uncompressed
+    Hessian-times-direction products of the same tape."""
+    t0 = time.time()
+    T = ref_build.build(config, n_k=n_k)
+    import casadi as cas
+    from casadi import _eval
+    nlp = T.nlp
+    n_v = len(T.w0)
+    g_fun = nlp.g_fun
+    ins = [v for s in g_fun._ins for v in s.e]
+    outs = [v for o in g_fun._outs for v in o.e]
+    LH = _eval.LagrangianHessian(ins, outs, n_v)
+    rng = np.random.default_rng(20261021 + n_k)
+    W = perturbed_points(T.w0, n_pts, 20261018 + n_k)
+    p = T.p0
+    LAM = rng.uniform(-1.0, 1.0, (n_pts, LH.n_g))
+    HV = np.array([LH.values(w, p, lam) for w, lam in zip(W, LAM)])
+    # self-check of the compression: H . D for three dense directions
+    D = rng.uniform(-1.0, 1.0, (n_v, 3))
+    HD = LH.times(W[-1], p, LAM[-1], D)
+    import scipy.sparse as sps
+    U = sps.csc_matrix((HV[-1], LH.row, LH.colind), shape=(n_v, n_v))
+    full = U + sps.triu(U, 1).T
+    err = np.abs(full @ D - HD).max() / max(1.0, np.abs(HD).max())
+    assert err < 1e-12, err
+    out = os.path.join(GOLDEN, '%s_nk%d_hess.npz' % (config, n_k))
+    np.savez_compressed(out, w=W, p=p, lam=LAM, colind=LH.colind, row=LH.row, hv=HV, dirs=D, hd=HD)
+    print('%s n_k=%d hess_lag (constraint part): n_v=%d nnz(triu)=%d colours=%d dense columns=%d  check %.1e  (%.1f s) -> %s'
+          % (config, n_k, n_v, len(LH.row), LH.n_colours, len(LH.head), err, time.time() - t0, os.path.relpath(out, ROOT)))
+
+
+HESS_JOBS = {'ampyx_ap2': [(4, 3), (40, 2)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 3)]}
+
 OBJ_JOBS = {'ampyx_ap2': [(4, 3), (40, 3)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 3)]}
 
 
 if __name__ == '__main__':
     import logging
     logging.disable(logging.CRITICAL)
-    args = [a for a in sys.argv[1:] if a != '--objective']
+    args = [a for a in sys.argv[1:] if a not in ('--objective', '--hessian')]
+    if '--hessian' in sys.argv[1:]:
+        small = '--small' in args
+        args = [a for a in args if a != '--small']
+        for config in (args or list(HESS_JOBS)):
+            for n_k, n_pts in (HESS_JOBS[config][:1] if small else HESS_JOBS[config]):
+                run_hessian(config, n_k, n_pts)
+        sys.exit(0)
     if '--objective' in sys.argv[1:]:
         for config in (args or list(OBJ_JOBS)):
             for n_k, n_pts in OBJ_JOBS[config]:
