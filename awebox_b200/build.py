@@ -37,6 +37,8 @@ def generate(spec_name, ocp=None):
     if ocp is None:
         ocp = OcpProblem(ModelSpec.load(spec_name))
     stats = NodeCode(ocp).write(gen_dir(spec_name))
+    from .ocp.hessian import LagrangianHessian
+    stats['hessian'] = LagrangianHessian(ocp).write(gen_dir(spec_name))
     with open(os.path.join(gen_dir(spec_name), 'stats.json'), 'w') as f:
         json.dump(stats, f, indent=1, sort_keys=True)
     return ocp, stats
@@ -65,7 +67,7 @@ def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None
     os.makedirs(LIBDIR, exist_ok=True)
     g = gen or gen_dir(spec_name)
     src = os.path.join(CSRC, 'awegpu_kernels.cu')
-    deps = [src] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", "_reduce.cu"))] + \
+    deps = [src] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", "_reduce.cu", "_hess.cu"))] + \
         [os.path.join(g, f) for f in sorted(os.listdir(g)) if f.endswith(('.h', '.inc'))] + \
         [os.path.join(ROOT, 'include', 'awegpu.h')]
     out = out or lib_path(spec_name)
@@ -91,8 +93,14 @@ def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None
         cmd = [nvcc] + common + ['-c', '-o', obj, os.path.join(CSRC, 'awegpu_reduce.cu')]
         return 'reduce', obj, cmd, subprocess.run(cmd, capture_output=True, text=True)
 
-    with ThreadPoolExecutor(N_TU + 1) as pool:
-        futs = [pool.submit(one, tu) for tu in range(N_TU)] + [pool.submit(reduce_unit, 0)]
+    def hess_unit(_):
+        # second-order hook (awegpu_hess.cu + generated node_hess_*.inc)
+        obj = os.path.join(objdir, 'hess.o')
+        cmd = [nvcc] + common + ['-c', '-o', obj, os.path.join(CSRC, 'awegpu_hess.cu')]
+        return 'hess', obj, cmd, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(N_TU + 2) as pool:
+        futs = [pool.submit(one, tu) for tu in range(N_TU)] + [pool.submit(reduce_unit, 0), pool.submit(hess_unit, 0)]
         results = [f.result() for f in futs]
     for tu, obj, cmd, res in results:
         logs.append(' '.join(cmd) + '\n' + res.stdout + res.stderr)

@@ -34,6 +34,7 @@
 
 #include "awegpu.h"
 #include "awegpu_reduce.h"
+#include "awegpu_hess.h"
 #include "model_defs.h"
 
 // Translation units.  The generated programs make this file expensive to compile (minutes of single-threaded
@@ -126,7 +127,6 @@ __constant__ double c_kconst[AWE_N_KCONST] = AWE_KCONST_INIT;
 __constant__ double c_coeff_coll[(N_D + 1) * (N_D + 1)];
 __constant__ double c_coeff_cont[N_D + 1];
 
-#define SIGN(x) ((double)(((x) > 0.0) - ((x) < 0.0)))
 // Reciprocal / reciprocal square root from the MUFU seed (>= 20 bits) and two Newton steps, without the
 // special-case paths of the CUDA library versions.  Division and square root get one extra residual
 // correction, which leaves them within 1 ulp of the correctly rounded result for finite, normal arguments
@@ -136,45 +136,7 @@ __constant__ double c_coeff_cont[N_D + 1];
 // arguments are read as zero.  Testing every division and root for these cases (a compare, a branch and an
 // out-of-line IEEE sequence per operation) was measured: 7 % (AP2) to 15 % (3-DOF) of the step, and rejected;
 // tests/test_gpu_parity.py::test_non_finite_and_degenerate_inputs_match_the_checker pins the behaviour.
-__device__ __forceinline__ double rcp_nr(const double x)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-__device__ __forceinline__ double div_nr(const double a, const double b)
-{
-    const double r = rcp_nr(b);
-    const double q = a * r;
-    return fma(fma(-b, q, a), r, q);
-}
-__device__ __forceinline__ double rsqrt_nr(const double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x * y, y, 1.0);
-    y = fma(y * 0.5, e, y);
-    e = fma(-x * y, y, 1.0);
-    return fma(y * 0.5, e, y);
-}
-__device__ __forceinline__ double sqrt_nr(const double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = fmin(y, 1e300);                         // rsqrt(0) = inf: keep 0 * y = 0
-    double e = fma(-x * y, y, 1.0);
-    y = fma(y * 0.5, e, y);
-    e = fma(-x * y, y, 1.0);
-    y = fma(y * 0.5, e, y);
-    const double s = x * y;
-    return fma(fma(-s, s, x), 0.5 * y, s);
-}
-#define RSQRT(x) rsqrt_nr(x)
-#define SQRTF(x) sqrt_nr(x)
-#define DIVF(a, b) div_nr(a, b)
+#include "awegpu_arith.cuh"
 
 // ---- statement macros of the generated code -------------------------------------------------------
 // asm volatile: the compiler must neither merge the generator's reloads into one long-lived register
@@ -1488,6 +1450,15 @@ struct awegpu_handle {
     bool mpc_obj = false;               // the objective is the tracking cost of the periodic MPC
     MpcObjParams mp{};
     int mpc_n_p = 0;
+    // second-order hook (awegpu_hess.cu): tables uploaded by awegpu_hess_setup
+    bool hess_ready = false;
+    HessArgs hs{};
+    std::vector<long long> hess_colind, hess_row, sp_hess, sp_lamf;
+    double *hess_scr = nullptr, *dHess = nullptr, *dLamH = nullptr;
+    size_t cap_hess_scr = 0, capHess = 0, capLamH = 0;
+    int hess_chunk_tiles = 64;
+    float hess_ms = -1.f;
+    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;
     // single-instance host calls as CUDA graphs (AWEGPU_GRAPH=0 disables)
     bool use_graph = true, capturing = false;
     cudaGraphExec_t graph_exec[8] = {nullptr};
@@ -1566,6 +1537,9 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     cudaFree(h->sc.rec), cudaFree(h->sc.xdc), cudaFree(h->sc.pt), cudaFree(h->sc.exc), cudaFree(h->sc.exs);
     cudaFree(h->counters), cudaFree(h->dLam), cudaFree(h->dVec), cudaFree(h->dRed);
     cudaFree(h->dF), cudaFree(h->dGrad), cudaFree(h->dComp);
+    cudaFree(h->hess_scr), cudaFree(h->dHess), cudaFree(h->dLamH);
+    if (h->ev_h0) cudaEventDestroy(h->ev_h0);
+    if (h->ev_h1) cudaEventDestroy(h->ev_h1);
     for (cudaGraphExec_t ge : h->graph_exec)
         if (ge) cudaGraphExecDestroy(ge);
     cudaFreeHost(h->hW), cudaFreeHost(h->hP), cudaFreeHost(h->hG), cudaFreeHost(h->hJ);
@@ -2475,6 +2449,136 @@ extern "C" int awegpu_eval_objective_host(awegpu_handle_t *h, int32_t B, const d
     return 0;
 }
 
+
+// --------------------------------------------------------------------------- second-order hook
+extern "C" int awegpu_hess_setup(awegpu_handle_t *h, int64_t nnz, int32_t n_hv, int64_t n_asm, const int64_t *colind,
+                                 const int64_t *row, const int64_t *asm_ptr, const int64_t *asm_idx, const double *asm_coef,
+                                 int32_t v_x0, int32_t row0, int32_t row_stride, const double *coeff)
+{
+    if (!h || !colind || !row || !asm_ptr || !asm_idx || !asm_coef || !coeff || nnz <= 0 || n_asm <= 0) return 1;
+    if (n_asm >= (1LL << 31) || nnz >= (1LL << 31)) {
+        set_err(h, "awegpu_hess_setup: table too large for 32-bit indices");
+        return 1;
+    }
+    CK(cudaSetDevice(h->device));
+    const DevProblem &d = h->dp;
+    h->hess_colind.assign(colind, colind + d.n_v + 1);
+    h->hess_row.assign(row, row + nnz);
+    std::vector<int> ptr32(asm_ptr, asm_ptr + nnz + 1), idx32(asm_idx, asm_idx + n_asm);
+    HessArgs &a = h->hs;
+    a = HessArgs{};
+    int rc = to_device(h, ptr32.data(), ptr32.size(), &a.asm_ptr) | to_device(h, idx32.data(), idx32.size(), &a.asm_idx) |
+             to_device(h, asm_coef, (size_t)n_asm, &a.asm_coef);
+    if (rc) return rc;
+    a.n_v = d.n_v, a.n_g = d.n_g, a.n_k = d.n_k, a.n_hv = n_hv, a.nnz = nnz;
+    a.v_x0 = v_x0, a.v_phi = d.v_phi, a.row0 = row0, a.row_stride = row_stride;
+    a.theta_idx = d.theta_idx;
+    if (awe_hess_set_coeff(coeff)) {
+        set_err(h, "awegpu_hess_setup: cudaMemcpyToSymbol failed");
+        return 2;
+    }
+    h->sp_hess.clear();
+    h->sp_hess.push_back(d.n_v);
+    h->sp_hess.push_back(d.n_v);
+    h->sp_hess.insert(h->sp_hess.end(), h->hess_colind.begin(), h->hess_colind.end());
+    h->sp_hess.insert(h->sp_hess.end(), h->hess_row.begin(), h->hess_row.end());
+    h->sp_lamf = {1, 1, 1};
+    if (!h->ev_h0) CK(cudaEventCreate(&h->ev_h0));
+    if (!h->ev_h1) CK(cudaEventCreate(&h->ev_h1));
+    h->hess_ready = true;
+    return 0;
+}
+
+extern "C" int64_t awegpu_hess_nnz(awegpu_handle_t *h) { return (h && h->hess_ready) ? h->hs.nnz : -1; }
+
+extern "C" int awegpu_hess_sparsity(awegpu_handle_t *h, int64_t *colind, int64_t *row)
+{
+    if (!h || !h->hess_ready) return 1;
+    for (size_t i = 0; i < h->hess_colind.size(); ++i) colind[i] = h->hess_colind[i];
+    for (size_t i = 0; i < h->hess_row.size(); ++i) row[i] = h->hess_row[i];
+    return 0;
+}
+
+extern "C" int awegpu_eval_hessian(awegpu_handle_t *h, int32_t B, const double *W, const double *P, const double *Lam,
+                                   int32_t flags, double *H, void *stream)
+{
+    if (!h) return 1;
+    if (B <= 0) return 0;
+    if (!h->hess_ready) {
+        set_err(h, "awegpu_eval_hessian: awegpu_hess_setup has not been called for this handle");
+        return 1;
+    }
+    if (!W || !P || !Lam || !H) {
+        set_err(h, "awegpu_eval_hessian: W, P, Lam and H are required");
+        return 1;
+    }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const DevProblem &d = h->dp;
+    const int tiles = (B + TILE - 1) / TILE;
+    const int chunk = tiles < h->hess_chunk_tiles ? tiles : h->hess_chunk_tiles;
+    const size_t need = awe_hess_scratch_per_tile(h->hs.n_hv) / sizeof(double) * (size_t)chunk;
+    if (need > h->cap_hess_scr) {
+        CK(cudaStreamSynchronize(st));
+        int rc = grow_dev(h, &h->hess_scr, &h->cap_hess_scr, need);
+        if (rc) return rc;
+    }
+    HessArgs a = h->hs;
+    a.B = B, a.W = W, a.P = P, a.Lam = Lam, a.H = H, a.scr = h->hess_scr;
+    a.ld_p = (flags & AWEGPU_P_SHARED) ? 0 : ((flags & AWEGPU_P_THETA0) ? d.n_theta0 : d.n_p);
+    a.p_off = (flags & AWEGPU_P_THETA0) ? 0 : d.p_theta0;
+    CK(cudaEventRecord(h->ev_h0, st));
+    for (int t0 = 0; t0 < tiles; t0 += chunk) {
+        const int nt = tiles - t0 < chunk ? tiles - t0 : chunk;
+        const int e = awe_hess_launch(st, a, t0, nt);
+        if (e) {
+            set_err(h, std::string("awegpu_eval_hessian: ") + cudaGetErrorString((cudaError_t)e));
+            return 2;
+        }
+        h->launches += 2;
+    }
+    CK(cudaEventRecord(h->ev_h1, st));
+    h->hess_ms = -2.f;      // recorded, not read yet
+    return 0;
+}
+
+extern "C" float awegpu_last_hessian_ms(awegpu_handle_t *h)
+{
+    if (!h || h->hess_ms == -1.f) return -1.f;
+    if (cudaEventSynchronize(h->ev_h1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev_h0, h->ev_h1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+extern "C" int awegpu_eval_hessian_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P, const double *Lam,
+                                        int32_t flags, double *H)
+{
+    if (!h) return 1;
+    if (B <= 0) return 0;
+    if (!h->hess_ready) {
+        set_err(h, "awegpu_eval_hessian_host: awegpu_hess_setup has not been called for this handle");
+        return 1;
+    }
+    CK(cudaSetDevice(h->device));
+    const DevProblem &d = h->dp;
+    const size_t ldp = (flags & AWEGPU_P_THETA0) ? (size_t)d.n_theta0 : (size_t)d.n_p;
+    const size_t nW = (size_t)B * d.n_v, nP = (flags & AWEGPU_P_SHARED) ? ldp : (size_t)B * ldp;
+    const size_t nL = (size_t)B * d.n_g, nH = (size_t)B * (size_t)h->hs.nnz;
+    int rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, nW, false) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, nP, false) |
+             grow_dev(h, &h->dLamH, &h->capLamH, nL) | grow_dev(h, &h->dHess, &h->capHess, nH);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->dW, W, nW * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->dLamH, Lam, nL * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = awegpu_eval_hessian(h, B, h->dW, h->dP, h->dLamH, flags, h->dHess, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(H, h->dHess, nH * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 // --------------------------------------------------------------------------- CasADi external ABI
 static void dense_sp(std::vector<long long> &v, long long n)
 {
@@ -2541,7 +2645,6 @@ static int casadi_eval(const double **arg, double **res, bool jac, int mem)
     extern "C" void F##_free_mem(int) {}
 CASADI_MEM_FUNCS(awegpu_g)
 CASADI_MEM_FUNCS(jac_awegpu_g)
-#undef CASADI_MEM_FUNCS
 
 extern "C" int awegpu_g(const double **arg, double **res, long long *, double *, int mem) { return casadi_eval(arg, res, false, mem); }
 extern "C" long long awegpu_g_n_in(void) { return 2; }
@@ -2593,5 +2696,51 @@ extern "C" int jac_awegpu_g_work(long long *sz_arg, long long *sz_res, long long
     if (sz_w) *sz_w = 0;
     return 0;
 }
+
+// hess_lag for cas.nlpsol(..., {'hess_lag': external('awegpu_hess_lag', lib)}): inputs (x, p, lam_f, lam_g), output the
+// upper triangle of the Hessian of the constraint part lam_g' g (awebox/opts/default.py:323 hessian_approximation = False).
+// lam_f is accepted and not used: the objective part of the Hessian is not on this path.
+CASADI_MEM_FUNCS(awegpu_hess_lag)
+extern "C" int awegpu_hess_lag(const double **arg, double **res, long long *, double *, int mem)
+{
+    awegpu_handle *h = casadi_handle(mem);
+    if (!h) return 1;
+    if (!arg || !arg[0] || !arg[1]) {
+        set_err(h, "awegpu_hess_lag: x and p must be given");
+        return 1;
+    }
+    double *out = res ? res[0] : nullptr;
+    if (!out) return 0;
+    std::lock_guard<std::mutex> lock(h->casadi_mu);
+    if (!arg[3]) {          // NULL = all-zero multipliers: the constraint part vanishes
+        for (long long i = 0; i < h->hs.nnz; ++i) out[i] = 0.0;
+        return 0;
+    }
+    return awegpu_eval_hessian_host(h, 1, arg[0], arg[1], arg[3], 0, out);
+}
+extern "C" long long awegpu_hess_lag_n_in(void) { return 4; }
+extern "C" long long awegpu_hess_lag_n_out(void) { return 1; }
+extern "C" const char *awegpu_hess_lag_name_in(long long i) { return i == 0 ? "x" : i == 1 ? "p" : i == 2 ? "lam_f" : i == 3 ? "lam_g" : nullptr; }
+extern "C" const char *awegpu_hess_lag_name_out(long long i) { return i == 0 ? "triu_hess_gamma_x_x" : nullptr; }
+extern "C" const long long *awegpu_hess_lag_sparsity_in(long long i)
+{
+    awegpu_handle *h = casadi_handle(-1);
+    if (!h || !h->hess_ready) return nullptr;
+    return i == 0 ? h->sp_v.data() : i == 1 ? h->sp_p.data() : i == 2 ? h->sp_lamf.data() : i == 3 ? h->sp_g.data() : nullptr;
+}
+extern "C" const long long *awegpu_hess_lag_sparsity_out(long long i)
+{
+    awegpu_handle *h = casadi_handle(-1);
+    return (h && h->hess_ready && i == 0) ? h->sp_hess.data() : nullptr;
+}
+extern "C" int awegpu_hess_lag_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w)
+{
+    if (sz_arg) *sz_arg = 4;
+    if (sz_res) *sz_res = 1;
+    if (sz_iw) *sz_iw = 0;
+    if (sz_w) *sz_w = 0;
+    return 0;
+}
+#undef CASADI_MEM_FUNCS
 
 #endif  /* TU_OWNS(0) */

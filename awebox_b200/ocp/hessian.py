@@ -41,7 +41,8 @@ class LagrangianHessian(object):
         # ---- collocation node over the extended variables
         self.xsum = S.symvec('xsum', n_x)
         tf = m.vars[ocp.tf_local]
-        inv_h_tf = S.const(float(n_k)) / tf
+        self.nk_sym = S.sym('n_k')                        # run-time leaf: one library serves every n_k
+        inv_h_tf = self.nk_sym / tf
         xdot_sym = m.vars[rng['xdot'][0]:rng['xdot'][1]]
         self.xdot_of = [self.xsum[i] * inv_h_tf for i in range(n_x)]
         eq_ext = S.substitute(eq, {xdot_sym[i]: self.xdot_of[i] for i in range(n_x)})
@@ -198,8 +199,8 @@ class LagrangianHessian(object):
         lc, ls = self.node_multipliers(lam)
         par = list(m.params[:m.n_theta0])
         n_c, n_s = xc.shape[1], xs.shape[1]
-        vc = S.evaluate(self.coll_exprs, self.ext_in + par + list(self.lam_c),
-                        np.concatenate([xc, np.repeat(theta0[:, None], n_c, 1), lc]))
+        vc = S.evaluate(self.coll_exprs, self.ext_in + par + list(self.lam_c) + [self.nk_sym],
+                        np.concatenate([xc, np.repeat(theta0[:, None], n_c, 1), lc, np.full((1, n_c), float(ocp.n_k))]))
         vs = S.evaluate(self.shoot_exprs, self.local_in + par + list(self.lam_s),
                         np.concatenate([xs, np.repeat(theta0[:, None], n_s, 1), ls]))
         hv = np.zeros(self.n_hv)
@@ -216,3 +217,54 @@ class LagrangianHessian(object):
         hv = self.node_values(np.asarray(w, dtype=float), np.asarray(p, dtype=float), np.asarray(lam, dtype=float))
         prod = self.asm_coef * hv[self.asm_idx]
         return np.add.reduceat(prod, self.asm_ptr[:-1])
+
+    # ------------------------------------------------------------------ generated node programs (CUDA path)
+    def emit(self, exprs, lam, xsum=None):
+        """straight-line code ``HOUT(n, value)`` over the leaves ``VIN(i)`` (node variables; ``XSIN(i)`` in place of
+        xdot for a collocation node), ``PIN(i)`` (theta0 | phi), ``LIN(i)`` (multipliers), ``HNK`` (n_k)."""
+        from ..codegen import _rhs, _fmt
+        m = self.ocp.model
+        names = {}
+        for i, v in enumerate(m.vars):
+            names[v.idx] = 'VIN(%d)' % i
+        for i, v in enumerate(m.params):
+            names[v.idx] = 'PIN(%d)' % i
+        for i, v in enumerate(lam):
+            names[v.idx] = 'LIN(%d)' % i
+        if xsum is not None:
+            for i, v in enumerate(xsum):
+                names[v.idx] = 'XSIN(%d)' % i
+        names[self.nk_sym.idx] = 'HNK'
+        lines, n_tmp = [], 0
+        out_of = {}
+        for k, e in enumerate(exprs):
+            out_of.setdefault(e.idx, []).append(k)
+
+        def ref(n):
+            return _fmt(n.val) if n.op == S.CONST else names[n.idx]
+        for n in S.topo(exprs):
+            if n.op == S.SYM:
+                if n.idx not in names:
+                    raise ValueError('free symbol %s in the node Hessian' % n.name)
+            elif n.op != S.CONST:
+                names[n.idx] = 't%d' % n_tmp
+                lines.append('const double t%d = %s;' % (n_tmp, _rhs(n.op, ref(n.a), ref(n.b) if n.b is not None else None)))
+                n_tmp += 1
+            for k in out_of.get(n.idx, []):
+                lines.append('HOUT(%d, %s);' % (k, ref(n)))
+        return '\n'.join(lines) + '\n', n_tmp
+
+    def write(self, out_dir):
+        """node_hess_coll.inc, node_hess_shoot.inc, hess_defs.h -> out_dir; returns statistics"""
+        import os
+        coll, n_c = self.emit(self.coll_exprs, self.lam_c, self.xsum)
+        shoot, n_s = self.emit(self.shoot_exprs, self.lam_s)
+        defs = ('// generated by awebox_b200/ocp/hessian.py -- do not edit\n'
+                '#define AWE_H_NEC %d\n#define AWE_H_NES %d\n#define AWE_H_NLAM_S %d\n'
+                % (self.n_ec, self.n_es, len(self.shoot_rows)))
+        for name, text in (('node_hess_coll.inc', coll), ('node_hess_shoot.inc', shoot), ('hess_defs.h', defs)):
+            path = os.path.join(out_dir, name)
+            if not os.path.exists(path) or open(path).read() != text:
+                with open(path, 'w') as f:
+                    f.write(text)
+        return {'hess_coll_ops': n_c, 'hess_shoot_ops': n_s, 'hess_coll_entries': self.n_ec, 'hess_shoot_entries': self.n_es}

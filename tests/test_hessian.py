@@ -71,3 +71,113 @@ def test_hessian_is_the_derivative_of_jT_lambda(name, n_k):
     U = sps.csc_matrix((H.evaluate(w, p, lam), H.row, H.colind), shape=(ocp.n_v, ocp.n_v))
     hd = (U + sps.triu(U, 1).T) @ dirn
     assert np.abs(hd - fd).max() <= 1e-6 * max(1.0, np.abs(hd).max())
+
+
+# ------------------------------------------------------------------------------------------------ CUDA path
+_EV = {}
+
+
+def evaluator(name, n_k):
+    from awebox_b200.evaluator import Evaluator
+    if (name, n_k) not in _EV:
+        _EV[(name, n_k)] = Evaluator(name, ocp=get_ocp(name, n_k))
+        _EV[(name, n_k)].hess = hessian(name, n_k) if (name, n_k) in _H else None
+        _EV[(name, n_k)].hessian_setup()
+    return _EV[(name, n_k)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,n_k', CASES)
+def test_gpu_against_reference_golden_vectors(name, n_k):
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d_hess.npz' % (name, n_k)))
+    ev = evaluator(name, n_k)
+    colind, row = ev.hess_sparsity()
+    assert colind.dtype == np.int64 and row.dtype == np.int64
+    assert np.array_equal(colind, gold['colind']) and np.array_equal(row, gold['row'])
+    H = ev.eval_hessian(gold['w'], gold['p'], gold['lam'])
+    Hh = hessian(name, n_k)
+    for hv, ref in zip(H, gold['hv']):
+        assert np.all(np.abs(hv - ref) <= hess_tolerance(Hh, ref))
+    # one instance per call, the way nlpsol calls hess_lag
+    one = ev.hess_lag_fun(gold['w'][0], gold['p'], gold['lam'][0])
+    assert np.array_equal(one, H[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,n_k,B', [('ampyx_ap2', 4, 70), ('dual_kites', 3, 37), ('mpc_3dof', 10, 97)])
+def test_gpu_against_host_restatement_on_a_seeded_ragged_batch(name, n_k, B):
+    from awebox_b200 import synthetic
+    ocp = get_ocp(name, n_k)
+    ev = evaluator(name, n_k)
+    Hh = hessian(name, n_k)
+    W = synthetic.batch(ocp, B, seed=11)
+    # parameter modes: one shared vector (AP2), per-instance theta0 (dual kites: a wind-speed sweep), per-instance full
+    # vectors (MPC scenarios)
+    if name == 'dual_kites':
+        P = synthetic.power_curve_params(ocp, B)
+    elif name == 'mpc_3dof':
+        P = synthetic.scenario_params(ocp, W, seed=12)
+    else:
+        P = ocp.default_p()
+    rng = np.random.default_rng(3)
+    Lam = rng.uniform(-1.0, 1.0, (B, ocp.n_g))
+    H = ev.eval_hessian(W, P, Lam)
+    for b in (0, 1, 31, 32, B - 1):
+        p = P if P.ndim == 1 else P[b]
+        ref = Hh.evaluate(W[b], p if len(p) == ocp.n_p else np.concatenate([np.zeros(ocp.p_theta0), p]), Lam[b])
+        assert np.all(np.abs(H[b] - ref) <= hess_tolerance(Hh, ref)), b
+    # deterministic: a second call gives the same bits
+    assert np.array_equal(H, ev.eval_hessian(W, P, Lam))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,n_k,B', [('ampyx_ap2', 40, 256), ('dual_kites', 20, 128), ('mpc_3dof', 10, 512)])
+def test_gpu_properties_at_full_size(name, n_k, B):
+    """linear in lam; zero multipliers give a zero Hessian; instances do not depend on their position in the batch"""
+    from awebox_b200 import synthetic
+    ocp = get_ocp(name, n_k)
+    ev = evaluator(name, n_k)
+    W, P = synthetic.batch(ocp, B, seed=12), ocp.default_p()
+    rng = np.random.default_rng(4)
+    L1, L2 = rng.uniform(-1.0, 1.0, (B, ocp.n_g)), rng.uniform(-1.0, 1.0, (B, ocp.n_g))
+    H1, H2 = ev.eval_hessian(W, P, L1), ev.eval_hessian(W, P, L2)
+    H12 = ev.eval_hessian(W, P, L1 + 2.0 * L2)
+    scale = np.maximum(1.0, np.abs(H1).max() + 2.0 * np.abs(H2).max())
+    assert np.abs(H12 - (H1 + 2.0 * H2)).max() <= 1e-12 * scale
+    assert not np.any(ev.eval_hessian(W[:3], P if P.ndim == 1 else P[:3], np.zeros((3, ocp.n_g))))
+    perm = rng.permutation(B)
+    Hp = ev.eval_hessian(W[perm], P if P.ndim == 1 else P[perm], L1[perm])
+    assert np.array_equal(Hp, H1[perm])
+
+
+@pytest.mark.gpu
+def test_casadi_hess_lag_symbols():
+    """awegpu_hess_lag called with CasADi's external-function conventions (arg / res pointer arrays, compact CCS)"""
+    import ctypes as C
+    name, n_k = 'ampyx_ap2', 4
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d_hess.npz' % (name, n_k)))
+    ev = evaluator(name, n_k)
+    lib = ev.lib
+    assert lib.awegpu_casadi_bind(ev.handle) == 0
+    lib.awegpu_hess_lag_n_in.restype = C.c_longlong
+    lib.awegpu_hess_lag_n_out.restype = C.c_longlong
+    assert lib.awegpu_hess_lag_n_in() == 4 and lib.awegpu_hess_lag_n_out() == 1
+    lib.awegpu_hess_lag_sparsity_out.restype = C.POINTER(C.c_longlong)
+    lib.awegpu_hess_lag_sparsity_out.argtypes = [C.c_longlong]
+    sp = lib.awegpu_hess_lag_sparsity_out(0)
+    n_v = ev.n_v
+    assert sp[0] == n_v and sp[1] == n_v
+    colind = np.array([sp[2 + i] for i in range(n_v + 1)], dtype=np.int64)
+    nnz = int(colind[-1])
+    row = np.array([sp[2 + n_v + 1 + i] for i in range(nnz)], dtype=np.int64)
+    assert np.array_equal(colind, gold['colind']) and np.array_equal(row, gold['row'])
+    lib.awegpu_hess_lag_checkout.restype = C.c_int
+    mem = lib.awegpu_hess_lag_checkout()
+    w, p, lam = (np.ascontiguousarray(a, dtype=np.float64) for a in (gold['w'][1], gold['p'], gold['lam'][1]))
+    lam_f = np.ones(1)
+    out = np.full(nnz, np.nan)
+    arg = (C.POINTER(C.c_double) * 4)(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in (w, p, lam_f, lam)])
+    res = (C.POINTER(C.c_double) * 1)(out.ctypes.data_as(C.POINTER(C.c_double)))
+    lib.awegpu_hess_lag.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    assert lib.awegpu_hess_lag(arg, res, None, None, mem) == 0
+    assert np.all(np.abs(out - gold['hv'][1]) <= hess_tolerance(hessian(name, n_k), gold['hv'][1]))
