@@ -37,8 +37,8 @@ def generate(spec_name, ocp=None):
     if ocp is None:
         ocp = OcpProblem(ModelSpec.load(spec_name))
     stats = NodeCode(ocp).write(gen_dir(spec_name))
-    from .ocp.hessian import LagrangianHessian
-    stats['hessian'] = LagrangianHessian(ocp).write(gen_dir(spec_name))
+    from .ocp.hessian import LagrangianHessian, has_objective
+    stats['hessian'] = LagrangianHessian(ocp, objective=has_objective(ocp)).write(gen_dir(spec_name))
     with open(os.path.join(gen_dir(spec_name), 'stats.json'), 'w') as f:
         json.dump(stats, f, indent=1, sort_keys=True)
     return ocp, stats

@@ -42,15 +42,21 @@
 #define TP_S ((N_TH + N_PHI) | 1)
 #define HESS_THREADS (32 * (N_D + 1))
 #define NODE_VALS (N_D * AWE_H_NEC + AWE_H_NES)
+#define HESS_SMEM_BYTES (8 * 32 * (SLAB_S + LAM_S + N_D * XS_S + TP_S))
+#ifndef AWE_HESS_MINB
+/* resident CTAs per SM the node kernel is compiled for: two if their staging fits the shared memory of an SM */
+#define AWE_HESS_MINB ((2 * HESS_SMEM_BYTES + 2048 <= 227 * 1024) ? 2 : 1)
+#endif
 
 __constant__ double c_hess_coll[(N_D + 1) * (N_D + 1)];       // C[r, j] (awebox_b200/ocp/collocation.py)
+__constant__ double c_hess_quad[N_D];                         // quadrature weights of the collocation nodes
 
 static size_t hess_node_smem()
 {
     return sizeof(double) * 32 * ((size_t)SLAB_S + LAM_S + (size_t)N_D * XS_S + TP_S);
 }
 
-__global__ void __launch_bounds__(HESS_THREADS, 1) awegpu_hess_node_kernel(const HessArgs a, const int tile0)
+__global__ void __launch_bounds__(HESS_THREADS, AWE_HESS_MINB) awegpu_hess_node_kernel(const HessArgs a, const int tile0)
 {
     extern __shared__ double sm[];
     double *slab = sm;                                  // [32][SLAB_S]
@@ -79,6 +85,25 @@ __global__ void __launch_bounds__(HESS_THREADS, 1) awegpu_hess_node_kernel(const
     const double *tp = thph + lane * TP_S;
     const double hnk = (double)a.n_k;
     double *out = a.scr + ((size_t)ltile * a.n_hv + (size_t)k * NODE_VALS) * 32 + lane;
+#if AWE_H_OBJ
+    // objective part (awebox_b200/ocp/hessian.py: _objective_term): references, weights and cost factors from the full
+    // parameter vector, or zeros (and lam_f = 0) when the caller asked for the constraint part only
+    const bool use_obj = a.Sigma != nullptr;
+    const double *pobj = use_obj ? a.P + (size_t)b * a.ld_p : a.zeros;
+    const double sigf = use_obj ? __ldg(a.Sigma + b) : 0.0;
+    double tper = 0.0, tref = 0.0;
+    for (int i = 0; i < a.n_t; ++i) {
+        tper = fma(a.t_coef[i], __ldg(a.W + (size_t)b * a.n_v + a.t_idx[i]), tper);
+        tref = fma(a.t_coef[i], __ldg(pobj + a.t_idx[i]), tref);
+    }
+    const double *pref = pobj + a.v_x0 + (size_t)k * SLAB_W;
+    const int *thi = a.theta_idx + k * N_TH;
+#define SIGF sigf
+#define TPER tper
+#define TREF tref
+#define PW(i) __ldg(pobj + a.n_v + (i))
+#define CF(i) __ldg(pobj + a.n_v + a.n_var + (i))
+#endif
 #define HNK hnk
 #define PIN(i) ((i) < AWE_N_THETA0 ? __ldg(pth0 + (i)) : tp[N_TH + (i) - AWE_N_THETA0])
 #define HOUT(n, v) out[(n) * 32] = (v)
@@ -99,6 +124,14 @@ __global__ void __launch_bounds__(HESS_THREADS, 1) awegpu_hess_node_kernel(const
                 (i) < 2 * N_X + N_U + N_Z ? zo[(i) - 2 * N_X - N_U] : tp[(i) - 2 * N_X - N_U - N_Z])
 #define XSIN(i) xs[(i)]
 #define LIN(i) lm[(i)]
+#if AWE_H_OBJ
+        const double qj = c_hess_quad[j], w0 = (k == 0 && j == 0) ? 1.0 : 0.0;
+        const double *rx = pref + OFF_CX(j), *rz = pref + OFF_CZ(j);
+#define QJ qj
+#define W0 w0
+#define REF(i) ((i) < N_X ? __ldg(rx + (i)) : (i) < 2 * N_X ? 0.0 : (i) < 2 * N_X + N_U ? __ldg(pref + OFF_U + (i) - 2 * N_X) : \
+                (i) < 2 * N_X + N_U + N_Z ? __ldg(rz + (i) - 2 * N_X - N_U) : __ldg(pobj + thi[(i) - 2 * N_X - N_U - N_Z]))
+#endif
         {
 #include "node_hess_coll.inc"
         }
@@ -132,11 +165,31 @@ __global__ void __launch_bounds__(32 * ASM_WARPS) awegpu_hess_asm_kernel(const H
     if (s0 >= a.nnz) return;
     const double *hv = a.scr + (size_t)ltile * a.n_hv * 32 + lane;
     const int n_s = (int)min((long long)32, a.nnz - s0);
-    for (int s = 0; s < n_s; ++s) {
-        const int t0 = __ldg(a.asm_ptr + s0 + s), t1 = __ldg(a.asm_ptr + s0 + s + 1);
-        double acc = 0.0;
-        for (int t = t0; t < t1; ++t) acc = fma(__ldg(a.asm_coef + t), __ldg(hv + (size_t)__ldg(a.asm_idx + t) * 32), acc);
-        stg[warp][s][lane] = acc;
+    // the terms of the warp's 32 slots are one contiguous range of the tables: walk it four terms at a time (independent
+    // loads in flight) and add every product to its slot's row (lane = instance; rows are private to the warp)
+    const int p_lo = __ldg(a.asm_ptr + s0 + min(lane, n_s)), p_hi = __ldg(a.asm_ptr + s0 + min(lane + 1, n_s));
+    const int T0 = __shfl_sync(0xffffffffu, p_lo, 0), T1 = __shfl_sync(0xffffffffu, p_hi, 31);
+#pragma unroll
+    for (int s = 0; s < 32; ++s) stg[warp][s][lane] = 0.0;
+    int s = 0, s_end = __shfl_sync(0xffffffffu, p_hi, 0);       // terms below s_end belong to slot s
+    for (int t = T0; t < T1; t += 4) {
+        double c[4], v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int tt = min(t + u, T1 - 1);
+            c[u] = (t + u < T1) ? __ldg(a.asm_coef + tt) : 0.0;
+            v[u] = __ldg(hv + (size_t)__ldg(a.asm_idx + tt) * 32);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (t + u < T1) {
+                while (t + u >= s_end) {
+                    ++s;
+                    s_end = __shfl_sync(0xffffffffu, p_hi, s);
+                }
+                stg[warp][s][lane] = fma(c[u], v[u], stg[warp][s][lane]);
+            }
+        }
     }
     __syncwarp();
     const int n_i = min(32, a.B - tile * 32);
@@ -146,10 +199,15 @@ __global__ void __launch_bounds__(32 * ASM_WARPS) awegpu_hess_asm_kernel(const H
 
 size_t awe_hess_scratch_per_tile(int n_hv) { return sizeof(double) * 32 * (size_t)n_hv; }
 
-int awe_hess_set_coeff(const double *C)
+int awe_hess_set_coeff(const double *C, const double *quad)
 {
-    return (int)cudaMemcpyToSymbol(c_hess_coll, C, sizeof(double) * (N_D + 1) * (N_D + 1));
+    cudaError_t e = cudaMemcpyToSymbol(c_hess_coll, C, sizeof(double) * (N_D + 1) * (N_D + 1));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_hess_quad, quad, sizeof(double) * N_D);
+    return (int)e;
 }
+
+int awe_hess_has_objective(void) { return AWE_H_OBJ; }
+void awe_hess_node_dims(int *n_ec, int *n_es) { *n_ec = AWE_H_NEC, *n_es = AWE_H_NES; }
 
 int awe_hess_launch(cudaStream_t st, const HessArgs &a, int tile0, int n_tiles)
 {

@@ -15,6 +15,11 @@ struct HessArgs {
     const int *theta_idx;          // [n_k][n_theta] V index of every theta entry of interval k
     const int *asm_ptr, *asm_idx;  // [nnz + 1], [n_asm]: node values of every CCS slot (index into the per-instance vector)
     const double *asm_coef;        // [n_asm]
+    // objective part (libraries generated with AWE_H_OBJ): multiplier lam_f per instance (NULL: constraint part only),
+    // P must then hold full parameter vectors (p.ref | p.weights | cost | theta0); zeros: n_p zeros read instead otherwise
+    const double *Sigma, *zeros;
+    int n_var, n_t, t_idx[2];      // time period T = sum_i t_coef[i] * V[t_idx[i]]
+    double t_coef[2];
     double *scr;                   // [tiles of this launch][n_hv][32] node Hessian values, lane-contiguous
     double *H;                     // [B, nnz]
 };
@@ -24,5 +29,8 @@ int awe_hess_launch(cudaStream_t st, const HessArgs &a, int tile0, int n_tiles);
 // bytes of a.scr per tile
 size_t awe_hess_scratch_per_tile(int n_hv);
 // collocation coefficients C[r, j], (d+1) x (d+1) row-major, into constant memory (once per process and device)
-int awe_hess_set_coeff(const double *C);
+int awe_hess_set_coeff(const double *C, const double *quad);
+// 1 if the node programs of this library carry the objective part; entries per collocation / shooting node Hessian
+int awe_hess_has_objective(void);
+void awe_hess_node_dims(int *n_ec, int *n_es);
 #endif

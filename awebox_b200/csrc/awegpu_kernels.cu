@@ -1451,7 +1451,7 @@ struct awegpu_handle {
     MpcObjParams mp{};
     int mpc_n_p = 0;
     // second-order hook (awegpu_hess.cu): tables uploaded by awegpu_hess_setup
-    bool hess_ready = false;
+    bool hess_ready = false, hess_obj = false;
     HessArgs hs{};
     std::vector<long long> hess_colind, hess_row, sp_hess, sp_lamf;
     double *hess_scr = nullptr, *dHess = nullptr, *dLamH = nullptr;
@@ -2453,9 +2453,23 @@ extern "C" int awegpu_eval_objective_host(awegpu_handle_t *h, int32_t B, const d
 // --------------------------------------------------------------------------- second-order hook
 extern "C" int awegpu_hess_setup(awegpu_handle_t *h, int64_t nnz, int32_t n_hv, int64_t n_asm, const int64_t *colind,
                                  const int64_t *row, const int64_t *asm_ptr, const int64_t *asm_idx, const double *asm_coef,
-                                 int32_t v_x0, int32_t row0, int32_t row_stride, const double *coeff)
+                                 int32_t v_x0, int32_t row0, int32_t row_stride, const double *coeff, const double *quad,
+                                 int32_t n_ec, int32_t n_es, int32_t with_objective, int32_t n_t, const int32_t *t_idx,
+                                 const double *t_coef)
 {
-    if (!h || !colind || !row || !asm_ptr || !asm_idx || !asm_coef || !coeff || nnz <= 0 || n_asm <= 0) return 1;
+    if (!h || !colind || !row || !asm_ptr || !asm_idx || !asm_coef || !coeff || !quad || nnz <= 0 || n_asm <= 0) return 1;
+    {
+        int ec = 0, es = 0;
+        awe_hess_node_dims(&ec, &es);
+        if (ec != n_ec || es != n_es || (with_objective != 0) != (awe_hess_has_objective() != 0)) {
+            set_err(h, "awegpu_hess_setup: the tables do not belong to the node Hessian programs of this library");
+            return 1;
+        }
+        if (n_t < 0 || n_t > 2 || (with_objective && (n_t == 0 || !t_idx || !t_coef))) {
+            set_err(h, "awegpu_hess_setup: time period terms");
+            return 1;
+        }
+    }
     if (n_asm >= (1LL << 31) || nnz >= (1LL << 31)) {
         set_err(h, "awegpu_hess_setup: table too large for 32-bit indices");
         return 1;
@@ -2473,7 +2487,15 @@ extern "C" int awegpu_hess_setup(awegpu_handle_t *h, int64_t nnz, int32_t n_hv, 
     a.n_v = d.n_v, a.n_g = d.n_g, a.n_k = d.n_k, a.n_hv = n_hv, a.nnz = nnz;
     a.v_x0 = v_x0, a.v_phi = d.v_phi, a.row0 = row0, a.row_stride = row_stride;
     a.theta_idx = d.theta_idx;
-    if (awe_hess_set_coeff(coeff)) {
+    a.n_var = h->host.n_var, a.n_t = with_objective ? n_t : 0;
+    for (int i = 0; i < a.n_t; ++i) a.t_idx[i] = t_idx[i], a.t_coef[i] = t_coef[i];
+    {
+        std::vector<double> z((size_t)d.n_p + 1, 0.0);
+        rc = to_device(h, z.data(), z.size(), &a.zeros);
+        if (rc) return rc;
+    }
+    h->hess_obj = with_objective != 0;
+    if (awe_hess_set_coeff(coeff, quad)) {
         set_err(h, "awegpu_hess_setup: cudaMemcpyToSymbol failed");
         return 2;
     }
@@ -2489,6 +2511,8 @@ extern "C" int awegpu_hess_setup(awegpu_handle_t *h, int64_t nnz, int32_t n_hv, 
     return 0;
 }
 
+extern "C" int awegpu_hess_has_objective(void) { return awe_hess_has_objective(); }
+
 extern "C" int64_t awegpu_hess_nnz(awegpu_handle_t *h) { return (h && h->hess_ready) ? h->hs.nnz : -1; }
 
 extern "C" int awegpu_hess_sparsity(awegpu_handle_t *h, int64_t *colind, int64_t *row)
@@ -2500,7 +2524,7 @@ extern "C" int awegpu_hess_sparsity(awegpu_handle_t *h, int64_t *colind, int64_t
 }
 
 extern "C" int awegpu_eval_hessian(awegpu_handle_t *h, int32_t B, const double *W, const double *P, const double *Lam,
-                                   int32_t flags, double *H, void *stream)
+                                   const double *Sigma, int32_t flags, double *H, void *stream)
 {
     if (!h) return 1;
     if (B <= 0) return 0;
@@ -2510,6 +2534,14 @@ extern "C" int awegpu_eval_hessian(awegpu_handle_t *h, int32_t B, const double *
     }
     if (!W || !P || !Lam || !H) {
         set_err(h, "awegpu_eval_hessian: W, P, Lam and H are required");
+        return 1;
+    }
+    if (Sigma && !h->hess_obj) {
+        set_err(h, "awegpu_eval_hessian: this problem has no objective part on this path (pass Sigma = NULL)");
+        return 1;
+    }
+    if (Sigma && (flags & AWEGPU_P_THETA0)) {
+        set_err(h, "awegpu_eval_hessian: the objective part needs full parameter vectors (not AWEGPU_P_THETA0)");
         return 1;
     }
     CK(cudaSetDevice(h->device));
@@ -2524,7 +2556,7 @@ extern "C" int awegpu_eval_hessian(awegpu_handle_t *h, int32_t B, const double *
         if (rc) return rc;
     }
     HessArgs a = h->hs;
-    a.B = B, a.W = W, a.P = P, a.Lam = Lam, a.H = H, a.scr = h->hess_scr;
+    a.B = B, a.W = W, a.P = P, a.Lam = Lam, a.Sigma = Sigma, a.H = H, a.scr = h->hess_scr;
     a.ld_p = (flags & AWEGPU_P_SHARED) ? 0 : ((flags & AWEGPU_P_THETA0) ? d.n_theta0 : d.n_p);
     a.p_off = (flags & AWEGPU_P_THETA0) ? 0 : d.p_theta0;
     CK(cudaEventRecord(h->ev_h0, st));
@@ -2552,7 +2584,7 @@ extern "C" float awegpu_last_hessian_ms(awegpu_handle_t *h)
 }
 
 extern "C" int awegpu_eval_hessian_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P, const double *Lam,
-                                        int32_t flags, double *H)
+                                        const double *Sigma, int32_t flags, double *H)
 {
     if (!h) return 1;
     if (B <= 0) return 0;
@@ -2566,13 +2598,14 @@ extern "C" int awegpu_eval_hessian_host(awegpu_handle_t *h, int32_t B, const dou
     const size_t nW = (size_t)B * d.n_v, nP = (flags & AWEGPU_P_SHARED) ? ldp : (size_t)B * ldp;
     const size_t nL = (size_t)B * d.n_g, nH = (size_t)B * (size_t)h->hs.nnz;
     int rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, nW, false) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, nP, false) |
-             grow_dev(h, &h->dLamH, &h->capLamH, nL) | grow_dev(h, &h->dHess, &h->capHess, nH);
+             grow_dev(h, &h->dLamH, &h->capLamH, nL + (size_t)B) | grow_dev(h, &h->dHess, &h->capHess, nH);
     if (rc) return rc;
     cudaStream_t st = h->stream;
     CK(cudaMemcpyAsync(h->dW, W, nW * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->dLamH, Lam, nL * sizeof(double), cudaMemcpyHostToDevice, st));
-    rc = awegpu_eval_hessian(h, B, h->dW, h->dP, h->dLamH, flags, h->dHess, st);
+    if (Sigma) CK(cudaMemcpyAsync(h->dLamH + nL, Sigma, (size_t)B * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = awegpu_eval_hessian(h, B, h->dW, h->dP, h->dLamH, Sigma ? h->dLamH + nL : nullptr, flags, h->dHess, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(H, h->dHess, nH * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -2698,8 +2731,8 @@ extern "C" int jac_awegpu_g_work(long long *sz_arg, long long *sz_res, long long
 }
 
 // hess_lag for cas.nlpsol(..., {'hess_lag': external('awegpu_hess_lag', lib)}): inputs (x, p, lam_f, lam_g), output the
-// upper triangle of the Hessian of the constraint part lam_g' g (awebox/opts/default.py:323 hessian_approximation = False).
-// lam_f is accepted and not used: the objective part of the Hessian is not on this path.
+// upper triangle of the Hessian of lam_f f + lam_g' g (awebox/opts/default.py:323 hessian_approximation = False).  Problems
+// without an objective on this path (the MPC trial, whose cost Pmpc builds itself): the constraint part, lam_f is not used.
 CASADI_MEM_FUNCS(awegpu_hess_lag)
 extern "C" int awegpu_hess_lag(const double **arg, double **res, long long *, double *, int mem)
 {
@@ -2712,11 +2745,10 @@ extern "C" int awegpu_hess_lag(const double **arg, double **res, long long *, do
     double *out = res ? res[0] : nullptr;
     if (!out) return 0;
     std::lock_guard<std::mutex> lock(h->casadi_mu);
-    if (!arg[3]) {          // NULL = all-zero multipliers: the constraint part vanishes
-        for (long long i = 0; i < h->hs.nnz; ++i) out[i] = 0.0;
-        return 0;
-    }
-    return awegpu_eval_hessian_host(h, 1, arg[0], arg[1], arg[3], 0, out);
+    h->scratch_g.assign(h->dp.n_g, 0.0);          // NULL = all-zero multipliers
+    const double zero = 0.0;
+    const double *lam_f = h->hess_obj ? (arg[2] ? arg[2] : &zero) : nullptr;
+    return awegpu_eval_hessian_host(h, 1, arg[0], arg[1], arg[3] ? arg[3] : h->scratch_g.data(), lam_f, 0, out);
 }
 extern "C" long long awegpu_hess_lag_n_in(void) { return 4; }
 extern "C" long long awegpu_hess_lag_n_out(void) { return 1; }

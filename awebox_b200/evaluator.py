@@ -60,12 +60,13 @@ def load_library(spec_name):
     lib.awegpu_launch_count.argtypes = [C.c_void_p]
     lib.awegpu_synchronize.argtypes = [C.c_void_p]
     lib.awegpu_casadi_bind.argtypes = [C.c_void_p]
-    lib.awegpu_hess_setup.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64] + [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_void_p]
+    lib.awegpu_hess_setup.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int64] + [C.c_void_p] * 5 + [C.c_int32] * 3 + \
+        [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p, C.c_void_p]
     lib.awegpu_hess_nnz.argtypes = [C.c_void_p]
     lib.awegpu_hess_nnz.restype = C.c_int64
     lib.awegpu_hess_sparsity.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.awegpu_eval_hessian.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
-    lib.awegpu_eval_hessian_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.awegpu_eval_hessian.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]
+    lib.awegpu_eval_hessian_host.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]
     lib.awegpu_last_hessian_ms.argtypes = [C.c_void_p]
     lib.awegpu_last_hessian_ms.restype = C.c_float
     lib.awegpu_model_dims.argtypes = [C.POINTER(C.c_int32)] * 4 + [C.POINTER(C.c_int64)] * 2
@@ -269,23 +270,31 @@ class Evaluator(object):
     def grad_f_fun(self, V, P):
         return self.eval_objective(np.asarray(V, dtype=float).reshape(1, -1), np.asarray(P, dtype=float).reshape(-1))[1][0]
 
-    # ---- second-order hook: triu of d^2/dw^2 (lam' g)
+    # ---- second-order hook: triu of d^2/dw^2 (lam_f f + lam_g' g)
     def hessian_setup(self):
         """derive the node Hessians' tables (awebox_b200/ocp/hessian.py) and upload them; idempotent"""
         if getattr(self, 'hess', None) is not None:
             return self.hess
-        from .ocp.hessian import LagrangianHessian
+        from .ocp.hessian import LagrangianHessian, has_objective
         ocp = self.ocp
-        H = LagrangianHessian(ocp)
+        with_obj = has_objective(ocp)
+        if bool(self.lib.awegpu_hess_has_objective()) != with_obj:
+            raise AwegpuError('the library was generated %s the objective part of the Hessian' % ('without' if with_obj else 'with'))
+        H = LagrangianHessian(ocp, objective=with_obj)
+        t_terms = H.T_terms if with_obj else []
         keep = [np.ascontiguousarray(a) for a in (H.colind.astype(np.int64), H.row.astype(np.int64), H.asm_ptr.astype(np.int64),
                                                   H.asm_idx.astype(np.int64), H.asm_coef.astype(np.float64),
-                                                  np.asarray(ocp.coll.coeff_collocation, dtype=np.float64))]
+                                                  np.asarray(ocp.coll.coeff_collocation, dtype=np.float64),
+                                                  np.asarray(ocp.coll.quad_weights, dtype=np.float64).ravel(),
+                                                  np.array([i for i, _ in t_terms] + [0, 0], dtype=np.int32),
+                                                  np.array([c for _, c in t_terms] + [0.0, 0.0], dtype=np.float64))]
         row_stride = ocp.row_shoot[1] - ocp.row_shoot[0] if ocp.n_k > 1 else ocp.n_shoot_eq + ocp.n_ineq + ocp.d * ocp.n_eq + ocp.n_x
         rc = self.lib.awegpu_hess_setup(self.handle, H.nnz, H.n_hv, len(H.asm_idx), keep[0].ctypes.data, keep[1].ctypes.data,
                                         keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data, int(ocp.v_x[0]),
-                                        int(ocp.row_shoot[0]), int(row_stride), keep[5].ctypes.data)
+                                        int(ocp.row_shoot[0]), int(row_stride), keep[5].ctypes.data, keep[6].ctypes.data,
+                                        H.n_ec, H.n_es, int(with_obj), len(t_terms), keep[7].ctypes.data, keep[8].ctypes.data)
         self._check(rc, 'awegpu_hess_setup')
-        self.hess, self.nnz_hess = H, H.nnz
+        self.hess, self.nnz_hess, self.hess_objective = H, H.nnz, with_obj
         return H
 
     def hess_sparsity(self):
@@ -296,8 +305,9 @@ class Evaluator(object):
         self._check(self.lib.awegpu_hess_sparsity(self.handle, colind.ctypes.data, row.ctypes.data), 'awegpu_hess_sparsity')
         return colind, row
 
-    def eval_hessian(self, W, P, Lam):
-        """non-zeros of triu(d^2/dw^2 (lam' g)) for a batch: W [B, n_v], P as ``eval``, Lam [B, n_g] -> [B, nnz_hess]"""
+    def eval_hessian(self, W, P, Lam, sigma=None):
+        """non-zeros of triu(d^2/dw^2 (sigma f + lam' g)) for a batch: W [B, n_v], P as ``eval``, Lam [B, n_g], sigma [B] (or a
+        scalar; None: the constraint part alone) -> [B, nnz_hess]"""
         self.hessian_setup()
         W = np.ascontiguousarray(W, dtype=np.float64)
         if W.ndim == 1:
@@ -306,15 +316,18 @@ class Evaluator(object):
         Lam = np.ascontiguousarray(Lam, dtype=np.float64).reshape(B, self.n_g)
         P = np.ascontiguousarray(P, dtype=np.float64)
         flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        if sigma is not None:
+            sigma = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, dtype=np.float64), (B,)))
         H = np.empty((B, self.nnz_hess))
-        rc = self.lib.awegpu_eval_hessian_host(self.handle, B, W.ctypes.data, P.ctypes.data, Lam.ctypes.data, flags, H.ctypes.data)
+        rc = self.lib.awegpu_eval_hessian_host(self.handle, B, W.ctypes.data, P.ctypes.data, Lam.ctypes.data,
+                                               sigma.ctypes.data if sigma is not None else None, flags, H.ctypes.data)
         self._check(rc, 'awegpu_eval_hessian_host')
         return H
 
-    def eval_hessian_device(self, W, P, Lam, H, stream=None):
+    def eval_hessian_device(self, W, P, Lam, H, sigma=None, stream=None):
         import torch
         self.hessian_setup()
-        for t in (W, P, Lam, H):
+        for t in (W, P, Lam, H) + ((sigma,) if sigma is not None else ()):
             if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
                 raise ValueError('eval_hessian_device needs contiguous float64 CUDA tensors')
         B = W.shape[0]
@@ -323,17 +336,19 @@ class Evaluator(object):
             stream = torch.cuda.current_stream(W.device).cuda_stream
         if not stream:
             stream = 1
-        rc = self.lib.awegpu_eval_hessian(self.handle, B, W.data_ptr(), P.data_ptr(), Lam.data_ptr(), flags, H.data_ptr(),
-                                          C.c_void_p(stream))
+        rc = self.lib.awegpu_eval_hessian(self.handle, B, W.data_ptr(), P.data_ptr(), Lam.data_ptr(),
+                                          sigma.data_ptr() if sigma is not None else None, flags, H.data_ptr(), C.c_void_p(stream))
         self._check(rc, 'awegpu_eval_hessian')
 
     def last_hessian_ms(self):
         return float(self.lib.awegpu_last_hessian_ms(self.handle))
 
-    def hess_lag_fun(self, V, P, lam_g):
-        """one instance, the way nlpsol calls hess_lag: values of triu(H) in CCS order"""
+    def hess_lag_fun(self, V, P, lam_f, lam_g):
+        """one instance, the way nlpsol calls hess_lag(x, p, lam_f, lam_g): values of triu(H) in CCS order"""
+        self.hessian_setup()
         return self.eval_hessian(np.asarray(V, dtype=np.float64)[None, :], np.asarray(P, dtype=np.float64),
-                                 np.asarray(lam_g, dtype=np.float64)[None, :])[0]
+                                 np.asarray(lam_g, dtype=np.float64)[None, :],
+                                 sigma=float(lam_f) if self.hess_objective else None)[0]
 
     def last_eval_ms(self):
         return float(self.lib.awegpu_last_eval_ms(self.handle))

@@ -407,6 +407,46 @@ def main():
                     'cpu_port': 'numpy restatement, 1 thread, %d instances' % n_cpu,
                     'finite': bool(torch.isfinite(dF).all().item())}
 
+    # ---- second-order hook: triu of the Hessian of lam_f f + lam_g' g, device entry, CUDA events
+    hess_line = None
+    if p_mode == 'shared':
+        Hs = ev.hessian_setup()
+        with_obj = ev.hess_objective
+        p_h = ocp.default_p()
+        if with_obj:
+            p_h[:ocp.n_v] = W[0]
+            p_h[ocp.n_v:ocp.p_theta0] = 1.0
+        dPh = torch.from_numpy(p_h).cuda()
+        rng_h = np.random.default_rng(11 + rank)
+        dLam = torch.from_numpy(rng_h.uniform(-1.0, 1.0, (B, ocp.n_g))).cuda()
+        dSig = torch.ones((B,), dtype=torch.float64, device='cuda') if with_obj else None
+        dH = torch.empty((B, Hs.nnz), dtype=torch.float64, device='cuda')
+        for _ in range(2):
+            ev.eval_hessian_device(dW, dPh, dLam, dH, sigma=dSig)
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        for _ in range(5):
+            ev.eval_hessian_device(dW, dPh, dLam, dH, sigma=dSig)
+        h1.record(stream)
+        torch.cuda.synchronize()
+        h_ms = h0.elapsed_time(h1) / 5
+        h_bytes = B * 8 * (ocp.n_v + ocp.n_g + Hs.nnz)               # read w and lam, write the non-zeros of triu(H)
+        # the numpy restatement (awebox_b200/ocp/hessian.py, the checker of tests/test_hessian.py) on the host, one thread
+        t0c, n_cpu = time.perf_counter(), 0
+        while n_cpu < 2 or (time.perf_counter() - t0c < 1.0 and n_cpu < 32):
+            Hs.evaluate(W[n_cpu % B], p_h, dLam[n_cpu % B].cpu().numpy(), 1.0 if with_obj else 0.0)
+            n_cpu += 1
+        hess_line = {'ms_per_step': h_ms, 'hess_lag_evals_per_s': B / (h_ms * 1e-3),
+                     'node_hessians_per_s': B * ocp.n_k * (ocp.d + 1) / (h_ms * 1e-3), 'nnz_triu': int(Hs.nnz),
+                     'with_objective_part': bool(with_obj),
+                     'algorithmic_bytes': int(h_bytes), 'GBps': h_bytes / (h_ms * 1e-3) / 1e9,
+                     'api': 'awegpu_eval_hessian (device pointers): node Hessian kernel + assembly kernel per chunk of 2048 instances',
+                     'cpu_port_evals_per_s': n_cpu / (time.perf_counter() - t0c),
+                     'cpu_port': 'numpy restatement, 1 thread, %d instances' % n_cpu,
+                     'finite': bool(torch.isfinite(dH).all().item())}
+        del dH, dLam
+
     # ---- NCCL gather of the per-rank results (north_star: "NCCL over NVLink used only to gather per-shard results")
     gather = None
     if args.gather != 'none' and world > 1:
@@ -573,6 +613,9 @@ def main():
         if obj_line is not None:
             obj_line['frac_of_hbm_peak'] = obj_line['GBps'] / peak
             line['objective'] = obj_line
+        if hess_line is not None:
+            hess_line['frac_of_hbm_peak'] = hess_line['GBps'] / peak
+            line['hessian'] = hess_line
         if gather is not None:
             line['gather'] = gather
         print(json.dumps(line), file=json_out, flush=True)

@@ -183,24 +183,32 @@ int awegpu_eval_objective(awegpu_handle_t *h, int32_t B, const double *W, const 
 int awegpu_eval_objective_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags,
                                double *F, double *GradF, double *comp);
 
-/* Second-order hook: upper triangle, CCS, of the Hessian of the constraint part of the Lagrangian,
- * d^2/dw^2 (lam' g(w, p)), B instances per call.  Replaces the nlp_hess_l function CasADi derives inside cas.nlpsol when the
+/* Second-order hook: upper triangle, CCS, of the Hessian of the Lagrangian,
+ * d^2/dw^2 (sigma f(w, p) + lam' g(w, p)), B instances per call.  Replaces the nlp_hess_l function CasADi derives inside cas.nlpsol when the
  * reference solves with the exact Hessian (awebox/opts/default.py:323 hessian_approximation = False; the Lagrangian:
  * awebox/tools/debug_operations.py:567-596; g: awebox/ocp/constraints.py:210-373).
  * awegpu_hess_setup uploads the tables of awebox_b200/ocp/hessian.py once per handle: CCS pattern of triu(H) (colind [n_v+1],
  * row [nnz]), the assembly matrix (asm_ptr [nnz+1], asm_idx / asm_coef [n_asm]: node Hessian values and coefficients of
- * every slot), V offset of x_0, first g row and rows per interval, collocation coefficients C[r, j] ((d+1) x (d+1), row-major).
- * W [B, n_v]; P as awegpu_eval_batch (flags AWEGPU_P_*); Lam [B, n_g] multipliers of g; H [B, nnz] instance-major.
+ * every slot), V offset of x_0, first g row and rows per interval, collocation coefficients C[r, j] ((d+1) x (d+1), row-major)
+ * and quadrature weights [d], entries per collocation / shooting node Hessian and whether they carry the objective part
+ * (checked against the compiled programs), the time period T = sum_i t_coef[i] V[t_idx[i]] (n_t <= 2 terms).
+ * W [B, n_v]; P as awegpu_eval_batch (flags AWEGPU_P_*); Lam [B, n_g] multipliers of g; Sigma [B] multiplier of f per instance
+ * (nlpsol's lam_f), or NULL for the constraint part alone -- with Sigma, P must hold full parameter vectors (the objective
+ * reads p.ref, p.weights and the cost factors; awebox/ocp/objective.py:422-455) and the problem must have an objective on
+ * this path (trajectory type power_cycle); H [B, nnz] instance-major.
  * Device pointers (asynchronous, stream as awegpu_eval_batch) / host pointers (synchronous). */
 int awegpu_hess_setup(awegpu_handle_t *h, int64_t nnz, int32_t n_hv, int64_t n_asm, const int64_t *colind,
                       const int64_t *row, const int64_t *asm_ptr, const int64_t *asm_idx, const double *asm_coef,
-                      int32_t v_x0, int32_t row0, int32_t row_stride, const double *coeff);
+                      int32_t v_x0, int32_t row0, int32_t row_stride, const double *coeff, const double *quad,
+                      int32_t n_ec, int32_t n_es, int32_t with_objective, int32_t n_t, const int32_t *t_idx,
+                      const double *t_coef);
+int awegpu_hess_has_objective(void);               /* 1: the node programs of this library carry the objective part */
 int64_t awegpu_hess_nnz(awegpu_handle_t *h);       /* -1 before awegpu_hess_setup */
 int awegpu_hess_sparsity(awegpu_handle_t *h, int64_t *colind /*[n_v+1]*/, int64_t *row /*[nnz]*/);
 int awegpu_eval_hessian(awegpu_handle_t *h, int32_t B, const double *W, const double *P, const double *Lam,
-                        int32_t flags, double *H, void *stream);
+                        const double *Sigma, int32_t flags, double *H, void *stream);
 int awegpu_eval_hessian_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P, const double *Lam,
-                             int32_t flags, double *H);
+                             const double *Sigma, int32_t flags, double *H);
 /* device time of the most recent awegpu_eval_hessian (ms, CUDA events on the launching stream); <0 if none */
 float awegpu_last_hessian_ms(awegpu_handle_t *h);
 
@@ -260,8 +268,8 @@ const long long *jac_awegpu_g_sparsity_out(long long i);
 int jac_awegpu_g_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w);
 
 /* hess_lag for cas.nlpsol('solver', 'ipopt', nlp, {'hess_lag': casadi.external('awegpu_hess_lag', lib), ...}): inputs
- * (x, p, lam_f, lam_g), output triu of the Hessian of lam_g' g with the pattern of awegpu_hess_sparsity (available after
- * awegpu_hess_setup).  lam_f is accepted and not used: the objective part is not on this path. */
+ * (x, p, lam_f, lam_g), output triu of the Hessian of lam_f f + lam_g' g with the pattern of awegpu_hess_sparsity (available
+ * after awegpu_hess_setup).  Problems without an objective on this path (MPC trial): constraint part, lam_f not used. */
 int  awegpu_hess_lag_checkout(void);
 void awegpu_hess_lag_release(int mem);
 void awegpu_hess_lag_incref(void);

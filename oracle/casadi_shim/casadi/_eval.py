@@ -242,7 +242,7 @@ class LagrangianHessian(object):
     ``phi``) get a direction each, the rest a greedy distance-2 colouring of the pattern without those rows and
     columns; entries in the dense rows are read from the symmetric position."""
 
-    def __init__(self, g_inputs, g_outputs, n_x):
+    def __init__(self, g_inputs, g_outputs, n_x, f_output=None):
         self.n_x = n_x
         self.n_in = len(g_inputs)
         self.n_g = len(g_outputs)
@@ -250,8 +250,13 @@ class LagrangianHessian(object):
         L = _sx.ZERO
         for l, g in zip(self.lam, g_outputs):
             L = _sx.binary(_sx.ADD, L, _sx.binary(_sx.MUL, l, g))
+        self.lam_f = []
+        if f_output is not None:
+            # gamma = lam_f f + lam_g' g (nlpsol: "triu:hess:gamma:x:x" with gamma = {f, g})
+            self.lam_f = [_sx.sym('lam_f')]
+            L = _sx.binary(_sx.ADD, _sx.binary(_sx.MUL, self.lam_f[0], f_output), L)
         grad = _sx.reverse_gradient(L, list(g_inputs[:n_x]))
-        self.tape = Tape(list(g_inputs) + self.lam, grad)
+        self.tape = Tape(list(g_inputs) + self.lam + self.lam_f, grad)
         rows = self.tape.pattern()                  # row i: columns (inputs) d grad_i depends on
         cols = [[] for _ in range(n_x)]
         for i, cs in enumerate(rows):
@@ -339,9 +344,9 @@ class LagrangianHessian(object):
                         dw[k] = pa * da + pb * db
         return [w[s] for s in t.out_slots], [dw[s] for s in t.out_slots]
 
-    def values(self, x, p, lam):
+    def values(self, x, p, lam, lam_f=None):
         """non-zeros of triu(H) in CCS order at (x, p, lam)"""
-        xin = np.concatenate([x, p, lam])
+        xin = np.concatenate([x, p, lam] + ([[lam_f]] if self.lam_f else []))
         nc = self.n_colours
         seeds = {}
         for j in range(self.n_x):
@@ -362,9 +367,9 @@ class LagrangianHessian(object):
                     vals[q] = 0.0 if d is None else d[self.colour[j]]
         return vals
 
-    def times(self, x, p, lam, V):
+    def times(self, x, p, lam, V, lam_f=None):
         """H . V for a dense direction block V [n_x, nd] (full symmetric product; independent of the colouring)"""
-        xin = np.concatenate([x, p, lam])
+        xin = np.concatenate([x, p, lam] + ([[lam_f]] if self.lam_f else []))
         seeds = {j: V[j] for j in range(self.n_x)}
         _, dg = self.tangent(xin, seeds)
         out = np.zeros((self.n_x, V.shape[1]))

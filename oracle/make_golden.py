@@ -293,6 +293,53 @@ def run_hessian(config, n_k, n_pts):
           % (config, n_k, n_v, len(LH.row), LH.n_colours, len(LH.head), err, time.time() - t0, os.path.relpath(out, ROOT)))
 
 
+def run_hessian_full(config, n_k, n_pts):
+    """golden vectors of the complete ``hess_lag`` of nlpsol: triu of the Hessian of gamma = lam_f f + lam_g' g with
+    respect to V, from the reference's own ``nlp.f_fun`` and ``nlp.g_fun`` (awebox/opti/preparation.py:373-379), with P
+    filled as before a solve (references, weights, distinct cost factors; as run_objective)
+    -> tests/golden/<config>_nk<N>_hessf.npz"""
+    t0 = time.time()
+    T = ref_build.build(config, n_k=n_k)
+    import casadi as cas
+    from casadi import _eval
+    import awebox.opti.preparation as prep
+    nlp = T.nlp
+    n_v = len(T.w0)
+    rng = np.random.default_rng(20261022 + n_k)
+    V_ref = nlp.V(T.w0 * (1.0 + 1e-2 * rng.uniform(-1.0, 1.0, n_v)) + 1e-3 * rng.uniform(-1.0, 1.0, n_v))
+    pfix = prep.add_weights_and_refs_to_opti_parameters(T.p_fix_num, V_ref, nlp, T.model, T.V_init, T.options['solver'])
+    p = np.array(pfix.cat.full()).ravel()
+    labs = nlp.P.labels()
+    cost_idx = [i for i, l in enumerate(labs) if l.startswith('[cost,')]
+    for n, i in enumerate(cost_idx):
+        p[i] = 0.5 + 0.1 * n
+    W = np.array([T.w0 * (1.0 + 1e-2 * rng.uniform(-1.0, 1.0, n_v)) + 1e-3 * rng.uniform(-1.0, 1.0, n_v)
+                  for _ in range(n_pts)])
+    phi_idx = [i for i, l in enumerate(nlp.V.labels()) if l.startswith('[phi,')]
+    W[:, phi_idx] = rng.uniform(0.2, 0.8, (n_pts, len(phi_idx)))
+    g_fun, f_fun = nlp.g_fun, nlp.f_fun
+    ins = [v for s in g_fun._ins for v in s.e]
+    assert all(a is b for sa, sb in zip(g_fun._ins, f_fun._ins) for a, b in zip(sa.e, sb.e))
+    outs = [v for o in g_fun._outs for v in o.e]
+    LH = _eval.LagrangianHessian(ins, outs, n_v, f_output=f_fun._outs[0].e[0])
+    LAM = rng.uniform(-1.0, 1.0, (n_pts, LH.n_g))
+    SIG = rng.uniform(0.5, 1.5, n_pts)
+    HV = np.array([LH.values(w, p, lam, sg) for w, lam, sg in zip(W, LAM, SIG)])
+    D = rng.uniform(-1.0, 1.0, (n_v, 3))
+    HD = LH.times(W[-1], p, LAM[-1], D, SIG[-1])
+    import scipy.sparse as sps
+    U = sps.csc_matrix((HV[-1], LH.row, LH.colind), shape=(n_v, n_v))
+    full = U + sps.triu(U, 1).T
+    err = np.abs(full @ D - HD).max() / max(1.0, np.abs(HD).max())
+    assert err < 1e-12, err
+    out = os.path.join(GOLDEN, '%s_nk%d_hessf.npz' % (config, n_k))
+    np.savez_compressed(out, w=W, p=p, lam=LAM, lam_f=SIG, colind=LH.colind, row=LH.row, hv=HV)
+    print('%s n_k=%d hess_lag (objective + constraints): n_v=%d nnz(triu)=%d colours=%d dense columns=%d  check %.1e  (%.1f s) -> %s'
+          % (config, n_k, n_v, len(LH.row), LH.n_colours, len(LH.head), err, time.time() - t0, os.path.relpath(out, ROOT)))
+
+
+HESSF_JOBS = {'ampyx_ap2': [(4, 3), (40, 2)], 'dual_kites': [(3, 2), (20, 2)]}
+
 HESS_JOBS = {'ampyx_ap2': [(4, 3), (40, 2)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 3)]}
 
 OBJ_JOBS = {'ampyx_ap2': [(4, 3), (40, 3)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 3)]}
@@ -305,9 +352,12 @@ if __name__ == '__main__':
     if '--hessian' in sys.argv[1:]:
         small = '--small' in args
         args = [a for a in args if a != '--small']
-        for config in (args or list(HESS_JOBS)):
-            for n_k, n_pts in (HESS_JOBS[config][:1] if small else HESS_JOBS[config]):
-                run_hessian(config, n_k, n_pts)
+        full = '--full' in args
+        args = [a for a in args if a != '--full']
+        jobs = HESSF_JOBS if full else HESS_JOBS
+        for config in (args or list(jobs)):
+            for n_k, n_pts in (jobs[config][:1] if small else jobs[config]):
+                (run_hessian_full if full else run_hessian)(config, n_k, n_pts)
         sys.exit(0)
     if '--objective' in sys.argv[1:]:
         for config in (args or list(OBJ_JOBS)):

@@ -16,16 +16,20 @@ ocp = ev.ocp
 H = ev.hessian_setup()
 W = synthetic.batch(ocp, a.batch, seed=1)
 p = ocp.default_p()
+if ev.hess_objective:
+    p[:ocp.n_v] = W[0]
+    p[ocp.n_v:ocp.p_theta0] = 1.0
 Lam = np.random.default_rng(2).uniform(-1.0, 1.0, (a.batch, ocp.n_g))
 dW, dP, dL = torch.from_numpy(W).cuda(), torch.from_numpy(p).cuda(), torch.from_numpy(Lam).cuda()
 dH = torch.empty((a.batch, H.nnz), dtype=torch.float64, device='cuda')
+dS = torch.ones((a.batch,), dtype=torch.float64, device='cuda') if ev.hess_objective else None
 for _ in range(2):
-    ev.eval_hessian_device(dW, dP, dL, dH)
+    ev.eval_hessian_device(dW, dP, dL, dH, sigma=dS)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.reps):
-    ev.eval_hessian_device(dW, dP, dL, dH)
+    ev.eval_hessian_device(dW, dP, dL, dH, sigma=dS)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.reps
