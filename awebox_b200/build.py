@@ -36,7 +36,10 @@ def generate(spec_name, ocp=None):
     from .codegen import NodeCode
     if ocp is None:
         ocp = OcpProblem(ModelSpec.load(spec_name))
-    stats = NodeCode(ocp).write(gen_dir(spec_name))
+    nc = NodeCode(ocp)
+    stats = nc.write(gen_dir(spec_name))
+    from .ocp.outputs import OutputsMap
+    stats['outputs'] = OutputsMap(ocp).write(gen_dir(spec_name), nc)
     from .ocp.hessian import LagrangianHessian, has_objective
     stats['hessian'] = LagrangianHessian(ocp, objective=has_objective(ocp)).write(gen_dir(spec_name))
     with open(os.path.join(gen_dir(spec_name), 'stats.json'), 'w') as f:
@@ -67,7 +70,7 @@ def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None
     os.makedirs(LIBDIR, exist_ok=True)
     g = gen or gen_dir(spec_name)
     src = os.path.join(CSRC, 'awegpu_kernels.cu')
-    deps = [src] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", "_reduce.cu", "_hess.cu"))] + \
+    deps = [src] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", "_reduce.cu", "_hess.cu", "_out.cu"))] + \
         [os.path.join(g, f) for f in sorted(os.listdir(g)) if f.endswith(('.h', '.inc'))] + \
         [os.path.join(ROOT, 'include', 'awegpu.h')]
     out = out or lib_path(spec_name)
@@ -99,8 +102,15 @@ def compile_cuda(spec_name, force=False, verbose=False, extra_flags=(), out=None
         cmd = [nvcc] + common + ['-c', '-o', obj, os.path.join(CSRC, 'awegpu_hess.cu')]
         return 'hess', obj, cmd, subprocess.run(cmd, capture_output=True, text=True)
 
-    with ThreadPoolExecutor(N_TU + 2) as pool:
-        futs = [pool.submit(one, tu) for tu in range(N_TU)] + [pool.submit(reduce_unit, 0), pool.submit(hess_unit, 0)]
+    def out_unit(_):
+        # outputs map (awegpu_out.cu + generated node_out.inc)
+        obj = os.path.join(objdir, 'out.o')
+        cmd = [nvcc] + common + ['-c', '-o', obj, os.path.join(CSRC, 'awegpu_out.cu')]
+        return 'out', obj, cmd, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(N_TU + 3) as pool:
+        futs = [pool.submit(one, tu) for tu in range(N_TU)] + [pool.submit(reduce_unit, 0), pool.submit(hess_unit, 0),
+                                                                pool.submit(out_unit, 0)]
         results = [f.result() for f in futs]
     for tu, obj, cmd, res in results:
         logs.append(' '.join(cmd) + '\n' + res.stdout + res.stderr)

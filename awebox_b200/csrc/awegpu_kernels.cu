@@ -35,6 +35,7 @@
 #include "awegpu.h"
 #include "awegpu_reduce.h"
 #include "awegpu_hess.h"
+#include "awegpu_out.h"
 #include "model_defs.h"
 
 // Translation units.  The generated programs make this file expensive to compile (minutes of single-threaded
@@ -1459,6 +1460,11 @@ struct awegpu_handle {
     int hess_chunk_tiles = 64;
     float hess_ms = -1.f;
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr;
+    // outputs map (awegpu_out.cu)
+    double *dOutCoeff = nullptr, *dOut = nullptr;
+    size_t capOut = 0;
+    float out_ms = -1.f;
+    cudaEvent_t ev_o0 = nullptr, ev_o1 = nullptr;
     // single-instance host calls as CUDA graphs (AWEGPU_GRAPH=0 disables)
     bool use_graph = true, capturing = false;
     cudaGraphExec_t graph_exec[8] = {nullptr};
@@ -1538,6 +1544,9 @@ extern "C" void awegpu_destroy(awegpu_handle_t *h)
     cudaFree(h->counters), cudaFree(h->dLam), cudaFree(h->dVec), cudaFree(h->dRed);
     cudaFree(h->dF), cudaFree(h->dGrad), cudaFree(h->dComp);
     cudaFree(h->hess_scr), cudaFree(h->dHess), cudaFree(h->dLamH);
+    cudaFree(h->dOutCoeff), cudaFree(h->dOut);
+    if (h->ev_o0) cudaEventDestroy(h->ev_o0);
+    if (h->ev_o1) cudaEventDestroy(h->ev_o1);
     if (h->ev_h0) cudaEventDestroy(h->ev_h0);
     if (h->ev_h1) cudaEventDestroy(h->ev_h1);
     for (cudaGraphExec_t ge : h->graph_exec)
@@ -1803,6 +1812,10 @@ static int create_impl(awegpu_handle *h, const awegpu_problem_t *p, int device)
     CK(awe_init_tu2(p->coeff_coll, p->coeff_cont));
     CK(awe_init_tu3(p->coeff_coll, p->coeff_cont));
     CK(awe_init_tu4(p->coeff_coll, p->coeff_cont));
+    CK(cudaMalloc(&h->dOutCoeff, sizeof(double) * (N_D + 1) * (N_D + 1)));
+    CK(cudaMemcpy(h->dOutCoeff, p->coeff_coll, sizeof(double) * (N_D + 1) * (N_D + 1), cudaMemcpyHostToDevice));
+    CK(cudaEventCreate(&h->ev_o0));
+    CK(cudaEventCreate(&h->ev_o1));
     CK((attr_node_impl<false, false, 0>()));
     CK((attr_node_impl<false, false, 1>()));
     CK((attr_node_impl<false, false, 2>()));
@@ -2608,6 +2621,72 @@ extern "C" int awegpu_eval_hessian_host(awegpu_handle_t *h, int32_t B, const dou
     rc = awegpu_eval_hessian(h, B, h->dW, h->dP, h->dLamH, Sigma ? h->dLamH + nL : nullptr, flags, h->dHess, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(H, h->dHess, nH * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// --------------------------------------------------------------------------- outputs map (awegpu_out.cu)
+extern "C" int32_t awegpu_outputs_n(void) { return awe_out_n(); }
+extern "C" const char *awegpu_outputs_label(int32_t i) { return awe_out_label(i); }
+extern "C" int32_t awegpu_outputs_nodes(awegpu_handle_t *h) { return h ? h->dp.n_k * (N_D + 1) : -1; }
+
+extern "C" int awegpu_eval_outputs(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags, double *Out,
+                                   void *stream)
+{
+    if (!h) return 1;
+    if (B <= 0) return 0;
+    if (!W || !P || !Out) {
+        set_err(h, "awegpu_eval_outputs: W, P and Out are required");
+        return 1;
+    }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    const DevProblem &d = h->dp;
+    OutArgs a{};
+    a.B = B, a.n_v = d.n_v, a.n_k = d.n_k, a.W = W, a.P = P, a.Out = Out;
+    a.ld_p = (flags & AWEGPU_P_SHARED) ? 0 : ((flags & AWEGPU_P_THETA0) ? d.n_theta0 : d.n_p);
+    a.p_off = (flags & AWEGPU_P_THETA0) ? 0 : d.p_theta0;
+    a.v_x0 = d.x_first, a.v_phi = d.v_phi, a.theta_idx = d.theta_idx, a.tf_idx = d.tf_idx, a.coeff = h->dOutCoeff;
+    CK(cudaEventRecord(h->ev_o0, st));
+    const int e = awe_out_launch(st, a);
+    if (e) {
+        set_err(h, std::string("awegpu_eval_outputs: ") + cudaGetErrorString((cudaError_t)e));
+        return 2;
+    }
+    h->launches += 1;
+    CK(cudaEventRecord(h->ev_o1, st));
+    h->out_ms = -2.f;
+    return 0;
+}
+
+extern "C" float awegpu_last_outputs_ms(awegpu_handle_t *h)
+{
+    if (!h || h->out_ms == -1.f) return -1.f;
+    if (cudaEventSynchronize(h->ev_o1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, h->ev_o0, h->ev_o1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+extern "C" int awegpu_eval_outputs_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags,
+                                        double *Out)
+{
+    if (!h) return 1;
+    if (B <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    const DevProblem &d = h->dp;
+    const size_t ldp = (flags & AWEGPU_P_THETA0) ? (size_t)d.n_theta0 : (size_t)d.n_p;
+    const size_t nW = (size_t)B * d.n_v, nP = (flags & AWEGPU_P_SHARED) ? ldp : (size_t)B * ldp;
+    const size_t nO = (size_t)B * (size_t)awe_out_n() * (size_t)(d.n_k * (N_D + 1));
+    int rc = grow(h, &h->dW, &h->hW, &h->capW, &h->hcapW, nW, false) | grow(h, &h->dP, &h->hP, &h->capP, &h->hcapP, nP, false) |
+             grow_dev(h, &h->dOut, &h->capOut, nO);
+    if (rc) return rc;
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->dW, W, nW * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->dP, P, nP * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = awegpu_eval_outputs(h, B, h->dW, h->dP, flags, h->dOut, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(Out, h->dOut, nO * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return 0;
 }

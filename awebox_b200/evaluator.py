@@ -70,6 +70,15 @@ def load_library(spec_name):
     lib.awegpu_last_hessian_ms.argtypes = [C.c_void_p]
     lib.awegpu_last_hessian_ms.restype = C.c_float
     lib.awegpu_model_dims.argtypes = [C.POINTER(C.c_int32)] * 4 + [C.POINTER(C.c_int64)] * 2
+    lib.awegpu_outputs_n.restype = C.c_int32
+    lib.awegpu_outputs_label.restype = C.c_char_p
+    lib.awegpu_outputs_label.argtypes = [C.c_int32]
+    lib.awegpu_outputs_nodes.restype = C.c_int32
+    lib.awegpu_outputs_nodes.argtypes = [C.c_void_p]
+    lib.awegpu_eval_outputs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.awegpu_eval_outputs_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.awegpu_last_outputs_ms.argtypes = [C.c_void_p]
+    lib.awegpu_last_outputs_ms.restype = C.c_float
     if lib.awegpu_model_name().decode() != spec_name:
         raise AwegpuError('library %s was generated for model %r' % (path, lib.awegpu_model_name().decode()))
     return lib
@@ -349,6 +358,50 @@ class Evaluator(object):
         return self.eval_hessian(np.asarray(V, dtype=np.float64)[None, :], np.asarray(P, dtype=np.float64),
                                  np.asarray(lam_g, dtype=np.float64)[None, :],
                                  sigma=float(lam_f) if self.hess_objective else None)[0]
+
+    # ------------------------------------------------------------------ outputs map
+    def outputs_labels(self):
+        """labels '[group,name,i]' of the rows of the outputs map, as in ``model.outputs.labels()``"""
+        return [self.lib.awegpu_outputs_label(i).decode() for i in range(int(self.lib.awegpu_outputs_n()))]
+
+    def outputs_index(self, group, name=None):
+        pre = '[%s,' % group if name is None else '[%s,%s,' % (group, name)
+        return [i for i, l in enumerate(self.outputs_labels()) if l.startswith(pre)]
+
+    def eval_outputs(self, W, P):
+        """``nlp.Outputs_fun(V, P)`` for a batch: W [B, n_v], P as ``eval`` -> [B, n_out, n_k (d+1)] (nodes of interval
+        k: shooting node, then the d collocation nodes)"""
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        if W.ndim == 1:
+            W = W[None, :]
+        B = W.shape[0]
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        out = np.empty((B, int(self.lib.awegpu_outputs_n()), int(self.lib.awegpu_outputs_nodes(self.handle))))
+        rc = self.lib.awegpu_eval_outputs_host(self.handle, B, W.ctypes.data, P.ctypes.data, flags, out.ctypes.data)
+        self._check(rc, 'awegpu_eval_outputs_host')
+        return out
+
+    def eval_outputs_device(self, W, P, Out, stream=None):
+        import torch
+        for t in (W, P, Out):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+                raise ValueError('eval_outputs_device needs contiguous float64 CUDA tensors')
+        B = W.shape[0]
+        flags = self.p_flags(P, self.n_p, self.n_theta0, B)
+        if stream is None:
+            stream = torch.cuda.current_stream(W.device).cuda_stream
+        if not stream:
+            stream = 1
+        rc = self.lib.awegpu_eval_outputs(self.handle, B, W.data_ptr(), P.data_ptr(), flags, Out.data_ptr(), C.c_void_p(stream))
+        self._check(rc, 'awegpu_eval_outputs')
+
+    def last_outputs_ms(self):
+        return float(self.lib.awegpu_last_outputs_ms(self.handle))
+
+    def outputs_fun(self, V, P):
+        """one instance, the way the reference calls ``nlp.Outputs_fun(V, P)``: -> [n_out, n_nodes]"""
+        return self.eval_outputs(np.asarray(V, dtype=np.float64)[None, :], np.asarray(P, dtype=np.float64))[0]
 
     def last_eval_ms(self):
         return float(self.lib.awegpu_last_eval_ms(self.handle))

@@ -387,6 +387,7 @@ class NodeModel(object):
             g_list.append(c), gdot_list.append(dc), gddot_list.append(ddc)
             work = work + self.si('z', 'lambda' + lab)[0] * c
         self.holonomic = (g_list, gdot_list, gddot_list)
+        self.work_holonomic = work
 
         lag = e_kin - e_pot - work
 
@@ -617,7 +618,8 @@ class NodeModel(object):
         f_body = S.vec([-f_ctrl[0], f_ctrl[1], -f_ctrl[2]])
         m_body = S.vec([-m_ctrl[0], m_ctrl[1], -m_ctrl[2]])
         f_earth = S.matvec(R, f_body)
-        self.aero[kite] = {'vec_u': vec_u, 'dcm': R, 'alpha': alpha, 'beta': beta}
+        self.aero[kite] = {'vec_u': vec_u, 'dcm': R, 'alpha': alpha, 'beta': beta, 'f_body': f_body, 'm_body': m_body,
+                           'f_earth': f_earth, 'f_control': S.vec(f_ctrl), 'rho': rho}
         return f_earth, m_body
 
     # ---- 3-DOF (point-mass) kite aerodynamics (three_dof_kite.py:47-64, 100-137, 171-218;
@@ -657,7 +659,7 @@ class NodeModel(object):
         lift_mag = cl * 1. / 2. * rho * S.dot(vec_u, vec_u) * s_ref
         drag_mag = cd * 1. / 2. * rho * self.norm(vec_u) * s_ref
         f_earth = S.vec([lift_mag * e3[i] + drag_mag * vec_u[i] for i in range(3)])
-        self.aero[kite] = {'vec_u': vec_u, 'dcm': dcm}
+        self.aero[kite] = {'vec_u': vec_u, 'dcm': dcm, 'f_earth': f_earth, 'rho': rho}
         return f_earth
 
     # ---- path inequalities (awebox/mdl/dynamics.py:457-484, 627-821, 1022-1117)

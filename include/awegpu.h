@@ -212,6 +212,23 @@ int awegpu_eval_hessian_host(awegpu_handle_t *h, int32_t B, const double *W, con
 /* device time of the most recent awegpu_eval_hessian (ms, CUDA events on the launching stream); <0 if none */
 float awegpu_last_hessian_ms(awegpu_handle_t *h);
 
+/* ---- outputs map.  Replaces nlp.Outputs_fun(V, P) (awebox/ocp/nlp.py:335-336), the
+ * horizontal concatenation of model.outputs_fun over the nodes of every interval: shooting node k, then the d
+ * collocation nodes (awebox/ocp/collocation.py:366-381, awebox/ocp/discretization.py:316-334; zoh controls).
+ * Out [B][n_out][n_nodes], n_nodes = n_k (d+1): Out[b] is the C-contiguous image of np.array(Outputs_fun(V_b, P_b))
+ * (one label = one contiguous series over the nodes).  The reference addresses entries BY LABEL
+ * ('[group,name,i]' of model.outputs); its index order depends on Python set iteration and is not fixed, so the label
+ * table is part of the interface: awegpu_outputs_label(i), i < awegpu_outputs_n().
+ * P: as for awegpu_eval_batch (AWEGPU_P_FULL / AWEGPU_P_THETA0 / AWEGPU_P_SHARED). */
+int32_t awegpu_outputs_n(void);
+const char *awegpu_outputs_label(int32_t i);
+int32_t awegpu_outputs_nodes(awegpu_handle_t *h);
+int awegpu_eval_outputs(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags, double *Out,
+                        void *stream);
+int awegpu_eval_outputs_host(awegpu_handle_t *h, int32_t B, const double *W, const double *P, int32_t flags, double *Out);
+/* device time of the most recent awegpu_eval_outputs (ms, CUDA events on the launching stream); <0 if none */
+float awegpu_last_outputs_ms(awegpu_handle_t *h);
+
 /* device time of the most recent eval (ms, CUDA events on the launching stream); <0 if none */
 float awegpu_last_eval_ms(awegpu_handle_t *h);
 /* device time of the dominant kernel (collocation-node programs, output stage) of the first chunk of the

@@ -342,13 +342,50 @@ HESSF_JOBS = {'ampyx_ap2': [(4, 3), (40, 2)], 'dual_kites': [(3, 2), (20, 2)]}
 
 HESS_JOBS = {'ampyx_ap2': [(4, 3), (40, 2)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 3)]}
 
+OUT_JOBS = {'ampyx_ap2': [(4, 3), (40, 2)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 2)]}
+
+
+def run_outputs(config, n_k, n_pts):
+    """golden vectors of the outputs map: nlp.Outputs_fun(V, P), the horizontal
+    concatenation of model.outputs_fun over the shooting and collocation nodes of every interval
+    (awebox/ocp/collocation.py:366-381, awebox/ocp/discretization.py:316-334), with the labels of
+    model.outputs -> tests/golden/<config>_nk<N>_out.npz: w [n, n_v], p [n_p], out [n, n_nodes, n_out]."""
+    t0 = time.time()
+    T = ref_build.build(config, n_k=n_k)
+    import casadi as cas
+    nlp = T.nlp
+    rng = np.random.default_rng(20261020 + n_k)
+    n_v = len(T.w0)
+    W = np.array([T.w0] + [T.w0 * (1.0 + 1e-2 * rng.uniform(-1.0, 1.0, n_v)) + 1e-3 * rng.uniform(-1.0, 1.0, n_v)
+                           for _ in range(n_pts - 1)])
+    phi_idx = [i for i, l in enumerate(nlp.V.labels()) if l.startswith('[phi,')]
+    W[1:, phi_idx] = rng.uniform(0.2, 0.8, (n_pts - 1, len(phi_idx)))
+    p = T.p0
+    OUT = []
+    for w in W:
+        o = np.array(nlp.Outputs_fun(cas.DM(w), cas.DM(p)).full())
+        OUT.append(o.T.copy())                      # [n_nodes, n_out]
+    labels = T.model.outputs.labels()
+    out = os.path.join(GOLDEN, '%s_nk%d_out.npz' % (config, n_k))
+    np.savez_compressed(out, w=W, p=p, out=np.array(OUT), labels=np.array(labels))
+    print('%s n_k=%d outputs: %s  (%.1f s) -> %s' % (config, n_k, np.array(OUT).shape, time.time() - t0,
+                                                   os.path.relpath(out, ROOT)))
+
+
 OBJ_JOBS = {'ampyx_ap2': [(4, 3), (40, 3)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 3)]}
 
 
 if __name__ == '__main__':
     import logging
     logging.disable(logging.CRITICAL)
-    args = [a for a in sys.argv[1:] if a not in ('--objective', '--hessian')]
+    args = [a for a in sys.argv[1:] if a not in ('--objective', '--hessian', '--outputs')]
+    if '--outputs' in sys.argv[1:]:
+        small = '--small' in args
+        args = [a for a in args if a != '--small']
+        for config in (args or list(OUT_JOBS)):
+            for n_k, n_pts in (OUT_JOBS[config][:1] if small else OUT_JOBS[config]):
+                run_outputs(config, n_k, n_pts)
+        sys.exit(0)
     if '--hessian' in sys.argv[1:]:
         small = '--small' in args
         args = [a for a in args if a != '--small']

@@ -1,0 +1,193 @@
+"""Outputs map: nlp.Outputs_fun(V, P) against the reference run.
+
+Golden vectors: tests/golden/*_out.npz (oracle/make_golden.py --outputs): the reference's own ``nlp.Outputs_fun`` at its
+initial guess and at perturbed points, with the labels of ``model.outputs``.  The reference addresses outputs by label
+(its index order follows Python set iteration), so entries are matched by label; every label of the reference must be
+present.
+
+CPU: the expressions of awebox_b200/mdl/outputs.py evaluated by the host restatement (OutputsMap.evaluate).
+GPU: awegpu_eval_outputs through the C ABI against the golden vectors, against the host restatement on seeded batches
+(ragged sizes, parameter modes, device entry) and, at BASELINE sizes, against properties: the 'model_equalities' rows of
+the collocation nodes are the collocation rows of g, airspeed = |air_velocity|, xdot of the shooting nodes is V[xdot].
+
+Tolerance: |a - b| <= 1e-9 max(|ref|, S_name, 1e-6 S_group), S_name = largest |ref| over the nodes and components of the
+same name, S_group the same over the group: relative to the entry, with a floor for entries that are cancellation
+noise at the test points (d c / d t at a consistent point, the side force of the 3-DOF kite, the Frenet centre
+velocity = difference of 20 m/s terms); at the unperturbed initial guess (point 0) an absolute 1e-10 is added."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, get_ocp
+
+CASES = [('ampyx_ap2', 4), ('ampyx_ap2', 40), ('dual_kites', 3), ('dual_kites', 20), ('mpc_3dof', 3), ('mpc_3dof', 10)]
+SMALL = [('ampyx_ap2', 4), ('dual_kites', 3), ('mpc_3dof', 3), ('mpc_3dof', 10)]
+_MAP = {}
+
+
+def outputs_map(name, n_k):
+    from awebox_b200.ocp.outputs import OutputsMap
+    if (name, n_k) not in _MAP:
+        _MAP[(name, n_k)] = OutputsMap(get_ocp(name, n_k))
+    return _MAP[(name, n_k)]
+
+
+def tolerance(labels, ref, consistent_point=False):
+    """ref [n_out, n_nodes] in the order of ``labels`` -> tolerance of the same shape.  ``consistent_point``: the
+    unperturbed initial guess, where whole outputs (d c / d t, xdot - x') vanish up to the rounding of their operands:
+    an absolute 1e-10 is added there (xdot of the collocation polynomial is a sum of terms 100 times larger than its value,
+    and it is multiplied by masses and speeds); the perturbed points are judged without it"""
+    names = [l[1:-1].rsplit(',', 1)[0] for l in labels]
+    groups = [n.split(',')[0] for n in names]
+    mag = np.max(np.abs(ref), axis=1)
+    s_name, s_group = {}, {}
+    for n, g, v in zip(names, groups, mag):
+        s_name[n] = max(s_name.get(n, 0.0), v)
+        s_group[g] = max(s_group.get(g, 0.0), v)
+    floor = np.array([max(s_name[n], 1e-6 * s_group[g]) for n, g in zip(names, groups)])
+    return 1e-9 * np.maximum(np.abs(ref), floor[:, None]) + (1e-10 if consistent_point else 0.0)
+
+
+def by_label(gold, labels, pt):
+    """golden values of point ``pt`` reordered to ``labels``: [n_out, n_nodes]"""
+    gi = {str(l): i for i, l in enumerate(gold['labels'])}
+    return gold['out'][pt][:, [gi[l] for l in labels]].T
+
+
+@pytest.mark.parametrize('name,n_k', CASES)
+def test_every_reference_label_is_present(name, n_k):
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d_out.npz' % (name, n_k)))
+    om = outputs_map(name, n_k)
+    assert sorted(om.labels) == sorted(str(l) for l in gold['labels'])
+    assert len(set(om.labels)) == om.n_out
+    assert gold['out'].shape[1:] == (om.n_nodes, om.n_out)
+
+
+@pytest.mark.parametrize('name,n_k', SMALL)
+def test_host_restatement_against_reference(name, n_k):
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d_out.npz' % (name, n_k)))
+    om = outputs_map(name, n_k)
+    for pt in range(gold['w'].shape[0]):
+        out = om.evaluate(gold['w'][pt], gold['p']).T
+        ref = by_label(gold, om.labels, pt)
+        assert np.all(np.isfinite(ref))
+        bad = np.abs(out - ref) > tolerance(om.labels, ref, pt == 0)
+        assert not bad.any(), [om.labels[i] for i in np.unique(np.nonzero(bad)[0])][:10]
+
+
+def test_library_labels_match_the_expressions():
+    """the compiled label table is the one of awebox_b200/mdl/outputs.py (no GPU needed: table lookups only)"""
+    from awebox_b200.evaluator import load_library
+    for name, n_k in (('ampyx_ap2', 4), ('dual_kites', 3), ('mpc_3dof', 3)):
+        lib = load_library(name)
+        om = outputs_map(name, n_k)
+        assert int(lib.awegpu_outputs_n()) == om.n_out
+        assert [lib.awegpu_outputs_label(i).decode() for i in range(om.n_out)] == om.labels
+        assert lib.awegpu_outputs_label(om.n_out) is None
+
+
+# ------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,n_k', CASES)
+def test_gpu_outputs_against_reference(name, n_k):
+    from awebox_b200.evaluator import Evaluator
+    gold = np.load(os.path.join(GOLDEN, '%s_nk%d_out.npz' % (name, n_k)))
+    ev = Evaluator(name, n_k=n_k)
+    labels = ev.outputs_labels()
+    assert sorted(labels) == sorted(str(l) for l in gold['labels'])
+    out = ev.eval_outputs(gold['w'], gold['p'])
+    assert out.shape == (gold['w'].shape[0], len(labels), n_k * (ev.ocp.d + 1))
+    worst = 0.0
+    for pt in range(gold['w'].shape[0]):
+        ref = by_label(gold, labels, pt)
+        err = np.abs(out[pt] - ref)
+        tol = tolerance(labels, ref, pt == 0)
+        bad = err > tol
+        assert not bad.any(), [labels[i] for i in np.unique(np.nonzero(bad)[0])][:10]
+        worst = max(worst, float(np.max(err[tol > 0] / tol[tol > 0])) * 1e-9)
+        # single-instance entry, the way the reference calls Outputs_fun(V, P)
+        one = ev.outputs_fun(gold['w'][pt], gold['p'])
+        assert np.array_equal(one, out[pt])
+    print('%s n_k=%d: %d outputs x %d nodes, largest error %.1e of the tolerance scale' % (name, n_k, len(labels),
+                                                                                          out.shape[2], worst))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,n_k,B', [('ampyx_ap2', 4, 37), ('dual_kites', 3, 5), ('mpc_3dof', 3, 33)])
+def test_gpu_outputs_batch_against_host_restatement(name, n_k, B):
+    """ragged batch, per-instance theta0, theta0-only and full parameter vectors, device entry"""
+    import torch
+    from awebox_b200.evaluator import Evaluator
+    from awebox_b200 import synthetic
+    ev = Evaluator(name, n_k=n_k)
+    ocp = ev.ocp
+    om = outputs_map(name, n_k)
+    W = synthetic.batch(ocp, B, seed=11)
+    rng = np.random.default_rng(5)
+    p0 = ocp.default_p()
+    P = np.tile(p0, (B, 1))
+    P[:, ocp.p_theta0:] *= 1.0 + 1e-3 * rng.uniform(-1.0, 1.0, (B, ocp.n_theta0))
+    out_full = ev.eval_outputs(W, P)
+    out_th0 = ev.eval_outputs(W, np.ascontiguousarray(P[:, ocp.p_theta0:]))
+    assert np.array_equal(out_full, out_th0)
+    out_shared = ev.eval_outputs(W, p0)
+    for b in (0, B // 2, B - 1):
+        ref = om.evaluate(W[b], P[b]).T
+        assert np.all(np.abs(out_full[b] - ref) <= tolerance(om.labels, ref))
+        ref = om.evaluate(W[b], p0).T
+        assert np.all(np.abs(out_shared[b] - ref) <= tolerance(om.labels, ref))
+    dev = torch.device('cuda:0')
+    Wd, Pd = torch.from_numpy(W).to(dev), torch.from_numpy(P).to(dev)
+    Od = torch.empty(out_full.shape, dtype=torch.float64, device=dev)
+    ev.eval_outputs_device(Wd, Pd, Od)
+    torch.cuda.synchronize()
+    assert np.array_equal(Od.cpu().numpy(), out_full)
+    assert ev.last_outputs_ms() > 0.0
+    assert ev.eval_outputs(W[:0], p0).shape[0] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,n_k,B', [('ampyx_ap2', 40, 512), ('dual_kites', 20, 256), ('mpc_3dof', 10, 2048)])
+def test_gpu_outputs_properties_at_baseline_sizes(name, n_k, B):
+    """size-independent properties: the equality rows of the collocation nodes are the collocation rows of g (two
+    different kernels and programs), airspeed = |air_velocity|, xdot of a shooting node is V[xdot, k], instances do not
+    leak into each other (permutation)"""
+    from awebox_b200.evaluator import Evaluator
+    from awebox_b200 import synthetic
+    ev = Evaluator(name, n_k=n_k)
+    ocp = ev.ocp
+    d = ocp.d
+    W = synthetic.batch(ocp, B, seed=3)
+    p = ocp.default_p()
+    out = ev.eval_outputs(W, p)
+    labels = ev.outputs_labels()
+    G, _ = ev.eval(W, p, jac=False)
+    eq = ev.outputs_index('model_equalities')
+    assert len(eq) == ocp.n_eq
+    scale = float(ocp.constraint_scale)
+    for k in (0, n_k // 2, n_k - 1):
+        for j in range(d):
+            node = k * (d + 1) + 1 + j
+            r0 = int(ocp.row_coll[k][j])
+            g_rows = G[:, r0:r0 + ocp.n_eq]
+            o_rows = out[:, eq, node] * scale
+            tol = 1e-10 * np.maximum(1.0, np.max(np.abs(g_rows), axis=0, keepdims=True))
+            assert np.all(np.abs(g_rows - o_rows) <= tol)
+    for kite in ocp.model.arch.kite_nodes:
+        va = out[:, ev.outputs_index('aerodynamics', 'air_velocity%d' % kite), :]
+        sp = out[:, ev.outputs_index('aerodynamics', 'airspeed%d' % kite)[0], :]
+        assert np.allclose(np.sqrt(np.sum(va * va, axis=1)), sp, rtol=1e-13, atol=0.0)
+    # shooting nodes read the lifted xdot
+    i0 = 0
+    for nm, sz in ocp.model.var_list['xdot']:
+        idx = ev.outputs_index('xdot_from_var', nm)
+        k0, _ = ocp.model.offset[('xdot', nm)]
+        s = ocp.spec.scaling[k0:k0 + sz]
+        for k in (0, n_k - 1):
+            lifted = W[:, ocp.v_xdot[k] + i0:ocp.v_xdot[k] + i0 + sz] * s
+            assert np.allclose(out[:, idx, k * (d + 1)], lifted, rtol=1e-14, atol=0.0)
+        i0 += sz
+    perm = np.random.default_rng(0).permutation(B)
+    assert np.array_equal(ev.eval_outputs(W[perm], p), out[perm])
+    assert np.all(np.isfinite(out))
