@@ -43,37 +43,34 @@ __global__ void __launch_bounds__(OUT_THREADS) awegpu_out_kernel(const OutArgs a
     const double *__restrict__ Wb = a.W + (size_t)b * a.n_v;
     const double *__restrict__ th0 = a.P + (size_t)b * a.ld_p + a.p_off;
     const double *__restrict__ slab = Wb + a.v_x0 + (size_t)k * SLAB_W;
-    double v[AWE_N_VAR];
+    // x, u, z are read where the program uses them (read-only loads: the compiler may repeat a load instead of keeping
+    // the value in a register); xdot and theta are formed once
+    const double *__restrict__ xp = jj < 0 ? slab : slab + OFF_CX(0) + (size_t)jj * (N_X + N_Z);
+    const double *__restrict__ zp = jj < 0 ? slab + OFF_Z : xp + N_X;
+    double xd[N_X], th[N_TH];
     if (jj < 0) {
 #pragma unroll
-        for (int m = 0; m < N_X; ++m) v[m] = slab[m], v[N_X + m] = slab[OFF_XDOT + m];
-#pragma unroll
-        for (int c = 0; c < N_Z; ++c) v[2 * N_X + N_U + c] = slab[OFF_Z + c];
+        for (int m = 0; m < N_X; ++m) xd[m] = __ldg(slab + OFF_XDOT + m);
     } else {
-        const double s = (double)a.n_k / Wb[__ldg(a.tf_idx + k)];
+        const double s = (double)a.n_k / __ldg(Wb + __ldg(a.tf_idx + k));
         double cc[N_D + 1];
 #pragma unroll
         for (int r = 0; r <= N_D; ++r) cc[r] = s * __ldg(a.coeff + r * (N_D + 1) + jj + 1);
-        const double *__restrict__ xj = slab + OFF_CX(0) + (size_t)jj * (N_X + N_Z);
 #pragma unroll
         for (int m = 0; m < N_X; ++m) {
-            double xd = cc[0] * slab[m];
+            double acc = cc[0] * __ldg(slab + m);
 #pragma unroll
-            for (int r = 1; r <= N_D; ++r) xd = fma(cc[r], slab[OFF_CX(r - 1) + m], xd);
-            v[m] = xj[m];
-            v[N_X + m] = xd;
+            for (int r = 1; r <= N_D; ++r) acc = fma(cc[r], __ldg(slab + OFF_CX(r - 1) + m), acc);
+            xd[m] = acc;
         }
-#pragma unroll
-        for (int c = 0; c < N_Z; ++c) v[2 * N_X + N_U + c] = xj[N_X + c];
     }
 #pragma unroll
-    for (int c = 0; c < N_U; ++c) v[2 * N_X + c] = slab[OFF_U + c];
-#pragma unroll
-    for (int c = 0; c < N_TH; ++c) v[2 * N_X + N_U + N_Z + c] = Wb[__ldg(a.theta_idx + k * N_TH + c)];
+    for (int c = 0; c < N_TH; ++c) th[c] = __ldg(Wb + __ldg(a.theta_idx + k * N_TH + c));
     double *__restrict__ outp = a.Out + (size_t)b * AWE_N_OUT * n_nodes + n;
     const double *__restrict__ phi = Wb + a.v_phi;
-#define VIN(i) v[i]
-#define PIN(i) ((i) < AWE_N_THETA0 ? __ldg(th0 + (i)) : phi[(i) - AWE_N_THETA0])
+#define VIN(i) ((i) < N_X ? __ldg(xp + (i)) : (i) < 2 * N_X ? xd[(i) - N_X] : (i) < 2 * N_X + N_U ? __ldg(slab + OFF_U + ((i) - 2 * N_X)) \
+                : (i) < 2 * N_X + N_U + N_Z ? __ldg(zp + ((i) - 2 * N_X - N_U)) : th[(i) - 2 * N_X - N_U - N_Z])
+#define PIN(i) ((i) < AWE_N_THETA0 ? __ldg(th0 + (i)) : __ldg(phi + ((i) - AWE_N_THETA0)))
 #define OUT(i, val) outp[(size_t)(i) * n_nodes] = (val)
 #include "node_out.inc"
 #undef VIN

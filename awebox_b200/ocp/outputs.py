@@ -10,6 +10,8 @@ collocation nodes take ``xdot`` from the collocation polynomial, the shooting no
 host restatement used by the tests (numpy + expression evaluation, one instance); the product path is the CUDA kernel
 behind ``awegpu_eval_outputs`` generated from the same expressions (node_out.inc).
 """
+import os
+
 import numpy as np
 
 from .. import sym as S
@@ -66,11 +68,43 @@ class OutputsMap(object):
         return out
 
     # ------------------------------------------------------------------ code generation
+    SECTION_OPS = 0        # operations per section of the straight-line program (0: one section)
+
+    def emit_sections(self, emitter):
+        """the program in sections of consecutive labels, each a scope of its own: common subexpressions are shared
+        inside a section and recomputed across sections, so that no temporary lives longer than its section (the
+        whole program in one scope needs more than 255 registers per thread for the dual-kite model)"""
+        budget = int(os.environ.get('AWE_OUT_SECTION_OPS', self.SECTION_OPS))
+        if budget <= 0:
+            text, st = emitter.emit(self.exprs)
+            st = dict(st)
+            st['sections'] = 1
+            return text, st
+        sections, cur = [], []
+        for i in range(self.n_out):
+            trial = cur + [i]
+            if cur and sum(S.count_ops([self.exprs[t] for t in trial]).values()) > budget:
+                sections.append(cur)
+                cur = [i]
+            else:
+                cur = trial
+        if cur:
+            sections.append(cur)
+        text, total = '', {}
+        for sec in sections:
+            body, st = emitter.emit([self.exprs[i] for i in sec])
+            for n_local, i in reversed(list(enumerate(sec))):          # local output numbers -> global ones
+                body = body.replace('OUT(%d, ' % n_local, 'OUT_(%d, ' % i)
+            text += '{\n' + body.replace('OUT_(', 'OUT(') + '}\n'
+            for key, v in st.items():
+                total[key] = total.get(key, 0) + v
+        total['sections'] = len(sections)
+        return text, total
+
     def write(self, out_dir, emitter):
         """node_out.inc (straight-line program: VIN(i) node variables, PIN(i) parameters, OUT(n, value)) and out_defs.h
         (entry count and the label table) for csrc/awegpu_out.cu; ``emitter``: a codegen.NodeCode"""
-        import os
-        text, stats = emitter.emit(self.exprs)
+        text, stats = self.emit_sections(emitter)
         banner = '// generated by awebox_b200/ocp/outputs.py from spec "%s" -- do not edit\n' % self.ocp.spec.name
         head = banner + '#define AWE_N_OUT %d\n' % self.n_out
         head += 'static const char *const awe_out_labels[AWE_N_OUT] = {\n'

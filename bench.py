@@ -447,6 +447,39 @@ def main():
                      'finite': bool(torch.isfinite(dH).all().item())}
         del dH, dLam
 
+    # ---- outputs map: nlp.Outputs_fun over all nodes, device entry, CUDA events
+    out_line = None
+    if p_mode == 'shared':
+        n_out, n_nodes = len(ev.outputs_labels()), ocp.n_k * (ocp.d + 1)
+        dPo_ = torch.from_numpy(ocp.default_p()).cuda()
+        dOut = torch.empty((B, n_out, n_nodes), dtype=torch.float64, device='cuda')
+        for _ in range(2):
+            ev.eval_outputs_device(dW, dPo_, dOut)
+        torch.cuda.synchronize()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(stream)
+        for _ in range(5):
+            ev.eval_outputs_device(dW, dPo_, dOut)
+        q1.record(stream)
+        torch.cuda.synchronize()
+        q_ms = q0.elapsed_time(q1) / 5
+        q_bytes = B * 8 * (ocp.n_v + n_out * n_nodes)                 # read w, write every output of every node
+        # the host restatement (awebox_b200/ocp/outputs.py, the checker of tests/test_outputs.py), one thread
+        from awebox_b200.ocp.outputs import OutputsMap
+        om = OutputsMap(ocp)
+        t0c, n_cpu = time.perf_counter(), 0
+        while n_cpu < 1 or (time.perf_counter() - t0c < 1.0 and n_cpu < 32):
+            om.evaluate(W[n_cpu % B], ocp.default_p())
+            n_cpu += 1
+        out_line = {'ms_per_step': q_ms, 'outputs_fun_evals_per_s': B / (q_ms * 1e-3),
+                    'node_outputs_per_s': B * n_nodes / (q_ms * 1e-3), 'n_out': n_out, 'n_nodes': n_nodes,
+                    'algorithmic_bytes': int(q_bytes), 'GBps': q_bytes / (q_ms * 1e-3) / 1e9,
+                    'api': 'awegpu_eval_outputs (device pointers): one kernel, thread = node, Out[b][label][node]',
+                    'cpu_port_evals_per_s': n_cpu / (time.perf_counter() - t0c),
+                    'cpu_port': 'expression-graph restatement, 1 thread, %d instances' % n_cpu,
+                    'finite': bool(torch.isfinite(dOut).all().item())}
+        del dOut
+
     # ---- NCCL gather of the per-rank results (north_star: "NCCL over NVLink used only to gather per-shard results")
     gather = None
     if args.gather != 'none' and world > 1:
@@ -616,6 +649,9 @@ def main():
         if hess_line is not None:
             hess_line['frac_of_hbm_peak'] = hess_line['GBps'] / peak
             line['hessian'] = hess_line
+        if out_line is not None:
+            out_line['frac_of_hbm_peak'] = out_line['GBps'] / peak
+            line['outputs'] = out_line
         if gather is not None:
             line['gather'] = gather
         print(json.dumps(line), file=json_out, flush=True)
