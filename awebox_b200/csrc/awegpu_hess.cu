@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(HESS_THREADS, AWE_HESS_MINB) awegpu_hess_node_
                 (i) < 2 * N_X + N_U + N_Z ? __ldg(rz + (i) - 2 * N_X - N_U) : __ldg(pobj + thi[(i) - 2 * N_X - N_U - N_Z]))
 #endif
         {
+// re-convergence point of the collocation warps of this CTA (generated only with HESS_SYNC_EVERY > 0)
+#define HSYNC asm volatile("bar.sync 1, %0;" ::"n"(32 * N_D) : "memory");
 #include "node_hess_coll.inc"
+#undef HSYNC
         }
 #undef VIN
 #undef XSIN
@@ -145,7 +148,9 @@ __global__ void __launch_bounds__(HESS_THREADS, AWE_HESS_MINB) awegpu_hess_node_
                 (i) < 2 * N_X + N_U + N_Z ? sl[OFF_Z + (i) - 2 * N_X - N_U] : tp[(i) - 2 * N_X - N_U - N_Z])
 #define LIN(i) lm[(i)]
         {
+#define HSYNC
 #include "node_hess_shoot.inc"
+#undef HSYNC
         }
 #undef VIN
 #undef LIN

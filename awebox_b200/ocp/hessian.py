@@ -38,6 +38,8 @@ def has_objective(ocp):
 
 
 HESS_SECTIONS = 16        # programs a node Hessian is cut into (whole columns each); see LagrangianHessian.emit
+HESS_SYNC_EVERY = 0       # > 0: a CTA-wide re-convergence point (HSYNC) every this many statements and after every section:
+                          # the warps that run the same program stay inside one instruction-cache window
 
 
 class LagrangianHessian(object):
@@ -343,6 +345,9 @@ class LagrangianHessian(object):
                 cs = set(cols[g:g + per])
                 groups.append([n for n, (_, b) in enumerate(keys) if b in cs])
         lines, n_ops = [], 0
+        import os
+        sync_every = int(os.environ.get('AWE_HESS_SYNC_EVERY', HESS_SYNC_EVERY))
+        since = 0
         for grp in groups:
             names = dict(leaf)
             n_tmp = 0
@@ -361,9 +366,16 @@ class LagrangianHessian(object):
                     names[n.idx] = 't%d' % n_tmp
                     lines.append('const double t%d = %s;' % (n_tmp, _rhs(n.op, ref(n.a), ref(n.b) if n.b is not None else None)))
                     n_tmp += 1
+                    since += 1
+                    if sync_every > 0 and since >= sync_every:
+                        lines.append('HSYNC')
+                        since = 0
                 for k in out_of.get(n.idx, []):
                     lines.append('HOUT(%d, %s);' % (k, ref(n)))
             lines.append('}')
+            if sync_every > 0:
+                lines.append('HSYNC')
+                since = 0
             n_ops += n_tmp
         return '\n'.join(lines) + '\n', n_ops
 

@@ -1,6 +1,6 @@
 """Experiments with the node Hessian programs: libraries of one spec with different section counts / nvcc flags.
 
-    python scripts/build_hess_variants.py name:sections[,-DFLAG...] ...
+    python scripts/build_hess_variants.py name:sections[,sync=N][,-DFLAG...] ...
 
 Output: awebox_b200/lib/var/libawegpu_<spec>.<name>.so (select with AWEGPU_LIB=<path>)."""
 import os
@@ -26,7 +26,8 @@ def main(argv):
         name, _, rest = arg.partition(':')
         parts = rest.split(',')
         HS.HESS_SECTIONS = int(parts[0])
-        flags = [f for f in parts[1:] if f]
+        flags = [f for f in parts[1:] if f and not f.startswith('sync=')]
+        os.environ['AWE_HESS_SYNC_EVERY'] = ([f[5:] for f in parts[1:] if f.startswith('sync=')] or ['0'])[0]
         g = os.path.join(pbuild.CSRC, 'gen', '_var_' + name)
         shutil.rmtree(g, ignore_errors=True)
         shutil.copytree(pbuild.gen_dir(SPEC), g, ignore=shutil.ignore_patterns('_obj'))
