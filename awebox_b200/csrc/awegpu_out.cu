@@ -32,8 +32,11 @@
 #define OFF_CZ(j) (OFF_CX(j) + N_X)
 #define SLAB_W (2 * N_X + N_U + N_Z + N_D * (N_X + N_Z))
 #define OUT_THREADS 128
+#ifndef AWE_OUT_MINB
+#define AWE_OUT_MINB 2          /* resident CTAs per SM the kernel is compiled for (register budget) */
+#endif
 
-__global__ void __launch_bounds__(OUT_THREADS) awegpu_out_kernel(const OutArgs a)
+__global__ void __launch_bounds__(OUT_THREADS, AWE_OUT_MINB) awegpu_out_kernel(const OutArgs a)
 {
     const int n_nodes = a.n_k * (N_D + 1);
     const long long t = (long long)blockIdx.x * OUT_THREADS + threadIdx.x;

@@ -26,12 +26,19 @@ def main(argv):
         name, _, rest = arg.partition(':')
         parts = rest.split(',')
         HS.HESS_SECTIONS = int(parts[0])
-        flags = [f for f in parts[1:] if f and not f.startswith('sync=')]
+        flags = [f for f in parts[1:] if f and not f.startswith(('sync=', 'outsec='))]
+        outsec = ([f[7:] for f in parts[1:] if f.startswith('outsec=')] or [None])[0]
         os.environ['AWE_HESS_SYNC_EVERY'] = ([f[5:] for f in parts[1:] if f.startswith('sync=')] or ['0'])[0]
         g = os.path.join(pbuild.CSRC, 'gen', '_var_' + name)
         shutil.rmtree(g, ignore_errors=True)
         shutil.copytree(pbuild.gen_dir(SPEC), g, ignore=shutil.ignore_patterns('_obj'))
         print(name, H.write(g), flush=True)
+        if outsec is not None:          # outputs map cut into sections of this many operations
+            from awebox_b200.ocp.outputs import OutputsMap
+            from awebox_b200.codegen import NodeCode
+            os.environ['AWE_OUT_SECTION_OPS'] = outsec
+            print(name, 'outputs', OutputsMap(ocp).write(g, NodeCode(ocp)), flush=True)
+            del os.environ['AWE_OUT_SECTION_OPS']
         out = os.path.join(pbuild.LIBDIR, 'var', 'libawegpu_%s.%s.so' % (SPEC, name))
         os.makedirs(os.path.dirname(out), exist_ok=True)
         jobs.append((name, flags, g, out))

@@ -191,3 +191,38 @@ def test_gpu_outputs_properties_at_baseline_sizes(name, n_k, B):
     perm = np.random.default_rng(0).permutation(B)
     assert np.array_equal(ev.eval_outputs(W[perm], p), out[perm])
     assert np.all(np.isfinite(out))
+
+
+def test_tether_moment_kat():
+    """the reference's own known-answer test of the outputs map (test/units/test_model.py:255-318): with the tether
+    attached at r_tether ('stick'), the moment of the holonomic constraint on a 6-DOF kite is
+    lambda * r_tether x (R^T q).  Same inputs and the same analytic answer as the reference's test (its model is the
+    drag-mode variant of the single 6-DOF kite; the tether moment does not involve the generators)."""
+    import copy
+    from awebox_b200.spec import ModelSpec
+    from awebox_b200.mdl.model import NodeModel
+    from awebox_b200.mdl.outputs import model_outputs
+    from awebox_b200 import sym as S
+    base = ModelSpec.load('ampyx_ap2')
+    d = copy.deepcopy(base.d)
+    d['options']['tether.attachment'] = 'stick'
+    m = NodeModel(ModelSpec(d))
+    r_tether = np.array([0.0, 0.0, -0.1])
+    si = {('x', 'q10'): [130.644, 24.5223, 74.2863], ('x', 'dq10'): [-16.3061, -27.0514, 37.5959],
+          ('x', 'omega10'): [-0.0181481, 0.275884, 1.5743],
+          ('x', 'r10'): [0.271805, 0.334641, -0.902295, 0.0595685, 0.929945, 0.362839, 0.960506, -0.15237, 0.23283],
+          ('x', 'delta10'): [0.0693676, 0.261684, -0.258425], ('x', 'l_t'): [152.184], ('z', 'lambda10'): [45.024],
+          ('theta', 'diam_t'): [0.005], ('theta', 't_f'): [3.93805]}
+    v = np.zeros(m.n_var)
+    for (vt, nm), val in si.items():
+        k, sz = m.offset[(vt, nm)]
+        v[k:k + sz] = np.array(val) / m.spec.scaling[k:k + sz]
+    params = np.concatenate([np.array(m.spec.theta0_values, dtype=float), np.ones(m.n_param - m.n_theta0)])
+    for i in range(3):
+        params[m.param_labels.index('[theta0,geometry,r_tether,%d]' % i)] = r_tether[i]
+    entries = dict(model_outputs(m))
+    exprs = [S._e(entries['[tether_moments,n10,%d]' % i]) for i in range(3)]
+    found = np.array(S.evaluate(exprs, list(m.vars) + list(m.params), np.concatenate([v, params])))
+    dcm = np.array(si[('x', 'r10')]).reshape(3, 3).T                  # column-major reshape, as cas.reshape
+    true = si[('z', 'lambda10')][0] * np.cross(r_tether, dcm.T @ np.array(si[('x', 'q10')]))
+    assert np.linalg.norm(true - found) / np.linalg.norm(true) < 1e-8
