@@ -56,6 +56,56 @@ def order(outputs):
     return seq
 
 
+ILP_WINDOW = 0      # > 0: latency-aware list scheduling inside a sliding window of the depth-first order (interleave)
+ILP_LATENCY = 8     # statements between an operation and its first consumer the interleaving aims for (DFMA: 8 clocks)
+
+
+def interleave(seq, window, latency):
+    """Depth-first order keeps the register pressure low but strings dependent operations together: a warp then issues
+    one FP64 instruction per pipeline latency.  This pass reorders inside a sliding window of ``window`` statements of
+    the depth-first order: the next statement is the earliest one of the window whose operands were issued at least
+    ``latency`` statements ago (else the one whose operands are oldest).  The first statement of the window is always
+    eligible, so the order stays a topological one and no value is delayed by more than ``window`` statements."""
+    import os
+    window = int(os.environ.get('AWE_ILP_WINDOW', window))
+    latency = int(os.environ.get('AWE_ILP_LATENCY', latency))
+    if window <= 1:
+        return seq
+    inside = set(n.idx for n in seq)
+    issued = {}
+    out, win, it = [], [], iter(seq)
+    for n in it:
+        win.append(n)
+        if len(win) >= window:
+            break
+    while win:
+        t = len(out)
+        best, best_at = None, None
+        for c in win:
+            at, ok = 0, True
+            for o in operands(c):
+                if o.idx in inside:
+                    if o.idx not in issued:
+                        ok = False
+                        break
+                    at = max(at, issued[o.idx] + latency)
+            if not ok:
+                continue
+            if at <= t:
+                best = c
+                break
+            if best_at is None or at < best_at:
+                best, best_at = c, at
+        win.remove(best)
+        issued[best.idx] = t
+        out.append(best)
+        nxt = next(it, None)
+        if nxt is not None:
+            win.append(nxt)
+    assert len(out) == len(seq)
+    return out
+
+
 class Program(object):
     """abstract instruction list:
         ('leaf', reg, node)         reg <- load of an input leaf
@@ -79,7 +129,7 @@ def allocate(outputs, n_regs, lookahead=12, seq=None, leaf_lookahead=None, leaf_
     one burst one slot, so a steady trickle of single loads (``leaf_lookahead``) makes every wait include loads that
     were issued a moment ago and exposes the full memory latency each time, whereas a generation is waited for once,
     W .. 2 W statements after it was requested."""
-    seq = order(outputs) if seq is None else seq
+    seq = interleave(order(outputs), ILP_WINDOW, ILP_LATENCY) if seq is None else seq
     # ---- schedule with output statements in output order
     pos_of = {n.idx: i for i, n in enumerate(seq)}
     sched = []          # ('op', node) | ('out', n, expr)

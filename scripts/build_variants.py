@@ -29,15 +29,22 @@ def main(argv):
         flags = []
         for k, v in defaults.items():
             setattr(CG, k, v)
+        os.environ.pop('AWE_ILP_WINDOW', None), os.environ.pop('AWE_ILP_LATENCY', None)
         for kv in filter(None, rest.split(',')):
             if kv.startswith('-D'):
                 flags.append(kv)
+            elif kv.startswith('ILP_'):                       # awebox_b200.schedule: ILP_WINDOW / ILP_LATENCY
+                k, v = kv.split('=')
+                os.environ['AWE_' + k] = v
             else:
                 k, v = kv.split('=')
                 setattr(CG, k, type(defaults[k])(v))
         CG.NodeCode.emit_scheduled.__defaults__ = (CG.N_REGS, CG.LOOKAHEAD, CG.HOT_SLOTS, CG.CHUNK, 0, False, None, 0, None, None)
         g = os.path.join(pbuild.CSRC, 'gen', '_var_' + name)
         stats = CG.NodeCode(ocp).write(g)
+        import shutil
+        for f in ('node_hess_coll.inc', 'node_hess_shoot.inc', 'hess_defs.h', 'node_out.inc', 'out_defs.h'):
+            shutil.copy(os.path.join(pbuild.gen_dir(SPEC), f), os.path.join(g, f))     # units the experiment does not touch
         out = os.path.join(pbuild.LIBDIR, 'var', 'libawegpu_%s.%s.so' % (SPEC, name))
         os.makedirs(os.path.dirname(out), exist_ok=True)
         jobs.append((name, flags, g, out))
