@@ -1455,6 +1455,8 @@ struct awegpu_handle {
     bool hess_ready = false, hess_obj = false;
     HessArgs hs{};
     std::vector<long long> hess_colind, hess_row, sp_hess, sp_lamf;
+    std::vector<long long> sp_pf, sp_one, sp_jfv, sp_jfp, sp_out;     // CasADi sparsities of awegpu_f / jac_awegpu_f / awegpu_outputs
+    std::vector<double> scratch_v, scratch_o;
     double *hess_scr = nullptr, *dHess = nullptr, *dLamH = nullptr;
     size_t cap_hess_scr = 0, capHess = 0, capLamH = 0;
     int hess_chunk_tiles = 64;
@@ -2847,6 +2849,137 @@ extern "C" const long long *awegpu_hess_lag_sparsity_out(long long i)
 extern "C" int awegpu_hess_lag_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w)
 {
     if (sz_arg) *sz_arg = 4;
+    if (sz_res) *sz_res = 1;
+    if (sz_iw) *sz_iw = 0;
+    if (sz_w) *sz_w = 0;
+    return 0;
+}
+
+// objective as CasADi externals: f = external('awegpu_f', lib) (inputs V, P; output f, 1 x 1) and the Jacobian function
+// external looks up by the jac_ prefix (inputs V, P, out_f; outputs jac_f_V dense 1 x n_v, jac_f_P structurally empty):
+// with awegpu_g, jac_awegpu_g and awegpu_hess_lag every function nlpsol evaluates comes from this library
+// (awebox/opti/preparation.py:373-379).  For an mpc trial P is Pmpc's own parameter vector (awebox/pmpc.py:152-162).
+CASADI_MEM_FUNCS(awegpu_f)
+CASADI_MEM_FUNCS(jac_awegpu_f)
+static int casadi_eval_f(const double **arg, double **res, bool jac, int mem)
+{
+    awegpu_handle *h = casadi_handle(mem);
+    if (!h) return 1;
+    if (!arg || !arg[0] || !arg[1]) {
+        set_err(h, "awegpu_f: V and P must be given");
+        return 1;
+    }
+    double *out = res ? res[0] : nullptr;
+    if (!out) return 0;
+    std::lock_guard<std::mutex> lock(h->casadi_mu);
+    double fval = 0.0;
+    if (!jac) h->scratch_v.resize(h->dp.n_v);
+    return awegpu_eval_objective_host(h, 1, arg[0], arg[1], AWEGPU_P_SHARED, jac ? &fval : out, jac ? out : h->scratch_v.data(),
+                                      nullptr);
+}
+static const long long *sp_f_in(long long i, bool jac)
+{
+    awegpu_handle *h = casadi_handle(-1);
+    if (!h) return nullptr;
+    if (h->sp_pf.empty()) dense_sp(h->sp_pf, h->mpc_obj ? h->mpc_n_p : h->dp.n_p);
+    if (h->sp_one.empty()) dense_sp(h->sp_one, 1);
+    return i == 0 ? h->sp_v.data() : i == 1 ? h->sp_pf.data() : (jac && i == 2) ? h->sp_one.data() : nullptr;
+}
+extern "C" int awegpu_f(const double **arg, double **res, long long *, double *, int mem) { return casadi_eval_f(arg, res, false, mem); }
+extern "C" long long awegpu_f_n_in(void) { return 2; }
+extern "C" long long awegpu_f_n_out(void) { return 1; }
+extern "C" const char *awegpu_f_name_in(long long i) { return i == 0 ? "V" : i == 1 ? "P" : nullptr; }
+extern "C" const char *awegpu_f_name_out(long long i) { return i == 0 ? "f" : nullptr; }
+extern "C" const long long *awegpu_f_sparsity_in(long long i) { return sp_f_in(i, false); }
+extern "C" const long long *awegpu_f_sparsity_out(long long i)
+{
+    awegpu_handle *h = casadi_handle(-1);
+    if (!h || i != 0) return nullptr;
+    if (h->sp_one.empty()) dense_sp(h->sp_one, 1);
+    return h->sp_one.data();
+}
+extern "C" int awegpu_f_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w)
+{
+    if (sz_arg) *sz_arg = 2;
+    if (sz_res) *sz_res = 1;
+    if (sz_iw) *sz_iw = 0;
+    if (sz_w) *sz_w = 0;
+    return 0;
+}
+extern "C" int jac_awegpu_f(const double **arg, double **res, long long *, double *, int mem) { return casadi_eval_f(arg, res, true, mem); }
+extern "C" long long jac_awegpu_f_n_in(void) { return 3; }
+extern "C" long long jac_awegpu_f_n_out(void) { return 2; }
+extern "C" const char *jac_awegpu_f_name_in(long long i) { return i == 0 ? "V" : i == 1 ? "P" : i == 2 ? "out_f" : nullptr; }
+extern "C" const char *jac_awegpu_f_name_out(long long i) { return i == 0 ? "jac_f_V" : i == 1 ? "jac_f_P" : nullptr; }
+extern "C" const long long *jac_awegpu_f_sparsity_in(long long i) { return sp_f_in(i, true); }
+extern "C" const long long *jac_awegpu_f_sparsity_out(long long i)
+{
+    awegpu_handle *h = casadi_handle(-1);
+    if (!h) return nullptr;
+    if (h->sp_jfv.empty()) {
+        // 1 x n_v dense in compact CCS: [nrow, ncol, colind[ncol + 1], row[nnz]]
+        const long long n = h->dp.n_v;
+        h->sp_jfv.assign(2 + (size_t)n + 1 + (size_t)n, 0);
+        h->sp_jfv[0] = 1, h->sp_jfv[1] = n;
+        for (long long c = 0; c <= n; ++c) h->sp_jfv[2 + c] = c;
+        const long long np_ = h->mpc_obj ? h->mpc_n_p : h->dp.n_p;
+        h->sp_jfp.assign(2 + (size_t)np_ + 1, 0);      // 1 x n_p, no non-zeros (not a source of parametric sensitivities)
+        h->sp_jfp[0] = 1, h->sp_jfp[1] = np_;
+    }
+    return i == 0 ? h->sp_jfv.data() : i == 1 ? h->sp_jfp.data() : nullptr;
+}
+extern "C" int jac_awegpu_f_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w)
+{
+    if (sz_arg) *sz_arg = 3;
+    if (sz_res) *sz_res = 2;
+    if (sz_iw) *sz_iw = 0;
+    if (sz_w) *sz_w = 0;
+    return 0;
+}
+
+// outputs map as a CasADi external: Outputs_fun = external('awegpu_outputs', lib) (awebox/ocp/nlp.py:335-336): inputs V, P;
+// output the dense n_out x n_nodes matrix in CasADi's column-major non-zero order (node after node), rows in the order
+// of awegpu_outputs_label
+CASADI_MEM_FUNCS(awegpu_outputs)
+extern "C" int awegpu_outputs(const double **arg, double **res, long long *, double *, int mem)
+{
+    awegpu_handle *h = casadi_handle(mem);
+    if (!h) return 1;
+    if (!arg || !arg[0] || !arg[1]) {
+        set_err(h, "awegpu_outputs: V and P must be given");
+        return 1;
+    }
+    double *out = res ? res[0] : nullptr;
+    if (!out) return 0;
+    std::lock_guard<std::mutex> lock(h->casadi_mu);
+    const size_t n_out = (size_t)awe_out_n(), n_nodes = (size_t)h->dp.n_k * (N_D + 1);
+    h->scratch_o.resize(n_out * n_nodes);
+    const int rc = awegpu_eval_outputs_host(h, 1, arg[0], arg[1], AWEGPU_P_SHARED, h->scratch_o.data());
+    if (rc) return rc;
+    for (size_t n = 0; n < n_nodes; ++n)
+        for (size_t i = 0; i < n_out; ++i) out[n * n_out + i] = h->scratch_o[i * n_nodes + n];
+    return 0;
+}
+extern "C" long long awegpu_outputs_n_in(void) { return 2; }
+extern "C" long long awegpu_outputs_n_out(void) { return 1; }
+extern "C" const char *awegpu_outputs_name_in(long long i) { return i == 0 ? "V" : i == 1 ? "P" : nullptr; }
+extern "C" const char *awegpu_outputs_name_out(long long i) { return i == 0 ? "outputs" : nullptr; }
+extern "C" const long long *awegpu_outputs_sparsity_in(long long i)
+{
+    awegpu_handle *h = casadi_handle(-1);
+    if (!h) return nullptr;
+    return i == 0 ? h->sp_v.data() : i == 1 ? h->sp_p.data() : nullptr;
+}
+extern "C" const long long *awegpu_outputs_sparsity_out(long long i)
+{
+    awegpu_handle *h = casadi_handle(-1);
+    if (!h || i != 0) return nullptr;
+    h->sp_out = {(long long)awe_out_n(), (long long)h->dp.n_k * (N_D + 1), 1};      // compact dense flag
+    return h->sp_out.data();
+}
+extern "C" int awegpu_outputs_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w)
+{
+    if (sz_arg) *sz_arg = 2;
     if (sz_res) *sz_res = 1;
     if (sz_iw) *sz_iw = 0;
     if (sz_w) *sz_w = 0;

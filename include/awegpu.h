@@ -303,6 +303,60 @@ const long long *awegpu_hess_lag_sparsity_in(long long i);
 const long long *awegpu_hess_lag_sparsity_out(long long i);
 int awegpu_hess_lag_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w);
 
+/* objective as CasADi externals (replace NLP.f_fun, awebox/ocp/nlp.py:119-121, 142): casadi.external('awegpu_f', lib) with
+ * inputs (V, P) and the scalar output f; casadi.external finds its Jacobian function jac_awegpu_f in the same library
+ * (inputs V, P, out_f; outputs jac_f_V dense 1 x n_v, jac_f_P structurally empty).  Power-cycle trials: P is the full
+ * parameter vector; mpc trials: Pmpc's own parameter vector (awebox/pmpc.py:152-162). */
+int  awegpu_f_checkout(void);
+void awegpu_f_release(int mem);
+void awegpu_f_incref(void);
+void awegpu_f_decref(void);
+int  awegpu_f_alloc_mem(void);
+int  awegpu_f_init_mem(int mem);
+void awegpu_f_free_mem(int mem);
+int awegpu_f(const double **arg, double **res, long long *iw, double *w, int mem);
+long long awegpu_f_n_in(void);
+long long awegpu_f_n_out(void);
+const char *awegpu_f_name_in(long long i);
+const char *awegpu_f_name_out(long long i);
+const long long *awegpu_f_sparsity_in(long long i);
+const long long *awegpu_f_sparsity_out(long long i);
+int awegpu_f_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w);
+
+int  jac_awegpu_f_checkout(void);
+void jac_awegpu_f_release(int mem);
+void jac_awegpu_f_incref(void);
+void jac_awegpu_f_decref(void);
+int  jac_awegpu_f_alloc_mem(void);
+int  jac_awegpu_f_init_mem(int mem);
+void jac_awegpu_f_free_mem(int mem);
+int jac_awegpu_f(const double **arg, double **res, long long *iw, double *w, int mem);
+long long jac_awegpu_f_n_in(void);
+long long jac_awegpu_f_n_out(void);
+const char *jac_awegpu_f_name_in(long long i);
+const char *jac_awegpu_f_name_out(long long i);
+const long long *jac_awegpu_f_sparsity_in(long long i);
+const long long *jac_awegpu_f_sparsity_out(long long i);
+int jac_awegpu_f_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w);
+
+/* outputs map as a CasADi external (replaces NLP.Outputs_fun, awebox/ocp/nlp.py:335-336): inputs (V, P), output the dense
+ * n_out x n_nodes matrix in CasADi's column-major non-zero order; rows in the order of awegpu_outputs_label. */
+int  awegpu_outputs_checkout(void);
+void awegpu_outputs_release(int mem);
+void awegpu_outputs_incref(void);
+void awegpu_outputs_decref(void);
+int  awegpu_outputs_alloc_mem(void);
+int  awegpu_outputs_init_mem(int mem);
+void awegpu_outputs_free_mem(int mem);
+int awegpu_outputs(const double **arg, double **res, long long *iw, double *w, int mem);
+long long awegpu_outputs_n_in(void);
+long long awegpu_outputs_n_out(void);
+const char *awegpu_outputs_name_in(long long i);
+const char *awegpu_outputs_name_out(long long i);
+const long long *awegpu_outputs_sparsity_in(long long i);
+const long long *awegpu_outputs_sparsity_out(long long i);
+int awegpu_outputs_work(long long *sz_arg, long long *sz_res, long long *sz_iw, long long *sz_w);
+
 #ifdef __cplusplus
 }
 #endif

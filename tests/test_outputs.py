@@ -226,3 +226,61 @@ def test_tether_moment_kat():
     dcm = np.array(si[('x', 'r10')]).reshape(3, 3).T                  # column-major reshape, as cas.reshape
     true = si[('z', 'lambda10')][0] * np.cross(r_tether, dcm.T @ np.array(si[('x', 'q10')]))
     assert np.linalg.norm(true - found) / np.linalg.norm(true) < 1e-8
+
+
+@pytest.mark.gpu
+def test_casadi_externals_for_objective_and_outputs():
+    """the symbols casadi.external('awegpu_f', lib) / ('awegpu_outputs', lib) bind, called with CasADi's conventions:
+    f(V, P) and jac_awegpu_f(V, P, out_f) -> (jac_f_V dense 1 x n_v, jac_f_P empty) against the golden vectors of the
+    reference's f_fun; Outputs_fun(V, P) -> dense n_out x n_nodes in column-major non-zero order against the batched
+    entry"""
+    import ctypes as C
+    from awebox_b200.evaluator import Evaluator
+    ev = Evaluator('ampyx_ap2', n_k=4)
+    lib, ocp = ev.lib, ev.ocp
+    assert lib.awegpu_casadi_bind(ev.handle) == 0
+    PD, PLL = C.POINTER(C.c_double), C.POINTER(C.c_longlong)
+    for f in (lib.awegpu_f_n_in, lib.awegpu_f_n_out, lib.jac_awegpu_f_n_in, lib.jac_awegpu_f_n_out, lib.awegpu_outputs_n_in,
+              lib.awegpu_outputs_n_out):
+        f.restype = C.c_longlong
+    assert (lib.awegpu_f_n_in(), lib.awegpu_f_n_out(), lib.jac_awegpu_f_n_in(), lib.jac_awegpu_f_n_out()) == (2, 1, 3, 2)
+    assert (lib.awegpu_outputs_n_in(), lib.awegpu_outputs_n_out()) == (2, 1)
+    for f in (lib.awegpu_f_sparsity_in, lib.awegpu_f_sparsity_out, lib.jac_awegpu_f_sparsity_out, lib.awegpu_outputs_sparsity_out,
+              lib.jac_awegpu_f_sparsity_in):
+        f.restype, f.argtypes = PLL, [C.c_longlong]
+    sp = lib.awegpu_f_sparsity_in(1)
+    assert (sp[0], sp[1], sp[2]) == (ocp.n_p, 1, 1)
+    sp = lib.awegpu_f_sparsity_out(0)
+    assert (sp[0], sp[1], sp[2]) == (1, 1, 1)
+    sp = lib.jac_awegpu_f_sparsity_out(0)
+    assert (sp[0], sp[1]) == (1, ocp.n_v) and sp[2 + ocp.n_v] == ocp.n_v and sp[2 + ocp.n_v + 1 + 5] == 0
+    sp = lib.jac_awegpu_f_sparsity_out(1)
+    assert (sp[0], sp[1]) == (1, ocp.n_p) and sp[2 + ocp.n_p] == 0
+    sp = lib.jac_awegpu_f_sparsity_in(2)
+    assert (sp[0], sp[1], sp[2]) == (1, 1, 1)
+    n_out, n_nodes = len(ev.outputs_labels()), ocp.n_k * (ocp.d + 1)
+    sp = lib.awegpu_outputs_sparsity_out(0)
+    assert (sp[0], sp[1], sp[2]) == (n_out, n_nodes, 1)
+    sig = [C.POINTER(PD), C.POINTER(PD), PLL, PD, C.c_int]
+    lib.awegpu_f.argtypes = lib.jac_awegpu_f.argtypes = lib.awegpu_outputs.argtypes = sig
+    gold = np.load(os.path.join(GOLDEN, 'ampyx_ap2_nk4_obj.npz'))
+    w, p = np.ascontiguousarray(gold['w'][1]), np.ascontiguousarray(gold['p'])
+    fv = np.empty(1)
+    arg = (PD * 3)(w.ctypes.data_as(PD), p.ctypes.data_as(PD), fv.ctypes.data_as(PD))
+    res = (PD * 2)(fv.ctypes.data_as(PD), None)
+    assert lib.awegpu_f(arg, res, None, None, 0) == 0
+    assert abs(fv[0] - gold['f'][1]) <= 1e-11 * abs(gold['f'][1])
+    gr = np.empty(ocp.n_v)
+    res = (PD * 2)(gr.ctypes.data_as(PD), None)
+    assert lib.jac_awegpu_f(arg, res, None, None, 0) == 0
+    g_ref = gold['grad'][1]
+    assert np.all(np.abs(gr - g_ref) <= np.maximum(1e-11 * np.abs(g_ref), 1e-13 * max(1.0, float(np.max(np.abs(g_ref))))))
+    go = np.load(os.path.join(GOLDEN, 'ampyx_ap2_nk4_out.npz'))
+    w, p = np.ascontiguousarray(go['w'][1]), np.ascontiguousarray(go['p'])
+    nz = np.empty(n_out * n_nodes)
+    arg = (PD * 2)(w.ctypes.data_as(PD), p.ctypes.data_as(PD))
+    res = (PD * 1)(nz.ctypes.data_as(PD))
+    assert lib.awegpu_outputs(arg, res, None, None, 0) == 0
+    assert np.array_equal(nz.reshape(n_nodes, n_out).T, ev.outputs_fun(w, p))       # column-major non-zeros
+    arg0 = (PD * 2)(None, p.ctypes.data_as(PD))
+    assert lib.awegpu_outputs(arg0, res, None, None, 0) != 0
