@@ -153,6 +153,19 @@ def cpu_leg(ocp, n_threads, budget_s, W, P, flags):
     return done * ocp.n_k * ocp.d / dt, dt, done, n_threads
 
 
+def workload_config(name, ocp, B, B_total, p_mode, world, workload, n_k):
+    """the `config` object of the bench line: identical for the GPU arm and the reference arm of one command"""
+    p_bytes = 8 * (ocp.n_theta0 if p_mode != 'full' else ocp.n_p)
+    step_bytes = B * (8 * (ocp.n_v + ocp.n_g + ocp.nnz) + (p_bytes if p_mode != 'shared' else 0))
+    return {'workload': workload, 'baseline_config': name, 'n_k': n_k, 'd': ocp.d,
+            'instances_per_gpu': B, 'instances_total': B_total, 'n_v': ocp.n_v,
+            'n_g': ocp.n_g, 'nnz': int(ocp.nnz), 'jac_layout': 'instance-major CCS values',
+            'parameters': {'shared': 'one parameter vector for the batch', 'theta0': 'per-instance theta0 [B, n_theta0]',
+                           'full': 'per-instance parameter vectors [B, n_p]'}[p_mode],
+            'l2': 'inputs+outputs per step (%.2f GB per GPU) exceed the 126 MB L2; no flush needed' % (step_bytes / 1e9),
+            'parallelism': 'batch sharded over %d GPU(s), no data-path collective' % world}
+
+
 def run_reference(args, json_out):
     """--impl reference: the CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get('RANK', '0'))
@@ -160,8 +173,14 @@ def run_reference(args, json_out):
         return
     from awebox_b200.spec import ModelSpec
     from awebox_b200.ocp.nlp import OcpProblem
-    spec, n_k, _, _, scaling, workload = CONFIGS[args.config]
+    spec, n_k, per_gpu, p_mode, scaling, workload = CONFIGS[args.config]
     ocp = OcpProblem(ModelSpec.load(spec), n_k=n_k)
+    world = max(1, int(args.gpus))
+    if per_gpu is None and not args.batch:
+        B_cfg, B_total_cfg = -(-MPC_SCENARIOS // world), MPC_SCENARIOS       # strong scaling: rank 0's share
+    else:
+        B_cfg = args.batch or per_gpu
+        B_total_cfg = B_cfg * world
     W, P, flags = make_inputs(args.config, ocp, 256, 0)
     threads = os.cpu_count()
     per_step = max(1.0, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
@@ -178,7 +197,7 @@ def run_reference(args, json_out):
         'impl': 'reference', 'metric': 'collocation-node g+Jacobian evals/s', 'value': value, 'unit': 'node-evals/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * secs / max(1, args.steps),
         'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': workload, 'n_k': n_k, 'd': ocp.d, 'n_v': ocp.n_v, 'n_g': ocp.n_g, 'nnz': int(ocp.nnz)},
+        'config': workload_config(args.config, ocp, B_cfg, B_total_cfg, p_mode, world, workload, n_k),
         'cpu_baseline': {'value': value, 'unit': 'node-evals/s', 'cores': threads, 'kind': 'port', 'sample': sample,
                          'note': 'plain-C port of the path (gcc -O2, OpenMP over instances); CasADi 3.6.4 itself is '
                                  'not installable on this box'},
@@ -597,15 +616,9 @@ def main():
             'metric': 'collocation-node g+Jacobian evals/s', 'value': value, 'unit': 'node-evals/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps,
             'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload, 'baseline_config': args.config, 'n_k': n_k, 'd': ocp.d,
-                       'instances_per_gpu': B, 'instances_total': B_total, 'n_v': ocp.n_v,
-                       'n_g': ocp.n_g, 'nnz': int(ocp.nnz), 'jac_layout': 'instance-major CCS values',
-                       'parameters': {'shared': 'one parameter vector for the batch', 'theta0': 'per-instance theta0 [B, n_theta0]',
-                                      'full': 'per-instance parameter vectors [B, n_p]'}[p_mode],
-                       'l2': 'inputs+outputs per step (%.2f GB per GPU) exceed the 126 MB L2; no flush needed' % (step_bytes / 1e9),
-                       'kernels_per_step': 'gather + %d collocation stages + %d shooting stages' % (
-                           sum(1 for g in info['groups_coll'] if g), sum(1 for g in info['groups_shoot'] if g)),
-                       'parallelism': 'batch sharded over %d GPU(s), no data-path collective' % world},
+            'config': workload_config(args.config, ocp, B, B_total, p_mode, world, workload, n_k),
+            'kernels_per_step': 'gather + %d collocation stages + %d shooting stages' % (
+                sum(1 for g in info['groups_coll'] if g), sum(1 for g in info['groups_shoot'] if g)),
             'clocks': sampler.summary(),
             'e2e': {'value': e2e_value, 'unit': 'node-evals/s',
                     'h2d_bytes_per_step': int(8 * (W.size + P.size)) * world,
