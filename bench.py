@@ -581,6 +581,24 @@ def main():
             for _ in range(200):
                 fn()
             lat[name] = (time.perf_counter() - t0) / 200 * 1e6
+        if p_mode == 'shared':
+            # the other functions of one IPOPT iteration / one post-processing pass, one instance per call
+            lam1 = np.random.default_rng(3).uniform(-1.0, 1.0, ocp.n_g)
+            more = [('outputs_fun', lambda: ev.outputs_fun(w1, ocp.default_p()))]
+            ev.hessian_setup()
+            p_h1 = ocp.default_p()
+            if ev.hess_objective:
+                p_h1[:ocp.n_v] = w1
+                p_h1[ocp.n_v:ocp.p_theta0] = 1.0
+                more.append(('f_and_grad_f', lambda: ev.eval_objective(w1[None, :], p_h1)))
+            more.append(('hess_lag_fun', lambda: ev.hess_lag_fun(w1, p_h1, 1.0, lam1)))
+            for name, fn in more:
+                for _ in range(5):
+                    fn()
+                t0 = time.perf_counter()
+                for _ in range(50):
+                    fn()
+                lat[name] = (time.perf_counter() - t0) / 50 * 1e6
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -634,6 +652,8 @@ def main():
                             'reduce_kernel': 'awegpu_reduce_kernel, all five products (J^T lambda, J v, row / column max-norms, '
                                              'max|g|) with per-instance lambda and v: one pass over the jac_g values'},
             'latency_b1_us': {'g_fun': lat.get('g_fun'), 'jac_g_fun': lat.get('jac_g_fun'),
+                              'f_and_grad_f': lat.get('f_and_grad_f'), 'hess_lag_fun': lat.get('hess_lag_fun'),
+                              'outputs_fun': lat.get('outputs_fun'),
                               'what': 'one OCP instance per call through Evaluator.g_fun / jac_g_fun (host numpy in and out), '
                                       'mean of 200 calls; the CPU port needs cpu_port_us on one core',
                               'cpu_port_us': (time.perf_counter() - t_one) * 1e6 / 2},
