@@ -342,7 +342,7 @@ HESSF_JOBS = {'ampyx_ap2': [(4, 3), (40, 2)], 'dual_kites': [(3, 2), (20, 2)]}
 
 HESS_JOBS = {'ampyx_ap2': [(4, 3), (40, 2)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 3)]}
 
-OUT_JOBS = {'ampyx_ap2': [(4, 3), (40, 2)], 'dual_kites': [(3, 2), (20, 2)], 'mpc_3dof': [(3, 3), (10, 2)]}
+OUT_JOBS = {'ampyx_ap2': [(4, 3), (40, 5)], 'dual_kites': [(3, 2), (20, 5)], 'mpc_3dof': [(3, 3), (10, 5)]}
 
 
 def run_outputs(config, n_k, n_pts):
