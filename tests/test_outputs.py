@@ -8,9 +8,9 @@ present.
 CPU: the expressions of awebox_b200/mdl/outputs.py evaluated by the host restatement (OutputsMap.evaluate).
 GPU: awegpu_eval_outputs through the C ABI against the golden vectors, against the host restatement on seeded batches
 (ragged sizes, parameter modes, device entry) and, at BASELINE sizes, against properties: the 'model_equalities' rows of
-the collocation nodes are the collocation rows of g, airspeed = |air_velocity|, xdot of the shooting nodes is V[xdot].
+the collocation nodes are the collocation rows of g, the inequalities of the shooting nodes its path rows, airspeed = |air_velocity|, xdot of the shooting nodes is V[xdot].
 
-Tolerance: |a - b| <= 1e-9 max(|ref|, S_name, 1e-6 S_group), S_name = largest |ref| over the nodes and components of the
+Tolerance: |a - b| <= 1e-10 max(|ref|, S_name, 1e-6 S_group), S_name = largest |ref| over the nodes and components of the
 same name, S_group the same over the group: relative to the entry, with a floor for entries that are cancellation
 noise at the test points (d c / d t at a consistent point, the side force of the 3-DOF kite, the Frenet centre
 velocity = difference of 20 m/s terms); at the unperturbed initial guess (point 0) an absolute 1e-10 is added."""
@@ -46,7 +46,7 @@ def tolerance(labels, ref, consistent_point=False):
         s_name[n] = max(s_name.get(n, 0.0), v)
         s_group[g] = max(s_group.get(g, 0.0), v)
     floor = np.array([max(s_name[n], 1e-6 * s_group[g]) for n, g in zip(names, groups)])
-    return 1e-9 * np.maximum(np.abs(ref), floor[:, None]) + (1e-10 if consistent_point else 0.0)
+    return 1e-10 * np.maximum(np.abs(ref), floor[:, None]) + (1e-10 if consistent_point else 0.0)
 
 
 def by_label(gold, labels, pt):
@@ -110,7 +110,7 @@ def test_gpu_outputs_against_reference(name, n_k):
         one = ev.outputs_fun(gold['w'][pt], gold['p'])
         assert np.array_equal(one, out[pt])
     print('%s n_k=%d: %d outputs x %d nodes, %d points: largest error / tolerance %.2e at the perturbed points '
-          '(tolerance = 1e-9 of the scale), %.2e at the unperturbed initial guess (with the absolute 1e-10)'
+          '(tolerance = 1e-10 of the scale), %.2e at the unperturbed initial guess (with the absolute 1e-10)'
           % (name, n_k, len(labels), out.shape[2], gold['w'].shape[0], worst[False], worst[True]))
 
 
@@ -175,6 +175,15 @@ def test_gpu_outputs_properties_at_baseline_sizes(name, n_k, B):
             o_rows = out[:, eq, node] * scale
             tol = 1e-10 * np.maximum(1.0, np.max(np.abs(g_rows), axis=0, keepdims=True))
             assert np.all(np.abs(g_rows - o_rows) <= tol)
+    # ... and the path inequalities of the shooting nodes are the path rows of g (zoh controls: constraints.py:261-268)
+    iq = ev.outputs_index('model_inequalities')
+    assert len(iq) == ocp.n_ineq
+    for k in (0, n_k // 2, n_k - 1):
+        r0 = int(ocp.row_path[k])
+        g_rows = G[:, r0:r0 + ocp.n_ineq]
+        o_rows = out[:, iq, k * (d + 1)] * scale
+        tol = 1e-10 * np.maximum(1.0, np.max(np.abs(g_rows), axis=0, keepdims=True))
+        assert np.all(np.abs(g_rows - o_rows) <= tol)
     for kite in ocp.model.arch.kite_nodes:
         va = out[:, ev.outputs_index('aerodynamics', 'air_velocity%d' % kite), :]
         sp = out[:, ev.outputs_index('aerodynamics', 'airspeed%d' % kite)[0], :]
