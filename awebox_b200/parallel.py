@@ -21,7 +21,11 @@ def shard_sizes(B, world):
 
 
 def gather_results(local, B, group=None):
-    """all-gather per-rank result blocks ``local [b_r, n]`` into ``[B, n]`` on every rank."""
+    """all-gather per-rank result blocks ``local [b_r, n]`` into ``[B, n]`` on every rank (trailing dimensions of any
+    rank, e.g. the outputs map ``[b_r, n_out, n_nodes]``, are carried along)."""
+    if local.dim() != 2:
+        tail = tuple(local.shape[1:])
+        return gather_results(local.reshape(local.shape[0], -1), B, group).reshape((B,) + tail)
     world = dist.get_world_size(group)
     sizes = shard_sizes(B, world)
     n = local.shape[1]
@@ -40,6 +44,10 @@ def gather_results(local, B, group=None):
 def gather_to_root(local, B, root=0, group=None):
     """gather the per-rank blocks ``local [b_r, n]`` on ``root`` only -> ``[B, n]`` there, None elsewhere (the
     "NCCL over NVLink only to gather per-shard results" step of BASELINE.json: north_star)."""
+    if local.dim() != 2:
+        tail = tuple(local.shape[1:])
+        out = gather_to_root(local.reshape(local.shape[0], -1), B, root, group)
+        return None if out is None else out.reshape((B,) + tail)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     sizes = shard_sizes(B, world)

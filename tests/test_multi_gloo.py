@@ -86,3 +86,44 @@ def test_power_curve_parameters_are_sharded_consistently():
 def test_two_ranks_mpc_scenarios(tmp_path):
     """BASELINE configs[4]: scenario batch with per-instance parameter vectors, both W and P sharded."""
     _run(9, tmp_path, spec='mpc_3dof', n_k=3)
+
+
+def _worker_outputs(rank, world, port, B, out):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from awebox_b200.parallel import shard_range, gather_results, gather_to_root
+    from awebox_b200.ocp.outputs import OutputsMap
+    from awebox_b200 import synthetic
+    from conftest import get_ocp
+    ocp = get_ocp('mpc_3dof', 3)
+    om = OutputsMap(ocp)
+    W = synthetic.batch(ocp, B, seed=9)
+    lo, hi = shard_range(B, rank, world)
+    local = np.array([om.evaluate(W[b], ocp.default_p()).T for b in range(lo, hi)])       # [b_r, n_out, n_nodes]
+    both = gather_results(torch.from_numpy(local), B)
+    root = gather_to_root(torch.from_numpy(local), B)
+    assert (root is None) == (rank != 0)
+    if rank == 0:
+        assert torch.equal(root, both)
+        np.save(out, both.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_outputs_map_sharded_and_gathered(tmp_path):
+    """the outputs map of a ragged batch sharded over two ranks (3-dimensional result blocks): gather on every rank and
+    on the root alone (the host restatement stands in for the kernel)"""
+    from awebox_b200.ocp.outputs import OutputsMap
+    from awebox_b200 import synthetic
+    from conftest import get_ocp
+    B = 5
+    out = str(tmp_path / 'gather_outputs.npy')
+    port = 29500 + (os.getpid() + 977) % 2000
+    mp.spawn(_worker_outputs, args=(2, port, B, out), nprocs=2, join=True)
+    ocp = get_ocp('mpc_3dof', 3)
+    om = OutputsMap(ocp)
+    W = synthetic.batch(ocp, B, seed=9)
+    ref = np.array([om.evaluate(W[b], ocp.default_p()).T for b in range(B)])
+    assert np.array_equal(np.load(out), ref)
