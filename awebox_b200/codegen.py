@@ -81,8 +81,9 @@ def _rhs(op, a, b):
 
 # per-model overrides of the parameters above, chosen by measurement on B200 (the planner's outcome is not monotone in
 # its budget: scripts/build_variants.py + scripts/gpu_variants.sh): mpc_3dof 0.81 ms per 8192-scenario step with the
-# default group budget, 0.66 ms with 1400
-TUNED = {'mpc_3dof': {'GROUP_OPS': 1400}}
+# default group budget, 0.66 ms with 1400; dual_kites 8.05 / 7.91 / 7.70 / 7.49 / 11.2 ms per 4096-instance step with 700 / 900 /
+# 1200 / 1600 / 2200
+TUNED = {'mpc_3dof': {'GROUP_OPS': 1400}, 'dual_kites': {'GROUP_OPS': 1600}}
 
 
 class NodeCode(object):

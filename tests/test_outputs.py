@@ -33,7 +33,7 @@ def outputs_map(name, n_k):
     return _MAP[(name, n_k)]
 
 
-def tolerance(labels, ref, consistent_point=False):
+def tolerance(labels, ref, consistent_point=False, rtol=1e-10):
     """ref [n_out, n_nodes] in the order of ``labels`` -> tolerance of the same shape.  ``consistent_point``: the
     unperturbed initial guess, where whole outputs (d c / d t, xdot - x') vanish up to the rounding of their operands:
     an absolute 1e-10 is added there (xdot of the collocation polynomial is a sum of terms 100 times larger than its value,
@@ -46,7 +46,7 @@ def tolerance(labels, ref, consistent_point=False):
         s_name[n] = max(s_name.get(n, 0.0), v)
         s_group[g] = max(s_group.get(g, 0.0), v)
     floor = np.array([max(s_name[n], 1e-6 * s_group[g]) for n, g in zip(names, groups)])
-    return 1e-10 * np.maximum(np.abs(ref), floor[:, None]) + (1e-10 if consistent_point else 0.0)
+    return rtol * np.maximum(np.abs(ref), floor[:, None]) + (1e-10 if consistent_point else 0.0)
 
 
 def by_label(gold, labels, pt):
@@ -134,10 +134,12 @@ def test_gpu_outputs_batch_against_host_restatement(name, n_k, B):
     assert np.array_equal(out_full, out_th0)
     out_shared = ev.eval_outputs(W, p0)
     for b in (0, B // 2, B - 1):
+        # synthetic points are not trajectories: outputs that vanish on one (lift of the 3-DOF kite at zero roll rate ...)
+        # are differences of large terms here, hence 1e-9 of the scale
         ref = om.evaluate(W[b], P[b]).T
-        assert np.all(np.abs(out_full[b] - ref) <= tolerance(om.labels, ref))
+        assert np.all(np.abs(out_full[b] - ref) <= tolerance(om.labels, ref, rtol=1e-9))
         ref = om.evaluate(W[b], p0).T
-        assert np.all(np.abs(out_shared[b] - ref) <= tolerance(om.labels, ref))
+        assert np.all(np.abs(out_shared[b] - ref) <= tolerance(om.labels, ref, rtol=1e-9))
     dev = torch.device('cuda:0')
     Wd, Pd = torch.from_numpy(W).to(dev), torch.from_numpy(P).to(dev)
     Od = torch.empty(out_full.shape, dtype=torch.float64, device=dev)
