@@ -51,6 +51,7 @@ GROUP_OPS = 900      # weight budget of one program group (~27 KB of SASS; the L
 _GROUP_OPS_DEFAULT = GROUP_OPS    # (an experiment that changes GROUP_OPS overrides the per-model table below)
 GROUP_OPS_SHOOT = 0  # > 0: separate budget for the shooting-node programs
 MAX_EXPORTS = 64     # intermediate values exported per stage (scaled up for large models, see NodeCode.plan)
+EXPORTS_PER_OPS = 40  # large models: one export per this many operations of the function (see NodeCode.plan)
 MAX_EXPORTS_SHOOT = 0 # > 0: the same for the shooting-node function (0: as MAX_EXPORTS)
 EXPORT_MIN_GAIN = 40
 EXPORT_LOAD_COST = 4
@@ -283,7 +284,7 @@ class NodeCode(object):
         if max_exports is None:
             # measured on B200 (AP2): 64 exports per stage beat both fewer (recomputation) and more (side-buffer
             # traffic); a model several times larger needs proportionally more to keep the group count down
-            max_exports = max(MAX_EXPORTS, n_ops // 40) if n_ops > 8000 else MAX_EXPORTS
+            max_exports = max(MAX_EXPORTS, n_ops // EXPORTS_PER_OPS) if n_ops > 8000 else MAX_EXPORTS
         pos = {n.idx: i for i, n in enumerate(order)}
         wgt = np.array([OP_WEIGHT.get(n.op, 1) for n in order], dtype=np.float32)
         nb = (n_ops + 7) // 8
