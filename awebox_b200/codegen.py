@@ -52,6 +52,8 @@ _GROUP_OPS_DEFAULT = GROUP_OPS    # (an experiment that changes GROUP_OPS overri
 GROUP_OPS_SHOOT = 0  # > 0: separate budget for the shooting-node programs
 MAX_EXPORTS = 64     # intermediate values exported per stage (scaled up for large models, see NodeCode.plan)
 EXPORTS_PER_OPS = 40  # large models: one export per this many operations of the function (see NodeCode.plan)
+_EXPORTS_PER_OPS_DEFAULT = EXPORTS_PER_OPS
+_exports_per_ops = [EXPORTS_PER_OPS]     # value in force for the model being generated (per-model table below)
 MAX_EXPORTS_SHOOT = 0 # > 0: the same for the shooting-node function (0: as MAX_EXPORTS)
 EXPORT_MIN_GAIN = 40
 EXPORT_LOAD_COST = 4
@@ -83,14 +85,17 @@ def _rhs(op, a, b):
 # per-model overrides of the parameters above, chosen by measurement on B200 (the planner's outcome is not monotone in
 # its budget: scripts/build_variants.py + scripts/gpu_variants.sh): mpc_3dof 0.81 ms per 8192-scenario step with the
 # default group budget, 0.66 ms with 1400; dual_kites 8.05 / 7.91 / 7.70 / 7.49 / 11.2 ms per 4096-instance step with 700 / 900 /
-# 1200 / 1600 / 2200
-TUNED = {'mpc_3dof': {'GROUP_OPS': 1400}, 'dual_kites': {'GROUP_OPS': 1600}}
+# 1200 / 1600 / 2200; with one export per 60 instead of 40 operations (328 instead of 449 exports per node) 6.89 ms
+TUNED = {'mpc_3dof': {'GROUP_OPS': 1400}, 'dual_kites': {'GROUP_OPS': 1600, 'EXPORTS_PER_OPS': 60}}
 
 
 class NodeCode(object):
     def __init__(self, ocp):
         self.ocp = ocp
         self.group_ops = TUNED.get(ocp.spec.name, {}).get('GROUP_OPS')
+        # an experiment that changes EXPORTS_PER_OPS overrides the per-model table (as for GROUP_OPS)
+        _exports_per_ops[0] = (TUNED.get(ocp.spec.name, {}).get('EXPORTS_PER_OPS', EXPORTS_PER_OPS)
+                               if EXPORTS_PER_OPS == _EXPORTS_PER_OPS_DEFAULT else EXPORTS_PER_OPS)
         self.group_ops_shoot = TUNED.get(ocp.spec.name, {}).get('GROUP_OPS_SHOOT')
         m = ocp.model
         d = ocp.d
@@ -284,7 +289,7 @@ class NodeCode(object):
         if max_exports is None:
             # measured on B200 (AP2): 64 exports per stage beat both fewer (recomputation) and more (side-buffer
             # traffic); a model several times larger needs proportionally more to keep the group count down
-            max_exports = max(MAX_EXPORTS, n_ops // EXPORTS_PER_OPS) if n_ops > 8000 else MAX_EXPORTS
+            max_exports = max(MAX_EXPORTS, n_ops // _exports_per_ops[0]) if n_ops > 8000 else MAX_EXPORTS
         pos = {n.idx: i for i, n in enumerate(order)}
         wgt = np.array([OP_WEIGHT.get(n.op, 1) for n in order], dtype=np.float32)
         nb = (n_ops + 7) // 8
